@@ -1,0 +1,365 @@
+"""CPU oracle for the DIR hot path (FDS / LDS / weighted losses / calibration).
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product path
+(`imbalanced-regression_b200/`) may import this module; only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference`
+legs do, and only as the checker / the timed CPU baseline.
+
+Each function is an independent numpy restatement of the reference algorithm
+(YyzHarry/imbalanced-regression @ a6fdc45) and cites the reference lines it
+follows.  The restatement is pinned against the reference itself: the
+fixtures in `tests/golden/*.npz` were produced by importing the reference's
+own modules from `/root/reference` (see `tests/golden/make_golden.py`) and
+`tests/test_oracle_golden.py` checks this file against them.  The reference
+ships no tests / golden vectors of its own, so this is the
+strongest pin available.
+"""
+from __future__ import annotations
+
+import math
+import numpy as np
+
+
+# --------------------------------------------------------------------------
+# kernel windows
+# --------------------------------------------------------------------------
+def _gaussian_impulse_response(ks: int, sigma: float, dtype) -> np.ndarray:
+    """scipy.ndimage.gaussian_filter1d applied to a centred unit impulse of
+    length ks, default mode='reflect', truncate=4.0 -- restated without scipy.
+
+    The filter radius is int(4*sigma+0.5); taps that fall outside the ks-long
+    signal are folded back by (half-sample symmetric) reflection, which is why
+    the FDS / LDS windows are not plain sampled Gaussians.
+    (agedb-dir/fds.py:41-44, agedb-dir/utils.py:113-115)
+    """
+    half = (ks - 1) // 2
+    radius = int(4.0 * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1, dtype=np.float64)
+    phi = np.exp(-0.5 / (float(sigma) * float(sigma)) * x ** 2)
+    phi = phi / phi.sum()
+    sig = np.zeros(ks, dtype=np.float64)
+    sig[half] = 1.0
+    out = np.zeros(ks, dtype=np.float64)
+    period = 2 * ks
+    for i in range(ks):
+        acc = 0.0
+        for j in range(-radius, radius + 1):
+            # correlate1d with a symmetric kernel; index i+j reflected
+            # ("reflect" == half-sample symmetric: d c b a | a b c d | d c b a)
+            k = (i + j) % period
+            if k < 0:
+                k += period
+            if k >= ks:
+                k = period - 1 - k
+            acc += phi[j + radius] * sig[k]
+        out[i] = acc
+    return out.astype(dtype)
+
+
+def fds_kernel_window(kernel: str, ks: int, sigma: float) -> np.ndarray:
+    """FDS smoothing window, float32, normalised to sum 1.
+    (agedb-dir/fds.py:37-52)"""
+    assert kernel in ("gaussian", "triang", "laplace")
+    half = (ks - 1) // 2
+    if kernel == "gaussian":
+        g = _gaussian_impulse_response(ks, sigma, np.float32)
+        w = g / sum(g)
+    elif kernel == "triang":
+        t = triang_window(ks)
+        w = t / sum(t)
+    else:
+        lap = [math.exp(-abs(x) / sigma) / (2.0 * sigma) for x in range(-half, half + 1)]
+        w = np.asarray(lap) / sum(lap)
+    return np.asarray(w, dtype=np.float32)
+
+
+def lds_kernel_window(kernel: str, ks: int, sigma: float) -> np.ndarray:
+    """LDS window, float64, normalised to max 1.  (agedb-dir/utils.py:110-122)"""
+    assert kernel in ("gaussian", "triang", "laplace")
+    half = (ks - 1) // 2
+    if kernel == "gaussian":
+        g = _gaussian_impulse_response(ks, sigma, np.float64)
+        w = g / max(g)
+    elif kernel == "triang":
+        w = triang_window(ks)
+    else:
+        lap = [math.exp(-abs(x) / sigma) / (2.0 * sigma) for x in range(-half, half + 1)]
+        w = np.asarray(lap) / max(lap)
+    return np.asarray(w, dtype=np.float64)
+
+
+def triang_window(m: int) -> np.ndarray:
+    """scipy.signal.windows.triang(M) (symmetric) restated."""
+    n = np.arange(1, (m + 1) // 2 + 1, dtype=np.float64)
+    if m % 2 == 0:
+        w = (2 * n - 1.0) / m
+        return np.concatenate([w, w[::-1]])
+    w = 2 * n / (m + 1.0)
+    return np.concatenate([w, w[-2::-1]])
+
+
+# --------------------------------------------------------------------------
+# LDS weights
+# --------------------------------------------------------------------------
+def lds_histogram(labels, max_target: int = 121) -> np.ndarray:
+    """bin = min(max_target-1, int(label)); int64 counts.
+    (agedb-dir/datasets.py:60-63)"""
+    hist = np.zeros(max_target, dtype=np.int64)
+    for v in np.asarray(labels).reshape(-1):
+        hist[min(max_target - 1, int(v))] += 1
+    return hist
+
+
+def convolve1d_constant(x: np.ndarray, w: np.ndarray) -> np.ndarray:
+    """scipy.ndimage.convolve1d(x, w, mode='constant') for an odd-length
+    SYMMETRIC w, restated with scipy's own accumulation order (its symmetric
+    fast path: centre tap first, then (x[i-j] + x[i+j]) * w[j] from the outermost
+    pair inwards, float64, no fused multiply-add) and its output-dtype rule:
+    the result takes the INPUT's dtype, so an integer histogram (the
+    'inverse' re-weighting, np.clip of Python ints) is truncated back to
+    int64, while the sqrt_inv histogram stays float64.
+    (agedb-dir/datasets.py:66-67, 76-77)"""
+    x = np.asarray(x)
+    xd = x.astype(np.float64)
+    w = np.asarray(w, dtype=np.float64)
+    h = len(w) // 2
+    assert len(w) % 2 == 1 and np.all(np.abs(w - w[::-1]) <= np.finfo(np.float64).eps)
+    n = len(xd)
+    pad = np.concatenate([np.zeros(h), xd, np.zeros(h)])
+    out = np.zeros(n, dtype=np.float64)
+    for i in range(n):
+        c = i + h
+        acc = pad[c] * w[h]
+        for j in range(-h, 0):
+            acc = acc + (pad[c + j] + pad[c - j]) * w[h + j]
+        out[i] = acc
+    if np.issubdtype(x.dtype, np.integer):
+        return np.trunc(out).astype(np.int64)
+    return out
+
+
+def lds_weights(labels, reweight: str, max_target: int = 121, lds: bool = False,
+                lds_kernel: str = "gaussian", lds_ks: int = 5, lds_sigma: float = 2):
+    """Per-sample loss weights.  (agedb-dir/datasets.py:55-83)
+    Returns (hist int64[max_target], weights float32[N]) or (hist, None)."""
+    assert reweight in ("none", "inverse", "sqrt_inv")
+    assert reweight != "none" if lds else True
+    labels = np.asarray(labels).reshape(-1)
+    hist = lds_histogram(labels, max_target)
+    if reweight == "none" or labels.size == 0:
+        return hist, None
+    if reweight == "sqrt_inv":
+        val = np.sqrt(hist.astype(np.float64))
+    else:
+        val = np.clip(hist, 5, 1000)                   # stays int64 (see convolve1d_constant)
+    if lds:
+        val = convolve1d_constant(val, lds_kernel_window(lds_kernel, lds_ks, lds_sigma))
+    bins = np.minimum(max_target - 1, labels.astype(np.int64))
+    w = (1.0 / val[bins]).astype(np.float32)          # np.float32(1 / x)  :80
+    scaling = np.float32(len(w)) / np.sum(w)           # float32 pairwise sum :81
+    return hist, (np.float32(scaling) * w).astype(np.float32)
+
+
+# --------------------------------------------------------------------------
+# FDS
+# --------------------------------------------------------------------------
+def fds_bin_index(labels, bucket_num: int, bucket_start: int) -> np.ndarray:
+    """Row -> FDS table row, reproducing the unique-label loop's three masks
+    (agedb-dir/fds.py:91-99, 120-143).  -1 == row not touched.
+    Out-of-range labels fold into an edge bin only when the edge value itself
+    occurs among the labels.  Contract: integer-valued labels."""
+    lab = np.asarray(labels, dtype=np.float32).reshape(-1)
+    lo, hi = np.float32(bucket_start), np.float32(bucket_num - 1)
+    has_lo = bool((lab == lo).any())
+    has_hi = bool((lab == hi).any())
+    out = np.full(lab.shape, -1, dtype=np.int32)
+    inr = (lab >= lo) & (lab <= hi)
+    out[inr] = (lab[inr] - lo).astype(np.int32)
+    if has_lo:
+        out[lab < lo] = 0
+    if has_hi:
+        out[lab > hi] = int(bucket_num - 1 - bucket_start)
+    return out
+
+
+def fds_batch_stats(features, labels, bucket_num, bucket_start):
+    """Per-bin (count, mean, unbiased var [0 when n==1]) in float64 -> float32.
+    (agedb-dir/fds.py:100-102)"""
+    f = np.asarray(features, dtype=np.float64)
+    bins = fds_bin_index(labels, bucket_num, bucket_start)
+    nb = bucket_num - bucket_start
+    cnt = np.zeros(nb, dtype=np.int64)
+    mean = np.zeros((nb, f.shape[1]), dtype=np.float32)
+    var = np.zeros((nb, f.shape[1]), dtype=np.float32)
+    for b in range(nb):
+        rows = f[bins == b]
+        n = rows.shape[0]
+        cnt[b] = n
+        if n == 0:
+            continue
+        mean[b] = rows.mean(0)
+        var[b] = rows.var(0, ddof=1) if n > 1 else 0.0
+    return cnt, mean, var
+
+
+class FDSState:
+    """Numpy restatement of fds.FDS's buffers and state machine
+    (agedb-dir/fds.py:16-35, 54-113), including the by-reference alias of
+    `running_*_last_epoch` onto `running_*` (:55-56)."""
+
+    def __init__(self, feature_dim, bucket_num=100, bucket_start=3, start_update=0,
+                 start_smooth=1, kernel="gaussian", ks=5, sigma=2, momentum=0.9):
+        nb = bucket_num - bucket_start
+        self.feature_dim, self.bucket_num, self.bucket_start = feature_dim, bucket_num, bucket_start
+        self.window = fds_kernel_window(kernel, ks, sigma)
+        self.half_ks = (ks - 1) // 2
+        self.momentum, self.start_update, self.start_smooth = momentum, start_update, start_smooth
+        self.epoch = int(start_update)
+        self.running_mean = np.zeros((nb, feature_dim), np.float32)
+        self.running_var = np.ones((nb, feature_dim), np.float32)
+        self.running_mean_last_epoch = np.zeros((nb, feature_dim), np.float32)
+        self.running_var_last_epoch = np.ones((nb, feature_dim), np.float32)
+        self.smoothed_mean_last_epoch = np.zeros((nb, feature_dim), np.float32)
+        self.smoothed_var_last_epoch = np.ones((nb, feature_dim), np.float32)
+        self.num_samples_tracked = np.zeros(nb, np.float32)
+
+    def update_last_epoch_stats(self, epoch):                     # fds.py:78-82
+        if epoch == self.epoch + 1:
+            self.epoch += 1
+            self.running_mean_last_epoch = self.running_mean      # alias  :55
+            self.running_var_last_epoch = self.running_var        # alias  :56
+            self.smoothed_mean_last_epoch = smooth_bins(self.running_mean, self.window)
+            self.smoothed_var_last_epoch = smooth_bins(self.running_var, self.window)
+
+    def update_running_stats(self, features, labels, epoch):      # fds.py:84-113
+        if epoch < self.epoch:
+            return
+        cnt, mean, var = fds_batch_stats(features, labels, self.bucket_num, self.bucket_start)
+        for b in np.nonzero(cnt)[0]:
+            n = float(cnt[b])
+            self.num_samples_tracked[b] += np.float32(n)
+            factor = self.momentum if self.momentum is not None else \
+                (1 - n / float(self.num_samples_tracked[b]))
+            factor = 0 if epoch == self.start_update else factor
+            a = np.float32(1 - factor)
+            f = np.float32(factor)
+            self.running_mean[b] = a * mean[b] + f * self.running_mean[b]
+            self.running_var[b] = a * var[b] + f * self.running_var[b]
+
+    def smooth(self, features, labels, epoch, clip=(0.1, 10.0)):  # fds.py:115-144
+        if epoch < self.start_smooth:
+            return features
+        return fds_calibrate(features, np.asarray(labels).reshape(-1), self.bucket_num,
+                             self.bucket_start, self.running_mean_last_epoch,
+                             self.running_var_last_epoch, self.smoothed_mean_last_epoch,
+                             self.smoothed_var_last_epoch, clip)
+
+
+def smooth_bins(table: np.ndarray, window: np.ndarray) -> np.ndarray:
+    """Reflect-pad by half_ks along the bin axis, then ks-tap correlation.
+    (agedb-dir/fds.py:58-67; F.pad mode='reflect' excludes the edge sample.)"""
+    t = np.asarray(table, dtype=np.float32)
+    nb = t.shape[0]
+    ks = len(window)
+    h = (ks - 1) // 2
+    out = np.zeros_like(t)
+    for b in range(nb):
+        acc = np.zeros(t.shape[1], dtype=np.float32)
+        for j in range(ks):
+            k = b + j - h
+            if k < 0:
+                k = -k
+            if k >= nb:
+                k = 2 * (nb - 1) - k
+            acc = acc + np.float32(window[j]) * t[k]
+        out[b] = acc
+    return out
+
+
+def calibrate_mean_var(matrix, m1, v1, m2, v2, clip_min=0.1, clip_max=10.0):
+    """(agedb-dir/utils.py:97-107) float32, same operation order."""
+    x = np.asarray(matrix, dtype=np.float32)
+    m1, v1, m2, v2 = (np.asarray(a, dtype=np.float32) for a in (m1, v1, m2, v2))
+    if np.sum(v1, dtype=np.float32) < 1e-10:
+        return x
+    valid = v1 != 0
+    out = x.copy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        fac = np.clip(v2[valid] / v1[valid], np.float32(clip_min), np.float32(clip_max))
+    out[:, valid] = (x[:, valid] - m1[valid]) * np.sqrt(fac) + m2[valid]
+    return out
+
+
+def fds_calibrate(features, labels, bucket_num, bucket_start, m1, v1, m2, v2, clip=(0.1, 10.0)):
+    x = np.array(features, dtype=np.float32, copy=True)
+    bins = fds_bin_index(labels, bucket_num, bucket_start)
+    for b in np.unique(bins):
+        if b < 0:
+            continue
+        rows = bins == b
+        x[rows] = calibrate_mean_var(x[rows], m1[b], v1[b], m2[b], v2[b], clip[0], clip[1])
+    return x
+
+
+def fds_calibrate_scale(labels, bucket_num, bucket_start, v1, v2, clip=(0.1, 10.0)):
+    """d(out)/d(in) of fds_calibrate per element (backward oracle)."""
+    bins = fds_bin_index(labels, bucket_num, bucket_start)
+    d = v1.shape[1]
+    s = np.ones((len(bins), d), dtype=np.float32)
+    for i, b in enumerate(bins):
+        if b < 0 or np.sum(v1[b], dtype=np.float32) < 1e-10:
+            continue
+        valid = v1[b] != 0
+        with np.errstate(divide="ignore", invalid="ignore"):
+            fac = np.clip(v2[b][valid] / v1[b][valid], np.float32(clip[0]), np.float32(clip[1]))
+        s[i, valid] = np.sqrt(fac)
+    return s
+
+
+# --------------------------------------------------------------------------
+# weighted losses  (agedb-dir/loss.py:5-48) -- forward and d/d(inputs)
+# --------------------------------------------------------------------------
+def _sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def weighted_loss(kind, inputs, targets, weights=None, activate="sigmoid", beta=None, gamma=1.0):
+    """Returns (loss float32 scalar, dloss/dinputs float32).  float64 inside."""
+    x = np.asarray(inputs, dtype=np.float64)
+    t = np.asarray(targets, dtype=np.float64)
+    d = x - t
+    a = np.abs(d)
+    sg = np.sign(d)
+    n = d.size
+    if kind == "mse":
+        l, g = d * d, 2 * d
+    elif kind == "l1":
+        l, g = a, sg
+    elif kind in ("focal_mse", "focal_l1"):
+        beta = 0.2 if beta is None else beta
+        if activate == "tanh":
+            fb = np.tanh(beta * a)
+            dfb = beta * (1 - fb * fb)
+        else:
+            s = _sigmoid(beta * a)
+            fb = 2 * s - 1
+            dfb = 2 * beta * s * (1 - s)
+        f = fb ** gamma
+        df = (gamma * np.where(gamma == 1.0, 1.0, fb ** (gamma - 1.0))) * dfb  # d f / d a
+        if kind == "focal_mse":
+            l = d * d * f
+            g = 2 * d * f + d * d * df * sg
+        else:
+            l = a * f
+            g = sg * f + a * df * sg
+    elif kind == "huber":
+        beta = 1.0 if beta is None else beta
+        small = a < beta
+        l = np.where(small, 0.5 * a * a / beta, a - 0.5 * beta)
+        g = np.where(small, d / beta, sg)
+    else:
+        raise ValueError(kind)
+    if weights is not None:
+        w = np.broadcast_to(np.asarray(weights, dtype=np.float64), d.shape)
+        l, g = l * w, g * w
+    return np.float32(l.mean()), (g / n).astype(np.float32)

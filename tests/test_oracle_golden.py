@@ -1,0 +1,112 @@
+"""The numpy oracle (oracle/dir_oracle.py) against fixtures produced by the
+reference's own code (tests/golden/make_golden.py).  CPU only."""
+import ast
+import numpy as np
+import pytest
+from util import golden, assert_close
+from oracle import dir_oracle as O
+
+
+def test_windows_match_reference():
+    g = golden("windows")
+    for key in g.files:
+        which, kernel, ks, sigma = key.split("_")
+        fn = O.fds_kernel_window if which == "fds" else O.lds_kernel_window
+        w = fn(kernel, int(ks), int(sigma))
+        assert w.dtype == g[key].dtype
+        assert_close(w, g[key], rtol=2e-7 if which == "fds" else 1e-14, atol=0, what=key)
+
+
+def test_survey_window_vectors():
+    # SURVEY.md §4 golden vectors (recorded from the reference at survey time)
+    assert_close(O.fds_kernel_window("gaussian", 5, 2),
+                 [0.18625069, 0.20524769, 0.21700326, 0.20524769, 0.18625069], rtol=1e-6)
+    assert_close(O.lds_kernel_window("gaussian", 5, 2),
+                 [0.858285238, 0.945827649, 1, 0.945827649, 0.858285238], rtol=1e-8)
+    assert_close(O.fds_kernel_window("laplace", 5, 2),
+                 [0.12475479, 0.20568587, 0.3391187, 0.20568587, 0.12475479], rtol=1e-6)
+    assert_close(O.lds_kernel_window("laplace", 9, 1)[:5],
+                 [0.018315639, 0.049787068, 0.135335283, 0.367879441, 1], rtol=1e-8)
+
+
+def test_lds_histogram_agedb_bit_exact():
+    g = golden("lds")
+    hist = O.lds_histogram(g["agedb_labels"])
+    assert hist.sum() == 12208 and hist.max() == 353 and int(np.argmax(hist)) == 35
+    assert list(hist[:30]) == [0, 1, 0, 4, 2, 2, 4, 5, 4, 2, 5, 8, 6, 8, 9, 15, 18, 28, 60, 50,
+                               101, 103, 123, 152, 199, 224, 215, 244, 287, 253]
+    assert (hist > 0).sum() == 100
+
+
+@pytest.mark.parametrize("tag", ["agedb", "imdb_wiki"])
+def test_lds_weights_match_reference(tag):
+    g = golden("lds")
+    labels = g[f"{tag}_labels"]
+    n = 0
+    for key in g.files:
+        if not key.startswith(f"{tag}_w_"):
+            continue
+        rest = key[len(tag) + 3:]
+        rw = "sqrt_inv" if rest.startswith("sqrt_inv") else "inverse"
+        lds_on, k, ks, sg = rest[len(rw) + 1:].split("_")
+        _, w = O.lds_weights(labels, rw, lds=bool(int(lds_on)), lds_kernel=k, lds_ks=int(ks), lds_sigma=int(sg))
+        assert_close(w, g[key], rtol=2e-6, atol=0, what=key)
+        assert abs(float(w.astype(np.float64).mean()) - 1) < 1e-5
+        n += 1
+    assert n >= 4
+
+
+def test_survey_agedb_weight_vectors():
+    g = golden("lds")
+    labels = g["agedb_labels"]
+    assert list(labels[:5]) == [31, 44, 34, 74, 62]
+    _, w = O.lds_weights(labels, "inverse", lds=True)
+    assert_close(w[:5], [0.46940538, 0.52160543, 0.43663308, 1.5401634, 0.8378155], rtol=2e-6)
+    _, w = O.lds_weights(labels, "sqrt_inv")
+    assert_close(w[:5], [0.81728405, 0.87962353, 0.7524706, 1.4806272, 0.98012847], rtol=2e-6)
+
+
+def test_calibrate_matches_reference():
+    g = golden("calibrate")
+    for tag in ("plain", "zeros", "allzero", "clip_hi", "clip_lo"):
+        y = O.calibrate_mean_var(g["x"], g["m1"], g[f"{tag}_v1"], g["m2"], g[f"{tag}_v2"])
+        assert_close(y, g[f"{tag}_y"], rtol=1e-6, atol=1e-6, what=tag)
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c", "d"])
+def test_fds_state_machine_matches_reference(name):
+    g = golden("fds")
+    bn, bs, ks, sg, mom, D, N = g[f"{name}_cfg"]
+    st = O.FDSState(int(D), int(bn), int(bs), 0, 1, str(g[f"{name}_kernel"]), int(ks), int(sg),
+                    None if mom < 0 else float(mom))
+    for ep in range(4):
+        sm = st.smooth(g[f"{name}_e{ep}_bx"], g[f"{name}_e{ep}_bl"], ep)
+        assert_close(sm, g[f"{name}_e{ep}_smooth"], rtol=1e-5, atol=1e-5, what=f"smooth e{ep}")
+        st.update_last_epoch_stats(ep)
+        st.update_running_stats(g[f"{name}_e{ep}_feats"], g[f"{name}_e{ep}_labels"], ep)
+        for k in ("running_mean", "running_var", "running_mean_last_epoch", "running_var_last_epoch",
+                  "smoothed_mean_last_epoch", "smoothed_var_last_epoch", "num_samples_tracked"):
+            assert_close(getattr(st, k), g[f"{name}_e{ep}_{k}"], rtol=1e-5, atol=1e-6, what=f"{k} e{ep}")
+        assert st.epoch == int(g[f"{name}_e{ep}_epoch"][0])
+
+
+def test_fds_bin_index_edge_rules():
+    # edge value present -> out-of-range labels fold; absent -> dropped (fds.py:92-99)
+    b = O.fds_bin_index([1, 3, 50, 99, 120], 100, 3)
+    assert list(b) == [0, 0, 47, 96, 96]
+    b = O.fds_bin_index([1, 4, 50, 98, 120], 100, 3)
+    assert list(b) == [-1, 1, 47, 95, -1]
+
+
+def test_losses_match_reference():
+    g = golden("loss")
+    i = 0
+    while f"case{i}_kind" in g.files:
+        kind = str(g[f"case{i}_kind"])
+        kw = ast.literal_eval(str(g[f"case{i}_kw"]))
+        for use_w in (0, 1):
+            l, gr = O.weighted_loss(kind, g["x"], g["t"], g["w"] if use_w else None, **kw)
+            assert_close(l, g[f"case{i}_w{use_w}_loss"], rtol=2e-6, what=f"{kind}{kw} loss")
+            assert_close(gr, g[f"case{i}_w{use_w}_grad"], rtol=2e-5, atol=1e-7, what=f"{kind}{kw} grad")
+        i += 1
+    assert i == 10
