@@ -1,0 +1,95 @@
+"""datasets.py -- mirror of agedb-dir/datasets.py / imdb-wiki-dir/datasets.py.
+
+The hot-path piece is `_prepare_weights` (datasets.py:55-83): the label
+histogram (int64, bit exact), the sqrt / clip re-weighting, the LDS
+convolution and the per-sample weight gather run in libdirb200
+(dirb200_lds_histogram / dirb200_lds_weights).  The image pipeline
+(PIL decode, crop, flip, normalise; datasets.py:27-53) is out of scope of the
+hot path and kept as thin torchvision host code.
+"""
+import logging
+import os
+
+import numpy as np
+import torch
+from torch.utils import data
+
+import _lib
+from utils import get_lds_kernel_window
+
+print = logging.info
+
+
+def lds_prepare_weights(labels, reweight, max_target=121, lds=False, lds_kernel='gaussian', lds_ks=5, lds_sigma=2,
+                        device=None, return_hist=False):
+    """GPU implementation of AgeDB._prepare_weights.  Returns a float32 CUDA
+    tensor [N] (or None for reweight == 'none'); with return_hist also the
+    int64 histogram.  Histograms all-reduce across ranks when labels are sharded."""
+    assert reweight in {'none', 'inverse', 'sqrt_inv'}
+    assert reweight != 'none' if lds else True, \
+        "Set reweight to 'sqrt_inv' (default) or 'inverse' when using LDS"
+    device = device or torch.device('cuda')
+    lab = torch.as_tensor(np.asarray(labels), dtype=torch.float32).reshape(-1).to(device).contiguous()
+    n = lab.numel()
+    hist = torch.zeros(max_target, dtype=torch.int64, device=device)
+    st = _lib.stream_ptr()
+    _lib.call("dirb200_lds_histogram", _lib.ptr(lab), n, max_target, _lib.ptr(hist), st)
+    if n == 0 or reweight == 'none':
+        return (None, hist) if return_hist else None
+    print(f"Using re-weighting: [{reweight.upper()}]")
+    window, ks = None, 0
+    if lds:
+        window = np.ascontiguousarray(get_lds_kernel_window(lds_kernel, lds_ks, lds_sigma), dtype=np.float64)
+        ks = len(window)
+        print(f'Using LDS: [{lds_kernel.upper()}] ({lds_ks}/{lds_sigma})')
+    scratch = torch.empty(2 * max_target + 2, dtype=torch.float64, device=device)
+    weights = torch.empty(n, dtype=torch.float32, device=device)
+    _lib.call("dirb200_lds_weights", _lib.ptr(lab), n, max_target, _lib.REWEIGHT[reweight],
+              None if window is None else window.ctypes.data_as(_lib.P), ks, _lib.ptr(hist), _lib.ptr(scratch),
+              _lib.ptr(weights), st)
+    return (weights, hist) if return_hist else weights
+
+
+class AgeDB(data.Dataset):
+    label_column = 'age'
+
+    def __init__(self, df, data_dir, img_size, split='train', reweight='none',
+                 lds=False, lds_kernel='gaussian', lds_ks=5, lds_sigma=2):
+        self.df = df
+        self.data_dir = data_dir
+        self.img_size = img_size
+        self.split = split
+        w = self._prepare_weights(reweight=reweight, lds=lds, lds_kernel=lds_kernel, lds_ks=lds_ks,
+                                  lds_sigma=lds_sigma)
+        self.weights = None if w is None else w.cpu().numpy()
+
+    def __len__(self):
+        return len(self.df)
+
+    def __getitem__(self, index):
+        from PIL import Image
+        index = index % len(self.df)
+        row = self.df.iloc[index]
+        img = Image.open(os.path.join(self.data_dir, row['path'])).convert('RGB')
+        img = self.get_transform()(img)
+        label = np.asarray([row[self.label_column]]).astype('float32')
+        weight = np.asarray([self.weights[index]]).astype('float32') if self.weights is not None else \
+            np.asarray([np.float32(1.)])
+        return img, label, weight
+
+    def get_transform(self):
+        from torchvision import transforms
+        norm = [transforms.ToTensor(), transforms.Normalize([.5, .5, .5], [.5, .5, .5])]
+        size = (self.img_size, self.img_size)
+        if self.split == 'train':
+            return transforms.Compose([transforms.Resize(size), transforms.RandomCrop(self.img_size, padding=16),
+                                       transforms.RandomHorizontalFlip()] + norm)
+        return transforms.Compose([transforms.Resize(size)] + norm)
+
+    def _prepare_weights(self, reweight, max_target=121, lds=False, lds_kernel='gaussian', lds_ks=5, lds_sigma=2):
+        return lds_prepare_weights(self.df[self.label_column].values, reweight, max_target, lds, lds_kernel,
+                                   lds_ks, lds_sigma)
+
+
+class IMDBWIKI(AgeDB):
+    pass

@@ -1,0 +1,144 @@
+/* dirb200.h -- C ABI of libdirb200.so: the B200-native (sm_100a) hot path of
+ * YyzHarry/imbalanced-regression (ResNet-50 + FDS + LDS training step).
+ *
+ * The reference has no FFI: its "plugin boundary" for this path is a set of
+ * Python callables.  Each entry point below names the
+ * reference function it replaces (file:line under /root/reference); the
+ * Python host mirrors in imbalanced-regression_b200/{fds,loss,utils,resnet,
+ * datasets}.py keep the reference's names/signatures and call these through
+ * ctypes.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer unless the name
+ *    ends in _host; the caller owns all memory, nothing is allocated here
+ *    except inside the opaque dirb200_net object;
+ *  - every function returns 0 on success, <0 on error (message via
+ *    dirb200_last_error(), thread local); nothing throws, nothing
+ *    synchronises the host, every launch goes to the cudaStream_t passed
+ *    (as void*; NULL = legacy default stream);
+ *  - there is NO CPU fallback: without a CUDA device every compute entry
+ *    point fails with DIRB200_ERR_CUDA.
+ */
+#ifndef DIRB200_H
+#define DIRB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIRB200_OK 0
+#define DIRB200_ERR_ARG (-1)
+#define DIRB200_ERR_CUDA (-2)
+#define DIRB200_ERR_WORKSPACE (-3)
+
+/* bin rules (row label -> FDS table row) */
+#define DIRB200_BIN_AGE 0 /* agedb-dir/fds.py:91-99 : int(label - bucket_start), edge folding */
+
+/* loss kinds (agedb-dir/loss.py) */
+#define DIRB200_LOSS_MSE 0       /* loss.py:5-10  */
+#define DIRB200_LOSS_L1 1        /* loss.py:13-18 */
+#define DIRB200_LOSS_FOCAL_MSE 2 /* loss.py:21-28 */
+#define DIRB200_LOSS_FOCAL_L1 3  /* loss.py:31-38 */
+#define DIRB200_LOSS_HUBER 4     /* loss.py:41-48 */
+#define DIRB200_ACT_SIGMOID 0
+#define DIRB200_ACT_TANH 1
+
+/* LDS re-weighting (agedb-dir/datasets.py:64-67) */
+#define DIRB200_REWEIGHT_SQRT_INV 1
+#define DIRB200_REWEIGHT_INVERSE 2
+
+const char* dirb200_last_error(void);
+int dirb200_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t dirb200_launch_count(void);
+
+/* ---------------------------------------------------------------- FDS ---- */
+
+/* Edge-label presence flags: flags[0] |= any(label == bucket_start),
+ * flags[1] |= any(label == bucket_num-1).  The caller zeroes flags (int32[2])
+ * and may OR-reduce them across ranks.  Replaces the `label == bucket_start`
+ * / `label == bucket_num-1` branches of the unique-label loop,
+ * agedb-dir/fds.py:94-97,124-137. */
+int dirb200_fds_label_flags(const float* labels, int64_t n, int bucket_num, int bucket_start,
+                            int bin_rule, int32_t* flags, void* stream);
+
+/* Row -> table row (int32, -1 = untouched), agedb-dir/fds.py:91-99. */
+int dirb200_fds_bin_rows(const float* labels, int64_t n, int bucket_num, int bucket_start,
+                         int bin_rule, const int32_t* flags, int32_t* bins_out, void* stream);
+
+/* Workspace for dirb200_fds_accumulate. */
+size_t dirb200_fds_accumulate_workspace_bytes(int64_t n, int nb);
+
+/* Segmented (per label bin) accumulation of sum / sum-of-squares in fp64 and
+ * row counts over features[n,d] (fp32 row-major, each element read exactly
+ * once).  ADDS into sums/sumsq [nb,d] (double) and counts [nb] (int64), so an
+ * epoch can be streamed batch by batch with no host round trip; the caller
+ * zeroes them at epoch start and may all-reduce(sum) them across ranks.
+ * Replaces the per-label mask/gather/mean/var loop, agedb-dir/fds.py:91-102,
+ * and the host round trip at agedb-dir/train.py:276-279. */
+int dirb200_fds_accumulate(const float* features, const int32_t* bins, int64_t n, int d, int nb,
+                           double* sums, double* sumsq, int64_t* counts,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* mean/var (unbiased; 0 when n==1) from the accumulators, then the running
+ * EMA update of every bin with count>0, agedb-dir/fds.py:100-111.
+ * momentum < 0 selects the `momentum is None` rule (factor = 1 - n/tracked);
+ * first_update != 0 forces factor 0 (epoch == start_update, fds.py:107). */
+int dirb200_fds_finalize(const double* sums, const double* sumsq, const int64_t* counts, int nb, int d,
+                         float* running_mean, float* running_var, float* num_samples_tracked,
+                         double momentum, int first_update, void* stream);
+
+/* dst[b,:] = sum_j window[j] * src[reflect(b + j - (ks-1)/2), :]; ks <= 33.
+ * Replaces F.pad(reflect)+F.conv1d, agedb-dir/fds.py:58-67. */
+int dirb200_fds_smooth_tables(const float* src, int nb, int d, const float* window_host, int ks,
+                              float* dst, void* stream);
+
+/* In-place whiten/re-colour of x[b,d] by label bin: FDS.smooth +
+ * calibrate_mean_var (agedb-dir/fds.py:115-144, agedb-dir/utils.py:97-107).
+ * Edge flags are evaluated on this batch's labels (as the reference does per
+ * call).  rowbin_out[b] (int32) = table row used, or -1 when the row was left
+ * untouched (label dropped, or sum(v1[row]) < 1e-10): the backward's input. */
+int dirb200_fds_calibrate_fwd(float* x, const float* labels, int64_t b, int d, int bucket_num,
+                              int bucket_start, int bin_rule, const float* m1, const float* v1,
+                              const float* m2, const float* v2, float clip_min, float clip_max,
+                              int32_t* rowbin_out, int32_t* flags_scratch /* int32[2]; may be NULL when b <= 2048 */,
+                              void* stream);
+
+/* grad_in[b,d] = grad_out[b,d] * d(calibrate)/dx (may alias). */
+int dirb200_fds_calibrate_bwd(const float* grad_out, const int32_t* rowbin, int64_t b, int d,
+                              const float* v1, const float* v2, float clip_min, float clip_max,
+                              float* grad_in, void* stream);
+
+/* ------------------------------------------------------------- losses ---- */
+
+size_t dirb200_loss_workspace_bytes(int64_t n);
+
+/* Fused forward + backward of weighted_{mse,l1,focal_mse,focal_l1,huber}_loss
+ * (agedb-dir/loss.py:5-48): loss_out[0] = mean(l_i * w_i); if grad_out != NULL,
+ * grad_out[i] = grad_scale * d loss / d pred_i.  weight may be NULL. */
+int dirb200_loss_fwd_bwd(int kind, const float* pred, const float* target, const float* weight, int64_t n,
+                         float beta, float gamma, int activate, float grad_scale,
+                         float* loss_out, float* grad_out, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* ---------------------------------------------------------------- LDS ---- */
+
+/* hist[min(max_target-1, int(label))]++ (int64, bit exact), ADDS into hist so
+ * it can be all-reduced when labels are sharded.  agedb-dir/datasets.py:60-63. */
+int dirb200_lds_histogram(const float* labels, int64_t n, int max_target, int64_t* hist, void* stream);
+
+/* hist -> per-bin value (sqrt / clip(5,1000), optional convolve1d(mode=constant)
+ * with the float64 window, integer truncation on the 'inverse' path as scipy
+ * does) -> per-sample float32 weight 1/value[bin] scaled to mean 1.
+ * scratch: >= (2*max_target + 2) doubles.  agedb-dir/datasets.py:64-82. */
+int dirb200_lds_weights(const float* labels, int64_t n, int max_target, int reweight,
+                        const double* window_host, int ks, const int64_t* hist,
+                        double* scratch, float* weights_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIRB200_H */

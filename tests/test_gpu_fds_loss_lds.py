@@ -1,0 +1,215 @@
+"""GPU parity: FDS / LDS / loss kernels (through the C ABI via the host mirrors)
+against the numpy oracle and the reference-generated golden fixtures.
+Tolerances: bins / histograms bit-exact; fp32 statistics and losses 1e-5 rel."""
+import ast
+import numpy as np
+import pytest
+import torch
+
+from util import golden, assert_close
+from oracle import dir_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def T(a, dtype=torch.float32):
+    return torch.as_tensor(np.asarray(a), dtype=dtype).to(DEV)
+
+
+# ------------------------------------------------------------------- FDS
+@pytest.mark.parametrize("name", ["a", "b", "c", "d"])
+def test_fds_state_machine_vs_reference_golden(name):
+    from fds import FDS
+    g = golden("fds")
+    bn, bs, ks, sg, mom, D, N = g[f"{name}_cfg"]
+    m = FDS(int(D), int(bn), int(bs), 0, 1, str(g[f"{name}_kernel"]), int(ks), int(sg),
+            None if mom < 0 else float(mom)).to(DEV)
+    for ep in range(4):
+        sm = m.smooth(T(g[f"{name}_e{ep}_bx"]), T(g[f"{name}_e{ep}_bl"]), ep)
+        assert_close(sm.cpu().numpy(), g[f"{name}_e{ep}_smooth"], rtol=1e-5, atol=1e-5, what=f"smooth e{ep}")
+        m.update_last_epoch_stats(ep)
+        m.update_running_stats(T(g[f"{name}_e{ep}_feats"]), T(g[f"{name}_e{ep}_labels"]), ep)
+        sd = m.state_dict()
+        for k in ("running_mean", "running_var", "running_mean_last_epoch", "running_var_last_epoch",
+                  "smoothed_mean_last_epoch", "smoothed_var_last_epoch", "num_samples_tracked", "epoch"):
+            assert_close(sd[k].cpu().numpy(), g[f"{name}_e{ep}_{k}"], rtol=1e-5, atol=1e-6, what=f"{k} e{ep}")
+
+
+def test_fds_state_dict_keys_and_alias():
+    from fds import FDS
+    m = FDS(8, 100, 3).to(DEV)
+    assert list(m.state_dict().keys()) == ['epoch', 'running_mean', 'running_var', 'running_mean_last_epoch',
+                                           'running_var_last_epoch', 'smoothed_mean_last_epoch',
+                                           'smoothed_var_last_epoch', 'num_samples_tracked']
+    assert m.running_mean.shape == (97, 8)
+    m.update_last_epoch_stats(1)
+    assert m.running_mean_last_epoch.data_ptr() == m.running_mean.data_ptr()   # fds.py:55 alias
+
+
+@pytest.mark.parametrize("bn,bs,n,d", [(100, 3, 1000, 2048), (101, 0, 256, 2048), (100, 0, 5000, 36), (50, 10, 77, 7)])
+def test_fds_bins_and_stats_vs_oracle(bn, bs, n, d):
+    import _lib
+    rng = np.random.RandomState(n + d)
+    labels = rng.randint(0, 130, size=n).astype(np.float32)
+    feats = np.maximum(rng.randn(n, d).astype(np.float32) * 0.7 + 3.0, 0)   # mean >> std
+    feats[:, d // 2] = 0
+    from fds import FDS
+    m = FDS(d, bn, bs, momentum=0.9).to(DEV)
+    m.begin_epoch_stats(T(labels))
+    # bins bit-exact
+    bins = torch.empty(n, dtype=torch.int32, device=DEV)
+    _lib.call("dirb200_fds_bin_rows", _lib.ptr(T(labels)), n, bn, bs, 0, _lib.ptr(m._acc["flags"]), _lib.ptr(bins),
+              _lib.stream_ptr())
+    assert np.array_equal(bins.cpu().numpy(), O.fds_bin_index(labels, bn, bs))
+    m.accumulate_batch(T(feats), T(labels))
+    cnt, mean, var = O.fds_batch_stats(feats, labels, bn, bs)
+    assert np.array_equal(m._acc["counts"].cpu().numpy(), cnt)
+    m.finish_epoch_stats(0)
+    has = cnt > 0
+    assert_close(m.running_mean.cpu().numpy()[has], mean[has], rtol=1e-5, atol=1e-7, what="mean")
+    assert_close(m.running_var.cpu().numpy()[has], var[has], rtol=1e-5, atol=1e-7, what="var")
+    assert (m.running_var.cpu().numpy()[~has] == 1).all() and (m.running_mean.cpu().numpy()[~has] == 0).all()
+    assert (m.running_var[:, d // 2].cpu().numpy()[has] == 0).all()       # dead channel -> exactly 0
+
+
+def test_fds_streamed_equals_one_shot_full_size():
+    """BASELINE config-2 size (N = 12 208 x 2048, 101 bins): streamed batches of
+    256 == one call; counts add up; constant column has zero variance."""
+    from fds import FDS
+    torch.manual_seed(0)
+    n, d = 12208, 2048
+    labels = torch.randint(0, 101, (n,), device=DEV).float()
+    feats = torch.relu(torch.randn(n, d, device=DEV) + 0.5)
+    feats[:, 5] = 2.5
+    a = FDS(d, 101, 0).to(DEV)
+    b = FDS(d, 101, 0).to(DEV)
+    a.update_running_stats(feats, labels, 0)
+    b.begin_epoch_stats(labels)
+    for i in range(0, n, 256):
+        b.accumulate_batch(feats[i:i + 256], labels[i:i + 256])
+    assert int(b._acc["counts"].sum()) == n
+    b.finish_epoch_stats(0)
+    assert_close(a.running_mean.cpu().numpy(), b.running_mean.cpu().numpy(), rtol=1e-6, atol=1e-7)
+    assert_close(a.running_var.cpu().numpy(), b.running_var.cpu().numpy(), rtol=1e-6, atol=1e-7)
+    assert float(a.running_var[:, 5].abs().max()) < 1e-6
+    # against torch on device (independent implementation), one bin
+    rows = feats[labels == 40]
+    assert_close(a.running_mean[40].cpu().numpy(), rows.mean(0).cpu().numpy(), rtol=1e-5, atol=1e-6)
+    assert_close(a.running_var[40].cpu().numpy(), rows.var(0, unbiased=True).cpu().numpy(), rtol=2e-5, atol=1e-6)
+
+
+def test_fds_calibrate_forward_backward_vs_oracle():
+    from fds import FDS
+    rng = np.random.RandomState(3)
+    d, bn, bs = 64, 100, 3
+    m = FDS(d, bn, bs).to(DEV)
+    nb = bn - bs
+    m1, m2 = rng.randn(nb, d).astype(np.float32), rng.randn(nb, d).astype(np.float32)
+    v1 = (rng.rand(nb, d).astype(np.float32) + 0.05)
+    v2 = (rng.rand(nb, d).astype(np.float32) * 4)
+    v1[:, 7] = 0                      # dead channel everywhere
+    v1[10] = 0                        # a whole row with sum(v1) < 1e-10 -> identity
+    v1[20, 3] = 1e-7                  # clamp at 10
+    v2[21, 4] = 1e-9                  # clamp at 0.1
+    m.running_mean_last_epoch, m.running_var_last_epoch = T(m1), T(v1)
+    m.smoothed_mean_last_epoch, m.smoothed_var_last_epoch = T(m2), T(v2)
+    labels = np.concatenate([np.arange(0, 120), [13, 23, 24, 24, 99, 3]]).astype(np.float32)
+    x = rng.randn(len(labels), d).astype(np.float32)
+    xt = T(x).requires_grad_(True)
+    y = m.smooth(xt * 1.0, T(labels).reshape(-1, 1), 5)
+    ref = O.fds_calibrate(x, labels, bn, bs, m1, v1, m2, v2)
+    assert_close(y.detach().cpu().numpy(), ref, rtol=1e-5, atol=1e-6, what="calibrate fwd")
+    gy = rng.randn(*x.shape).astype(np.float32)
+    y.backward(T(gy))
+    assert_close(xt.grad.cpu().numpy(), gy * O.fds_calibrate_scale(labels, bn, bs, v1, v2), rtol=1e-5, atol=1e-7,
+                 what="calibrate bwd")
+    # edge value absent from the batch -> out-of-range rows untouched
+    lab2 = np.array([1, 2, 50, 120], dtype=np.float32)
+    x2 = rng.randn(4, d).astype(np.float32)
+    y2 = m.smooth(T(x2), T(lab2).reshape(-1, 1), 5)
+    assert_close(y2.cpu().numpy(), O.fds_calibrate(x2, lab2, bn, bs, m1, v1, m2, v2), rtol=1e-5, atol=1e-6)
+    assert np.array_equal(y2.cpu().numpy()[[0, 1, 3]], x2[[0, 1, 3]])
+
+
+def test_calibrate_mean_var_function_vs_golden():
+    from utils import calibrate_mean_var
+    g = golden("calibrate")
+    for tag in ("plain", "zeros", "allzero", "clip_hi", "clip_lo"):
+        y = calibrate_mean_var(T(g["x"]), T(g["m1"]), T(g[f"{tag}_v1"]), T(g["m2"]), T(g[f"{tag}_v2"]))
+        assert_close(y.cpu().numpy(), g[f"{tag}_y"], rtol=1e-5, atol=1e-6, what=tag)
+
+
+def test_smooth_tables_vs_oracle():
+    from fds import FDS
+    rng = np.random.RandomState(5)
+    for kernel, ks, sg, nb in (("gaussian", 5, 2, 97), ("gaussian", 9, 1, 100), ("triang", 9, 1, 101), ("laplace", 3, 2, 5)):
+        m = FDS(2048, nb, 0, kernel=kernel, ks=ks, sigma=sg).to(DEV)
+        tab = rng.rand(nb, 2048).astype(np.float32)
+        out = m._smooth_table(T(tab))
+        assert_close(out.cpu().numpy(), O.smooth_bins(tab, O.fds_kernel_window(kernel, ks, sg)), rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ losses
+def test_losses_vs_reference_golden():
+    import loss as L
+    g = golden("loss")
+    i = 0
+    while f"case{i}_kind" in g.files:
+        kind = str(g[f"case{i}_kind"])
+        kw = ast.literal_eval(str(g[f"case{i}_kw"]))
+        for use_w in (0, 1):
+            x = T(g["x"]).requires_grad_(True)
+            l = getattr(L, f"weighted_{kind}_loss")(x, T(g["t"]), T(g["w"]) if use_w else None, **kw)
+            l.backward()
+            assert_close(l.item(), g[f"case{i}_w{use_w}_loss"], rtol=1e-5, what=f"{kind}{kw} loss")
+            assert_close(x.grad.cpu().numpy(), g[f"case{i}_w{use_w}_grad"], rtol=2e-5, atol=1e-7, what=f"{kind}{kw} grad")
+        i += 1
+    assert i == 10
+
+
+@pytest.mark.parametrize("n", [1, 256, 100003, 32 * 240 * 320])
+def test_loss_sizes_vs_oracle(n):
+    import loss as L
+    rng = np.random.RandomState(n % 1000)
+    x = (rng.randn(n, 1) * 5 + 30).astype(np.float32)
+    t = rng.randint(0, 100, size=(n, 1)).astype(np.float32)
+    w = (rng.rand(n, 1) + 0.5).astype(np.float32)
+    for kind in ("l1", "mse", "focal_l1", "huber"):
+        xt = T(x).requires_grad_(True)
+        l = getattr(L, f"weighted_{kind}_loss")(xt, T(t), T(w))
+        (l * 2).backward()
+        lo, go = O.weighted_loss(kind, x, t, w)
+        assert_close(l.item(), lo, rtol=1e-5)
+        assert_close(xt.grad.cpu().numpy(), 2 * go, rtol=2e-5, atol=1e-9 / max(1, n) ** 0)
+
+
+# --------------------------------------------------------------------- LDS
+@pytest.mark.parametrize("tag", ["agedb", "imdb_wiki"])
+def test_lds_weights_vs_reference_golden(tag):
+    from datasets import lds_prepare_weights
+    g = golden("lds")
+    labels = g[f"{tag}_labels"]
+    n = 0
+    for key in g.files:
+        if not key.startswith(f"{tag}_w_"):
+            continue
+        rest = key[len(tag) + 3:]
+        rw = "sqrt_inv" if rest.startswith("sqrt_inv") else "inverse"
+        lds_on, k, ks, sg = rest[len(rw) + 1:].split("_")
+        w, hist = lds_prepare_weights(labels, rw, lds=bool(int(lds_on)), lds_kernel=k, lds_ks=int(ks),
+                                      lds_sigma=int(sg), return_hist=True)
+        assert np.array_equal(hist.cpu().numpy(), O.lds_histogram(labels))         # bit exact
+        assert_close(w.cpu().numpy(), g[key], rtol=2e-6, atol=0, what=key)
+        n += 1
+    assert n >= 4
+
+
+def test_lds_histogram_clamps_and_accumulates():
+    import _lib
+    lab = T([0, 0.9, 1, 119.5, 120, 121, 186, 500])
+    hist = torch.zeros(121, dtype=torch.int64, device=DEV)
+    for _ in range(2):
+        _lib.call("dirb200_lds_histogram", _lib.ptr(lab), lab.numel(), 121, _lib.ptr(hist), _lib.stream_ptr())
+    h = hist.cpu().numpy()
+    assert h[0] == 4 and h[1] == 2 and h[119] == 2 and h[120] == 8 and h.sum() == 16
