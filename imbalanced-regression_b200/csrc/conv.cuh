@@ -1,0 +1,25 @@
+// Internal (C++) interface of the convolution stage shared by conv_igemm.cu, conv_api.cu and the network runner.
+#pragma once
+#include "common.cuh"
+
+namespace dirb200 {
+
+struct ConvShape {
+  int n, h, w, cin, cout, kh, kw, stride, pad, ho, wo;
+};
+
+int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, const ConvShape& s, bool stem,
+               cudaStream_t st);
+int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* dx, const ConvShape& s,
+               cudaStream_t st);
+int conv_wgrad_splits(const ConvShape& s);
+size_t conv_wgrad_workspace_bytes(const ConvShape& s);
+int conv_wgrad_partials(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* partial, const ConvShape& s, bool stem,
+                        int* splits_out, cudaStream_t st);
+int conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* workspace, const ConvShape& s,
+               bool stem, bool accumulate, cudaStream_t st);
+int prep_weights(const float* w, int cout, int cin, int kh, int kw, bool stem, __nv_bfloat16* wf, __nv_bfloat16* wd,
+                 cudaStream_t st);
+int input_to_s2d(const float* x, int n, int h, int w, __nv_bfloat16* out, cudaStream_t st);
+
+}  // namespace dirb200

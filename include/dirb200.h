@@ -138,6 +138,43 @@ int dirb200_lds_weights(const float* labels, int64_t n, int max_target, int rewe
                         const double* window_host, int ks, const int64_t* hist,
                         double* scratch, float* weights_out, void* stream);
 
+/* ------------------------------------------------- convolution stack ---- */
+/* Activations are NHWC bf16; weights arrive in the reference's fp32
+ * [Cout][Cin][KH][KW] layout (agedb-dir/resnet.py:46-51,79,112-118, i.e. the
+ * nn.Conv2d parameters / state_dict tensors) and are re-laid-out to bf16 GEMM
+ * operands by dirb200_conv_prep_weights.  The convolutions themselves are
+ * tcgen05 implicit GEMMs (fp32 accumulate in TMEM); they replace the cuDNN
+ * calls behind nn.Conv2d forward and its autograd backward.
+ * Cin and Cout must be multiples of 64, except the stem (stem=1: Cin=3, 7x7,
+ * stride 2, pad 3), which consumes the 16-channel space-to-depth input made
+ * by dirb200_input_to_s2d. */
+
+/* w fp32 [Cout][Cin][KH][KW] -> w_fprop bf16 [Cout][KH][KW][Cin] and (if not
+ * NULL) w_dgrad bf16 [Cin][KH][KW][Cout].  stem: w_fprop bf16 [Cout][256]. */
+int dirb200_conv_prep_weights(const float* w, int cout, int cin, int kh, int kw, int stem,
+                              void* w_fprop, void* w_dgrad, void* stream);
+
+/* x fp32 NCHW [n,3,h,w] (what ResNet.forward receives, resnet.py:127) ->
+ * bf16 [n, h/2, w/2, 16], channel (ph*2+pw)*4+c, c==3 zero. */
+int dirb200_input_to_s2d(const float* x_nchw, int n, int h, int w, void* out_bf16, void* stream);
+
+/* y[n,ho,wo,cout] = conv2d(x[n,h,w,cin], w)  (bias-free, as every conv in resnet.py) */
+int dirb200_conv_fprop(const void* x, const void* w_fprop, void* y, int n, int h, int w, int cin,
+                       int cout, int kh, int kw, int stride, int pad, int stem, void* stream);
+
+/* dx[n,h,w,cin] = d loss / d x given dy[n,ho,wo,cout] */
+int dirb200_conv_dgrad(const void* dy, const void* w_dgrad, void* dx, int n, int h, int w, int cin,
+                       int cout, int kh, int kw, int stride, int pad, void* stream);
+
+size_t dirb200_conv_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout, int kh, int kw,
+                                          int stride, int pad, int stem);
+
+/* dw fp32 [Cout][Cin][KH][KW] (=, or += when accumulate) d loss / d w from x and dy
+ * (split-K partials in `workspace`, then a deterministic reduce). */
+int dirb200_conv_wgrad(const void* x, const void* dy, float* dw, void* workspace, size_t workspace_bytes,
+                       int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad,
+                       int stem, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

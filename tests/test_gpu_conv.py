@@ -1,0 +1,125 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolutions (fprop / dgrad / wgrad)
+against torch fp32 conv on the same bf16-rounded operands.  Tolerance: the
+kernel accumulates in fp32 and rounds the result to bf16 once, so outputs must
+match the fp32 reference to bf16 precision (rel 2^-8 of the tensor scale);
+wgrad is fp32 end to end (1e-3 of scale for the long reductions)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def nhwc_bf16(t):      # NCHW fp32 -> NHWC bf16 contiguous
+    return t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def to_nchw_f32(t):
+    return t.float().permute(0, 3, 1, 2).contiguous()
+
+
+def run_conv(n, h, w, cin, cout, k, stride, pad, seed=0, check_dgrad=True):
+    import _lib, _convlib  # noqa: F401
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(n, cin, h, w, generator=g).to(DEV)
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+    xb = nhwc_bf16(x)
+    xr = to_nchw_f32(xb)                                  # bf16-rounded x as fp32 NCHW
+    wr = wt.to(torch.bfloat16).float()
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    st = _lib.stream_ptr()
+    wf = torch.empty(cout, k, k, cin, dtype=torch.bfloat16, device=DEV)
+    wd = torch.empty(cin, k, k, cout, dtype=torch.bfloat16, device=DEV)
+    _lib.call("dirb200_conv_prep_weights", _lib.ptr(wt), cout, cin, k, k, 0, _lib.ptr(wf), _lib.ptr(wd), st)
+    assert torch.equal(wf, wt.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+    assert torch.equal(wd, wt.permute(1, 2, 3, 0).contiguous().to(torch.bfloat16))
+    y = torch.full((n, ho, wo, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    shape = (n, h, w, cin, cout, k, k, stride, pad)
+    _lib.call("dirb200_conv_fprop", _lib.ptr(xb), _lib.ptr(wf), _lib.ptr(y), *shape, 0, st)
+    ref = F.conv2d(xr, wr, stride=stride, padding=pad)
+    err = (to_nchw_f32(y) - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2 ** -7 * scale + 1e-6, f"fprop err {err} scale {scale}"
+
+    dy = torch.randn(n, cout, ho, wo, generator=g).to(DEV)
+    dyb = nhwc_bf16(dy)
+    dyr = to_nchw_f32(dyb)
+    if check_dgrad:
+        dx = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
+        _lib.call("dirb200_conv_dgrad", _lib.ptr(dyb), _lib.ptr(wd), _lib.ptr(dx), *shape, st)
+        ref_dx = torch.nn.grad.conv2d_input(xr.shape, wr, dyr, stride=stride, padding=pad)
+        err = (to_nchw_f32(dx) - ref_dx).abs().max().item()
+        scale = ref_dx.abs().max().item()
+        assert err <= 2 ** -7 * scale + 1e-6, f"dgrad err {err} scale {scale}"
+
+    nbytes = _lib.raw("dirb200_conv_wgrad_workspace_bytes")(*shape, 0)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    dw = torch.full((cout, cin, k, k), float("nan"), dtype=torch.float32, device=DEV)
+    _lib.call("dirb200_conv_wgrad", _lib.ptr(xb), _lib.ptr(dyb), _lib.ptr(dw), _lib.ptr(ws), nbytes, *shape, 0, 0, st)
+    ref_dw = torch.nn.grad.conv2d_weight(xr, wr.shape, dyr, stride=stride, padding=pad)
+    err = (dw - ref_dw).abs().max().item()
+    scale = ref_dw.abs().max().item()
+    assert err <= 2e-3 * scale + 1e-5, f"wgrad err {err} scale {scale}"
+    # accumulate mode
+    _lib.call("dirb200_conv_wgrad", _lib.ptr(xb), _lib.ptr(dyb), _lib.ptr(dw), _lib.ptr(ws), nbytes, *shape, 0, 1, st)
+    assert (dw - 2 * ref_dw).abs().max().item() <= 4e-3 * scale + 1e-5
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("cfg", [
+    # n, h, w, cin, cout, k, stride, pad      (every distinct conv form of ResNet-50, small spatial sizes)
+    (2, 8, 8, 64, 64, 1, 1, 0),        # layer1 1x1
+    (2, 8, 8, 64, 256, 1, 1, 0),       # expand 1x1, BN=128 tiles x2
+    (2, 8, 8, 256, 64, 1, 1, 0),       # reduce 1x1, 4 k-blocks
+    (2, 8, 8, 64, 64, 3, 1, 1),        # layer1 3x3
+    (2, 8, 8, 128, 128, 3, 2, 1),      # strided 3x3
+    (2, 8, 8, 256, 512, 1, 2, 0),      # strided 1x1 downsample
+    (3, 7, 7, 512, 512, 3, 1, 1),      # ragged M (147 pixels), many k-blocks (72)
+    (1, 14, 14, 1024, 256, 1, 1, 0),   # 16 k-blocks > ring depth
+    (4, 7, 7, 512, 2048, 1, 1, 0),     # 16 n-tiles
+    (5, 9, 11, 64, 128, 3, 2, 1),      # odd sizes, non-square
+])
+def test_conv_forms(cfg):
+    run_conv(*cfg)
+
+
+def test_conv_layer1_full_batch_shape():
+    # a BASELINE-size layer: batch 32 of the 56x56x64 3x3 (M = 100 352 rows, 784 tiles)
+    run_conv(32, 56, 56, 64, 64, 3, 1, 1, seed=1)
+
+
+def test_stem_conv_and_s2d():
+    import _lib, _convlib  # noqa: F401
+    g = torch.Generator(device="cpu").manual_seed(3)
+    n, h, w, cout = 3, 32, 32, 64
+    x = torch.randn(n, 3, h, w, generator=g).to(DEV)
+    wt = (torch.randn(cout, 3, 7, 7, generator=g) / 147 ** 0.5).to(DEV)
+    st = _lib.stream_ptr()
+    xs = torch.empty(n, h // 2, w // 2, 16, dtype=torch.bfloat16, device=DEV)
+    _lib.call("dirb200_input_to_s2d", _lib.ptr(x), n, h, w, _lib.ptr(xs), st)
+    ref_s2d = torch.zeros(n, h // 2, w // 2, 16, device=DEV)
+    for ph in range(2):
+        for pw in range(2):
+            for c in range(3):
+                ref_s2d[..., (ph * 2 + pw) * 4 + c] = x[:, c, ph::2, pw::2]
+    assert torch.equal(xs, ref_s2d.to(torch.bfloat16))
+    wf = torch.empty(cout, 256, dtype=torch.bfloat16, device=DEV)
+    _lib.call("dirb200_conv_prep_weights", _lib.ptr(wt), cout, 3, 7, 7, 1, _lib.ptr(wf), None, st)
+    shape = (n, h, w, 3, cout, 7, 7, 2, 3)
+    y = torch.full((n, h // 2, w // 2, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    _lib.call("dirb200_conv_fprop", _lib.ptr(xs), _lib.ptr(wf), _lib.ptr(y), *shape, 1, st)
+    xr, wr = x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float()
+    ref = F.conv2d(xr, wr, stride=2, padding=3)
+    err = (to_nchw_f32(y) - ref).abs().max().item()
+    assert err <= 2 ** -7 * ref.abs().max().item() + 1e-6, err
+    dy = torch.randn(n, cout, h // 2, w // 2, generator=g).to(DEV)
+    dyb = nhwc_bf16(dy)
+    nbytes = _lib.raw("dirb200_conv_wgrad_workspace_bytes")(*shape, 1)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    dw = torch.full((cout, 3, 7, 7), float("nan"), dtype=torch.float32, device=DEV)
+    _lib.call("dirb200_conv_wgrad", _lib.ptr(xs), _lib.ptr(dyb), _lib.ptr(dw), _lib.ptr(ws), nbytes, *shape, 1, 0, st)
+    ref_dw = torch.nn.grad.conv2d_weight(xr, wr.shape, to_nchw_f32(dyb), stride=2, padding=3)
+    err = (dw - ref_dw).abs().max().item()
+    assert err <= 2e-3 * ref_dw.abs().max().item() + 1e-5, err
