@@ -1,0 +1,33 @@
+// Internal (C++) interface of the HBM-bound ResNet layers (nn_kernels.cu).
+#pragma once
+#include "common.cuh"
+
+namespace dirb200 {
+
+int bn_stats(const __nv_bfloat16* y, int64_t rows, int c, double* sum, double* sumsq, cudaStream_t st);
+int bn_finalize(double* sum, double* sumsq, int64_t rows, int c, const float* gamma, const float* beta, float eps,
+                float momentum, float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
+                float* shift, cudaStream_t st);
+int bn_eval_coeffs(int c, const float* gamma, const float* beta, float eps, const float* running_mean,
+                   const float* running_var, float* scale, float* shift, cudaStream_t st);
+int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, const __nv_bfloat16* res,
+             const __nv_bfloat16* res_y, const float* res_scale, const float* res_shift, bool relu, int64_t rows, int c,
+             __nv_bfloat16* out, cudaStream_t st);
+int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* act, const __nv_bfloat16* y,
+                  const float* mean, const float* invstd, const __nv_bfloat16* y2, const float* mean2,
+                  const float* invstd2, int64_t rows, int c, double* dbeta, double* dgamma, double* dgamma2,
+                  cudaStream_t st);
+int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* act, const __nv_bfloat16* y,
+                 const float* mean, const float* invstd, const float* gamma, const double* dbeta, const double* dgamma,
+                 const __nv_bfloat16* y2, const float* mean2, const float* invstd2, const float* gamma2,
+                 const double* dgamma2, int64_t rows, int c, __nv_bfloat16* dy, __nv_bfloat16* dy2,
+                 __nv_bfloat16* dz_out, cudaStream_t st);
+int bn_param_grads(double* dbeta, double* dgamma, int c, float* grad_gamma, float* grad_beta, bool zero_dbeta,
+                   cudaStream_t st);
+int maxpool_fwd(const __nv_bfloat16* x, int n, int h, int w, int c, __nv_bfloat16* out, uint8_t* idx, cudaStream_t st);
+int maxpool_bwd(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const uint8_t* idx, int n, int h, int w, int c,
+                __nv_bfloat16* dx, cudaStream_t st);
+int avgpool_fwd(const __nv_bfloat16* x, int n, int hw, int c, float* enc, cudaStream_t st);
+int avgpool_bwd(const float* genc, int n, int hw, int c, __nv_bfloat16* dx, cudaStream_t st);
+
+}  // namespace dirb200

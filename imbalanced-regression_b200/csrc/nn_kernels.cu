@@ -1,0 +1,629 @@
+// HBM-bound layers of the ResNet stack around the tcgen05 convolutions, NHWC bf16:
+// batch-norm (training statistics, apply(+residual)(+ReLU), backward), 3x3/2 max-pool,
+// global average pool, the 2048->1 regressor and the fused Adam / SGD step.
+// Replaces nn.BatchNorm2d / nn.ReLU / nn.MaxPool2d / nn.AvgPool2d / nn.Linear of
+// agedb-dir/resnet.py:41-70,79-88,127-148 and torch.optim of agedb-dir/train.py:163-164.
+#include "common.cuh"
+#include "nn.cuh"
+
+namespace dirb200 {
+
+struct V8 {
+  float v[8];
+};
+__device__ __forceinline__ V8 load8(const __nv_bfloat16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  V8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const V8& a) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(a.v[2 * i], a.v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ V8 loadf8(const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  return V8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+
+// Column (per-channel) reduction over the rows of [P][C]: thread owns channel group cg = tid % (C/8) and walks
+// rows; K partial sums per channel; partials of threads with the same cg are combined in smem, then one fp64
+// atomic per (channel, k) per CTA.
+template <int K>
+__device__ __forceinline__ void column_reduce_finish(float (&acc)[K][8], int c8, int cgroups, double* const (&dst)[K]) {
+  extern __shared__ float sh[];  // [blockDim][K*8]
+  float* mine = sh + threadIdx.x * (K * 8);
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mine[k * 8 + j] = acc[k][j];
+  __syncthreads();
+  // threads 0..cgroups-1 sum over the row-lanes
+  if (threadIdx.x < cgroups) {
+    const int lanes = blockDim.x / cgroups;
+    for (int k = 0; k < K; ++k)
+      for (int j = 0; j < 8; ++j) {
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += sh[(l * cgroups + threadIdx.x) * (K * 8) + k * 8 + j];
+        atomicAdd(dst[k] + c8 + j, (double)t);
+      }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const __nv_bfloat16* __restrict__ y, int64_t rows, int c, double* __restrict__ sum,
+                double* __restrict__ sumsq) {
+  const int cgroups = c / 8;
+  const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
+  float acc[2][8] = {};
+  if (lane < lanes)
+    for (int64_t r = blockIdx.x * (int64_t)lanes + lane; r < rows; r += (int64_t)gridDim.x * lanes) {
+      const V8 x = load8(y + r * c + cg * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += x.v[j];
+        acc[1][j] = fmaf(x.v[j], x.v[j], acc[1][j]);
+      }
+    }
+  double* const dst[2] = {sum, sumsq};
+  column_reduce_finish<2>(acc, cg * 8, cgroups, dst);
+}
+
+// mean / invstd / scale / shift from the accumulated sums; running statistics as nn.BatchNorm2d (momentum 0.1,
+// unbiased running variance).  Re-zeroes the accumulators for the next step.
+__global__ void bn_finalize_kernel(double* __restrict__ sum, double* __restrict__ sumsq, int64_t rows, int c,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                   float* __restrict__ scale, float* __restrict__ shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const double n = (double)rows;
+  const double m = sum[i] / n;
+  double var = sumsq[i] / n - m * m;
+  if (var < 0.0) var = 0.0;
+  sum[i] = 0.0;
+  sumsq[i] = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  mean_out[i] = (float)m;
+  invstd_out[i] = invstd;
+  const float sc = gamma[i] * invstd;
+  scale[i] = sc;
+  shift[i] = beta[i] - (float)m * sc;
+  if (running_mean) {
+    const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
+    running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * (float)m;
+    running_var[i] = (1.f - momentum) * running_var[i] + momentum * (float)unbiased;
+  }
+}
+
+// eval mode: scale/shift from the running statistics
+__global__ void bn_eval_coeffs_kernel(int c, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                      const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                      float* __restrict__ scale, float* __restrict__ shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const float sc = gamma[i] * rsqrtf(running_var[i] + eps);
+  scale[i] = sc;
+  shift[i] = beta[i] - running_mean[i] * sc;
+}
+
+// out = [relu]( y*scale + shift  [+ res]  [+ res_y*res_scale + res_shift] )
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                const __nv_bfloat16* __restrict__ res, const __nv_bfloat16* __restrict__ res_y,
+                const float* __restrict__ res_scale, const float* __restrict__ res_shift, int relu, int64_t total8,
+                int c, __nv_bfloat16* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)((i * 8) % c);
+    V8 x = load8(y + i * 8);
+    const V8 sc = loadf8(scale + c8), sh = loadf8(shift + c8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x.v[j] = fmaf(x.v[j], sc.v[j], sh.v[j]);
+    if (res) {
+      const V8 r = load8(res + i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x.v[j] += r.v[j];
+    }
+    if (res_y) {
+      const V8 r = load8(res_y + i * 8);
+      const V8 rs = loadf8(res_scale + c8), rh = loadf8(res_shift + c8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x.v[j] += fmaf(r.v[j], rs.v[j], rh.v[j]);
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x.v[j] = fmaxf(x.v[j], 0.f);
+    }
+    store8(out + i * 8, x);
+  }
+}
+
+// ---- backward.  dz = (g1 [+ g2]) * (act > 0); per channel: dbeta = sum dz, dgamma = sum dz * xhat.
+// Optional second BN (the downsample branch) shares dz.
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
+                     const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ y,
+                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                     const __nv_bfloat16* __restrict__ y2, const float* __restrict__ mean2,
+                     const float* __restrict__ invstd2, int64_t rows, int c, double* __restrict__ dbeta,
+                     double* __restrict__ dgamma, double* __restrict__ dgamma2) {
+  const int cgroups = c / 8;
+  const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
+  float acc[3][8] = {};
+  if (lane < lanes) {
+    const V8 mu = loadf8(mean + cg * 8), is = loadf8(invstd + cg * 8);
+    V8 mu2{}, is2{};
+    if (y2) {
+      mu2 = loadf8(mean2 + cg * 8);
+      is2 = loadf8(invstd2 + cg * 8);
+    }
+    for (int64_t r = blockIdx.x * (int64_t)lanes + lane; r < rows; r += (int64_t)gridDim.x * lanes) {
+      const int64_t off = r * c + cg * 8;
+      V8 g = load8(g1 + off);
+      if (g2) {
+        const V8 t = load8(g2 + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.v[j] += t.v[j];
+      }
+      if (act) {
+        const V8 a = load8(act + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.v[j] = a.v[j] > 0.f ? g.v[j] : 0.f;
+      }
+      const V8 x = load8(y + off);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += g.v[j];
+        acc[1][j] = fmaf(g.v[j], (x.v[j] - mu.v[j]) * is.v[j], acc[1][j]);
+      }
+      if (y2) {
+        const V8 x2 = load8(y2 + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[2][j] = fmaf(g.v[j], (x2.v[j] - mu2.v[j]) * is2.v[j], acc[2][j]);
+      }
+    }
+  }
+  double* const dst[3] = {dbeta, dgamma, dgamma2 ? dgamma2 : dgamma};
+  if (y2) {
+    column_reduce_finish<3>(acc, cg * 8, cgroups, dst);
+  } else {
+    float acc2[2][8];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc2[k][j] = acc[k][j];
+    double* const dst2[2] = {dbeta, dgamma};
+    column_reduce_finish<2>(acc2, cg * 8, cgroups, dst2);
+  }
+}
+
+// dy = gamma*invstd * (dz - dbeta/n - xhat * dgamma/n)  (and the same for the second BN); optionally writes dz.
+// Also accumulates dgamma/dbeta into the fp32 parameter gradients (done by the thread that owns row 0).
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
+                    const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ y,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const double* __restrict__ dbeta, const double* __restrict__ dgamma,
+                    const __nv_bfloat16* __restrict__ y2, const float* __restrict__ mean2,
+                    const float* __restrict__ invstd2, const float* __restrict__ gamma2,
+                    const double* __restrict__ dgamma2, int64_t rows, int c, __nv_bfloat16* __restrict__ dy,
+                    __nv_bfloat16* __restrict__ dy2, __nv_bfloat16* __restrict__ dz_out) {
+  const int64_t total8 = rows * c / 8;
+  const float inv_n = 1.f / (float)rows;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)((i * 8) % c);
+    V8 g = load8(g1 + i * 8);
+    if (g2) {
+      const V8 t = load8(g2 + i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g.v[j] += t.v[j];
+    }
+    if (act) {
+      const V8 a = load8(act + i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g.v[j] = a.v[j] > 0.f ? g.v[j] : 0.f;
+    }
+    if (dz_out) store8(dz_out + i * 8, g);
+    {
+      const V8 x = load8(y + i * 8);
+      const V8 mu = loadf8(mean + c8), is = loadf8(invstd + c8), ga = loadf8(gamma + c8);
+      V8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (x.v[j] - mu.v[j]) * is.v[j];
+        const float db = (float)dbeta[c8 + j] * inv_n, dg = (float)dgamma[c8 + j] * inv_n;
+        o.v[j] = ga.v[j] * is.v[j] * (g.v[j] - db - xh * dg);
+      }
+      store8(dy + i * 8, o);
+    }
+    if (y2) {
+      const V8 x = load8(y2 + i * 8);
+      const V8 mu = loadf8(mean2 + c8), is = loadf8(invstd2 + c8), ga = loadf8(gamma2 + c8);
+      V8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (x.v[j] - mu.v[j]) * is.v[j];
+        const float db = (float)dbeta[c8 + j] * inv_n, dg = (float)dgamma2[c8 + j] * inv_n;
+        o.v[j] = ga.v[j] * is.v[j] * (g.v[j] - db - xh * dg);
+      }
+      store8(dy2 + i * 8, o);
+    }
+  }
+}
+
+// grad_gamma += dgamma, grad_beta += dbeta (fp32 parameter gradients); re-zero the fp64 accumulators
+__global__ void bn_param_grads_kernel(double* __restrict__ dbeta, double* __restrict__ dgamma, int c,
+                                      float* __restrict__ grad_gamma, float* __restrict__ grad_beta, int zero_dbeta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  grad_gamma[i] += (float)dgamma[i];
+  grad_beta[i] += (float)dbeta[i];
+  dgamma[i] = 0.0;
+  if (zero_dbeta) dbeta[i] = 0.0;
+}
+
+// ------------------------------------------------------------------ pooling
+// 3x3 / stride 2 / pad 1 max pool; idx = r*3+s of the first maximum (PyTorch's tie rule)
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c,
+                                   __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx) {
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1, cg = c / 8;
+  const int64_t total = (int64_t)n * ho * wo * cg;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    int64_t t = i / cg;
+    const int xo = (int)(t % wo); t /= wo;
+    const int yo = (int)(t % ho);
+    const int b = (int)(t / ho);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+    for (int r = 0; r < 3; ++r) {
+      const int yi = 2 * yo - 1 + r;
+      if (yi < 0 || yi >= h) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int xi = 2 * xo - 1 + s;
+        if (xi < 0 || xi >= w) continue;
+        const V8 v = load8(x + (((int64_t)b * h + yi) * w + xi) * c + g * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (v.v[j] > best[j]) { best[j] = v.v[j]; bi[j] = r * 3 + s; }
+      }
+    }
+    V8 o;
+    __align__(8) uint8_t ib[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o.v[j] = best[j]; ib[j] = (uint8_t)bi[j]; }
+    const int64_t off = (((int64_t)b * ho + yo) * wo + xo) * c + g * 8;
+    store8(out + off, o);
+    *reinterpret_cast<uint2*>(idx + off) = *reinterpret_cast<uint2*>(ib);
+  }
+}
+
+// dx[h,w] = sum over the (<= 4) windows containing (h,w) whose argmax is this position of (g1 [+ g2])
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
+                                   const uint8_t* __restrict__ idx, int n, int h, int w, int c,
+                                   __nv_bfloat16* __restrict__ dx) {
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1, cg = c / 8;
+  const int64_t total = (int64_t)n * h * w * cg;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    int64_t t = i / cg;
+    const int xi = (int)(t % w); t /= w;
+    const int yi = (int)(t % h);
+    const int b = (int)(t / h);
+    V8 acc{};
+    for (int yo = max(0, yi / 2); yo <= min(ho - 1, (yi + 1) / 2); ++yo) {
+      const int r = yi - (2 * yo - 1);
+      if (r < 0 || r > 2) continue;
+      for (int xo = max(0, xi / 2); xo <= min(wo - 1, (xi + 1) / 2); ++xo) {
+        const int s = xi - (2 * xo - 1);
+        if (s < 0 || s > 2) continue;
+        const int64_t off = (((int64_t)b * ho + yo) * wo + xo) * c + g * 8;
+        V8 gv = load8(g1 + off);
+        if (g2) {
+          const V8 t2 = load8(g2 + off);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gv.v[j] += t2.v[j];
+        }
+        const uint2 iv = *reinterpret_cast<const uint2*>(idx + off);
+        const uint8_t* ib = reinterpret_cast<const uint8_t*>(&iv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (ib[j] == r * 3 + s) acc.v[j] += gv.v[j];
+      }
+    }
+    store8(dx + i * 8, acc);
+  }
+}
+
+// enc[b, c] = mean over hw pixels (fp32)            (nn.AvgPool2d(7) on a 7x7 map + view, resnet.py:137-138)
+__global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, int hw, int c, float* __restrict__ enc) {
+  const int cg = c / 8;
+  const int64_t total = (int64_t)n * cg;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const int b = (int)(i / cg);
+    float acc[8] = {};
+    for (int p = 0; p < hw; ++p) {
+      const V8 v = load8(x + ((int64_t)b * hw + p) * c + g * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v.v[j];
+    }
+    const float inv = 1.f / (float)hw;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) enc[(int64_t)b * c + g * 8 + j] = acc[j] * inv;
+  }
+}
+
+__global__ void avgpool_bwd_kernel(const float* __restrict__ genc, int n, int hw, int c, __nv_bfloat16* __restrict__ dx) {
+  const int cg = c / 8;
+  const int64_t total = (int64_t)n * hw * cg;
+  const float inv = 1.f / (float)hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const int b = (int)(i / ((int64_t)cg * hw));
+    V8 o = loadf8(genc + (int64_t)b * c + g * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] *= inv;
+    store8(dx + i * 8, o);
+  }
+}
+
+// --------------------------------------------------------------- regressor
+// pred[b] = dot(x[b,:], w) + bias          (nn.Linear(2048, 1), resnet.py:88,148)
+__global__ void __launch_bounds__(256) linear1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, int d,
+                                                          float* __restrict__ pred) {
+  __shared__ float sh[8];
+  const int b = blockIdx.x;
+  float acc = 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) acc = fmaf(x[(int64_t)b * d + c], w[c], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
+    pred[b] = t + bias[0];
+  }
+}
+
+// dx[b,c] = g[b]*w[c];  dw[c] = sum_b g[b]*x[b,c];  dbias = sum_b g[b]     (thread per c)
+__global__ void linear1_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ w,
+                                   int n, int d, float* __restrict__ dx, float* __restrict__ dw,
+                                   float* __restrict__ dbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  const float wc = w[c];
+  float acc = 0.f, gb = 0.f;
+  for (int b = 0; b < n; ++b) {
+    const float gv = g[b];
+    acc = fmaf(gv, x[(int64_t)b * d + c], acc);
+    gb += gv;
+    if (dx) dx[(int64_t)b * d + c] = gv * wc;
+  }
+  dw[c] = acc;
+  if (c == 0) dbias[0] = gb;
+}
+
+// ---------------------------------------------------------------- optimizer
+// torch.optim.Adam (no amsgrad; L2 weight decay added to the gradient), bias correction folded into step_size /
+// bc2_sqrt on the host.  Flat fp32 buffers, 128-bit accesses.
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
+            float grad_scale) {
+  const int64_t n4 = n / 4;
+  const float step_size = lr / bc1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float* pa = &pp.x;
+    const float* ga = &gg.x;
+    float* ma = &mm.x;
+    float* va = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gr = ga[j] * grad_scale;
+      if (weight_decay != 0.f) gr = fmaf(weight_decay, pa[j], gr);
+      ma[j] = fmaf(beta1, ma[j], (1.f - beta1) * gr);
+      va[j] = fmaf(beta2, va[j], (1.f - beta2) * gr * gr);
+      const float denom = sqrtf(va[j]) / bc2_sqrt + eps;
+      pa[j] -= step_size * (ma[j] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail
+  const int64_t i = n4 * 4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    float gr = g[i] * grad_scale;
+    if (weight_decay != 0.f) gr = fmaf(weight_decay, p[i], gr);
+    m[i] = fmaf(beta1, m[i], (1.f - beta1) * gr);
+    v[i] = fmaf(beta2, v[i], (1.f - beta2) * gr * gr);
+    p[i] -= step_size * (m[i] / (sqrtf(v[i]) / bc2_sqrt + eps));
+  }
+}
+
+// torch.optim.SGD with momentum (dampening 0, no nesterov), weight decay
+__global__ void __launch_bounds__(256)
+sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n, float lr,
+           float momentum, float weight_decay, int first_step, float grad_scale) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gr = g[i] * grad_scale;
+    if (weight_decay != 0.f) gr = fmaf(weight_decay, p[i], gr);
+    if (momentum != 0.f) {
+      const float b = first_step ? gr : fmaf(momentum, buf[i], gr);
+      buf[i] = b;
+      gr = b;
+    }
+    p[i] -= lr * gr;
+  }
+}
+
+static inline int grid1d(int64_t n, int block = 256, int per_sm = 8) {
+  int64_t g = (n + block - 1) / block;
+  const int64_t cap = (int64_t)per_sm * num_sms();
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+static inline int reduce_grid(int64_t rows, int lanes) {
+  int64_t g = (rows + (int64_t)lanes * 16 - 1) / ((int64_t)lanes * 16);   // >= ~16 rows per thread
+  const int64_t cap = 4 * (int64_t)num_sms();
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// ------------------------------------------------------------- host wrappers
+int bn_stats(const __nv_bfloat16* y, int64_t rows, int c, double* sum, double* sumsq, cudaStream_t st) {
+  const int cgroups = c / 8;
+  DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_stats: unsupported channel count %d", c);
+  const int lanes = 256 / cgroups;
+  bn_stats_kernel<<<reduce_grid(rows, lanes), 256, 256 * 16 * sizeof(float), st>>>(y, rows, c, sum, sumsq);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+int bn_finalize(double* sum, double* sumsq, int64_t rows, int c, const float* gamma, const float* beta, float eps,
+                float momentum, float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
+                float* shift, cudaStream_t st) {
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(sum, sumsq, rows, c, gamma, beta, eps, momentum, running_mean,
+                                                      running_var, mean, invstd, scale, shift);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+int bn_eval_coeffs(int c, const float* gamma, const float* beta, float eps, const float* running_mean,
+                   const float* running_var, float* scale, float* shift, cudaStream_t st) {
+  bn_eval_coeffs_kernel<<<(c + 127) / 128, 128, 0, st>>>(c, gamma, beta, eps, running_mean, running_var, scale, shift);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, const __nv_bfloat16* res,
+             const __nv_bfloat16* res_y, const float* res_scale, const float* res_shift, bool relu, int64_t rows, int c,
+             __nv_bfloat16* out, cudaStream_t st) {
+  const int64_t total8 = rows * c / 8;
+  bn_apply_kernel<<<grid1d(total8), 256, 0, st>>>(y, scale, shift, res, res_y, res_scale, res_shift, relu ? 1 : 0,
+                                                  total8, c, out);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* act, const __nv_bfloat16* y,
+                  const float* mean, const float* invstd, const __nv_bfloat16* y2, const float* mean2,
+                  const float* invstd2, int64_t rows, int c, double* dbeta, double* dgamma, double* dgamma2,
+                  cudaStream_t st) {
+  const int cgroups = c / 8;
+  DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_bwd_reduce: unsupported channel count %d", c);
+  const int lanes = 256 / cgroups;
+  bn_bwd_reduce_kernel<<<reduce_grid(rows, lanes), 256, 256 * 24 * sizeof(float), st>>>(
+      g1, g2, act, y, mean, invstd, y2, mean2, invstd2, rows, c, dbeta, dgamma, dgamma2);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* act, const __nv_bfloat16* y,
+                 const float* mean, const float* invstd, const float* gamma, const double* dbeta, const double* dgamma,
+                 const __nv_bfloat16* y2, const float* mean2, const float* invstd2, const float* gamma2,
+                 const double* dgamma2, int64_t rows, int c, __nv_bfloat16* dy, __nv_bfloat16* dy2,
+                 __nv_bfloat16* dz_out, cudaStream_t st) {
+  bn_bwd_apply_kernel<<<grid1d(rows * c / 8), 256, 0, st>>>(g1, g2, act, y, mean, invstd, gamma, dbeta, dgamma, y2,
+                                                           mean2, invstd2, gamma2, dgamma2, rows, c, dy, dy2, dz_out);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+int bn_param_grads(double* dbeta, double* dgamma, int c, float* grad_gamma, float* grad_beta, bool zero_dbeta,
+                   cudaStream_t st) {
+  bn_param_grads_kernel<<<(c + 127) / 128, 128, 0, st>>>(dbeta, dgamma, c, grad_gamma, grad_beta, zero_dbeta ? 1 : 0);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+int maxpool_fwd(const __nv_bfloat16* x, int n, int h, int w, int c, __nv_bfloat16* out, uint8_t* idx, cudaStream_t st) {
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  maxpool_fwd_kernel<<<grid1d((int64_t)n * ho * wo * c / 8), 256, 0, st>>>(x, n, h, w, c, out, idx);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+int maxpool_bwd(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const uint8_t* idx, int n, int h, int w, int c,
+                __nv_bfloat16* dx, cudaStream_t st) {
+  maxpool_bwd_kernel<<<grid1d((int64_t)n * h * w * c / 8), 256, 0, st>>>(g1, g2, idx, n, h, w, c, dx);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+int avgpool_fwd(const __nv_bfloat16* x, int n, int hw, int c, float* enc, cudaStream_t st) {
+  avgpool_fwd_kernel<<<grid1d((int64_t)n * c / 8, 128), 128, 0, st>>>(x, n, hw, c, enc);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+int avgpool_bwd(const float* genc, int n, int hw, int c, __nv_bfloat16* dx, cudaStream_t st) {
+  avgpool_bwd_kernel<<<grid1d((int64_t)n * hw * c / 8), 256, 0, st>>>(genc, n, hw, c, dx);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+}  // namespace dirb200
+
+using namespace dirb200;
+
+extern "C" {
+
+int dirb200_linear1_fwd(const float* x, const float* w, const float* bias, int64_t n, int d, float* pred,
+                        void* stream) {
+  DIRB_CHECK_ARG(x && w && bias && pred && n > 0 && d > 0, "linear1_fwd: bad arguments");
+  linear1_fwd_kernel<<<(unsigned)n, 256, 0, as_stream(stream)>>>(x, w, bias, d, pred);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+int dirb200_linear1_bwd(const float* grad_pred, const float* x, const float* w, int64_t n, int d, float* dx,
+                        float* dw, float* dbias, void* stream) {
+  DIRB_CHECK_ARG(grad_pred && x && w && dw && dbias && n > 0 && d > 0, "linear1_bwd: bad arguments");
+  linear1_bwd_kernel<<<(d + 127) / 128, 128, 0, as_stream(stream)>>>(grad_pred, x, w, (int)n, d, dx, dw, dbias);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+int dirb200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                      void* stream) {
+  DIRB_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad arguments");
+  DIRB_CHECK_ARG((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
+                  reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) % 16 == 0,
+                 "adam_step: buffers must be 16-byte aligned");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<grid1d(n / 4 + 1), 256, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                               eps, weight_decay, (float)bc1, (float)sqrt(bc2),
+                                                               grad_scale);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+int dirb200_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr, float momentum,
+                     float weight_decay, int first_step, float grad_scale, void* stream) {
+  DIRB_CHECK_ARG(params && grads && n > 0 && (momentum == 0.f || momentum_buf), "sgd_step: bad arguments");
+  sgd_kernel<<<grid1d(n), 256, 0, as_stream(stream)>>>(params, grads, momentum_buf, n, lr, momentum, weight_decay,
+                                                      first_step, grad_scale);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,310 @@
+// Native runner of the bottleneck-ResNet backbone (agedb-dir/resnet.py:41-70,73-138): sequences the
+// tcgen05 convolutions and the HBM-bound layers for one forward and one backward pass over a fixed
+// batch shape, owning every activation / gradient / operand buffer (NHWC bf16) so that a training
+// step issues no allocation and no host synchronisation.
+//
+// Parameters and their gradients live in ONE flat fp32 buffer each, laid out in the reference's
+// named_parameters() order (conv1.weight, bn1.weight, bn1.bias, layer1.0.conv1.weight, ...), which the
+// Python module (resnet.py) exposes as ordinary nn.Parameter views -> identical state_dict keys/shapes.
+#include <vector>
+#include "common.cuh"
+#include "conv.cuh"
+#include "nn.cuh"
+
+namespace dirb200 {
+
+struct BNLayer {
+  int c = 0;
+  size_t gamma_off = 0, beta_off = 0;  // in the flat parameter buffer (floats)
+  size_t rm_off = 0, rv_off = 0;       // in the flat BN running-statistics buffer (floats)
+  float *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr;
+  double* acc = nullptr;               // [2][c] fp64: (sum, sumsq) forward / (dbeta, dgamma) backward; kept zero between uses
+};
+
+struct ConvLayer {
+  ConvShape s{};
+  bool stem = false;
+  size_t w_off = 0;
+  __nv_bfloat16 *wf = nullptr, *wd = nullptr;  // GEMM operands (fprop / dgrad layouts)
+  __nv_bfloat16* y = nullptr;                  // raw conv output [rows][cout]
+  __nv_bfloat16* a = nullptr;                  // relu(bn(y)) when this conv is followed by BN+ReLU
+  int64_t rows = 0;                            // n*ho*wo
+  BNLayer bn;
+};
+
+struct Block {
+  ConvLayer c1, c2, c3, ds;
+  bool has_ds = false;
+  const __nv_bfloat16* in = nullptr;
+  __nv_bfloat16* out = nullptr;
+};
+
+}  // namespace dirb200
+
+using namespace dirb200;
+
+struct dirb200_net {
+  int n = 0, h = 0, w = 0;
+  ConvLayer stem;
+  std::vector<Block> blocks;
+  __nv_bfloat16 *x_s2d = nullptr, *pool_out = nullptr;
+  uint8_t* pool_idx = nullptr;
+  int pool_h = 0, pool_w = 0;
+  int feat_c = 0, feat_hw = 0;
+  __nv_bfloat16* scratch[8] = {};
+  float* wgrad_ws = nullptr;
+  size_t param_count = 0, running_count = 0, activation_bytes = 0;
+  std::vector<void*> allocs;
+  bool forward_was_training = false;
+};
+
+namespace dirb200 {
+
+static bool dev_alloc(dirb200_net* net, void** p, size_t bytes) {
+  if (cudaMalloc(p, bytes) != cudaSuccess) {
+    set_error("resnet_create: cudaMalloc of %zu bytes failed", bytes);
+    return false;
+  }
+  net->allocs.push_back(*p);
+  net->activation_bytes += bytes;
+  return true;
+}
+
+#define NET_ALLOC(ptr, bytes)                                                     \
+  do {                                                                            \
+    if (!dev_alloc(net, reinterpret_cast<void**>(&(ptr)), (bytes))) return false; \
+  } while (0)
+
+static bool setup_bn(dirb200_net* net, BNLayer& bn, int c) {
+  bn.c = c;
+  bn.gamma_off = net->param_count;
+  bn.beta_off = net->param_count + c;
+  net->param_count += 2 * (size_t)c;
+  bn.rm_off = net->running_count;
+  bn.rv_off = net->running_count + c;
+  net->running_count += 2 * (size_t)c;
+  float* f = nullptr;
+  NET_ALLOC(f, sizeof(float) * 4 * c);
+  bn.mean = f; bn.invstd = f + c; bn.scale = f + 2 * c; bn.shift = f + 3 * c;
+  NET_ALLOC(bn.acc, sizeof(double) * 2 * c);
+  return cudaMemset(bn.acc, 0, sizeof(double) * 2 * c) == cudaSuccess;
+}
+
+static bool setup_conv(dirb200_net* net, ConvLayer& cv, int n, int h, int w, int cin, int cout, int k, int stride,
+                       int pad, bool stem, bool with_act) {
+  cv.stem = stem;
+  const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+  if (stem) cv.s = ConvShape{n, h / 2, w / 2, 16, cout, 4, 4, 1, 2, h / 2, w / 2};
+  else cv.s = ConvShape{n, h, w, cin, cout, k, k, stride, pad, ho, wo};
+  cv.w_off = net->param_count;
+  net->param_count += (size_t)cout * cin * k * k;
+  cv.rows = (int64_t)n * ho * wo;
+  const size_t welems = stem ? (size_t)cout * 256 : (size_t)cout * cin * k * k;
+  NET_ALLOC(cv.wf, welems * 2);
+  if (!stem) NET_ALLOC(cv.wd, welems * 2);
+  NET_ALLOC(cv.y, (size_t)cv.rows * cout * 2);
+  if (with_act) NET_ALLOC(cv.a, (size_t)cv.rows * cout * 2);
+  return setup_bn(net, cv.bn, cout);
+}
+
+static bool build(dirb200_net* net, const int* blocks_per_stage, int num_stages) {
+  const int n = net->n;
+  if (!setup_conv(net, net->stem, n, net->h, net->w, 3, 64, 7, 2, 3, true, true)) return false;
+  int h = net->h / 2, w = net->w / 2;
+  NET_ALLOC(net->x_s2d, (size_t)n * h * w * 16 * 2);
+  net->pool_h = (h - 1) / 2 + 1;
+  net->pool_w = (w - 1) / 2 + 1;
+  const size_t pool_elems = (size_t)n * net->pool_h * net->pool_w * 64;
+  NET_ALLOC(net->pool_out, pool_elems * 2);
+  NET_ALLOC(net->pool_idx, pool_elems);
+  h = net->pool_h; w = net->pool_w;
+  int inplanes = 64;
+  const __nv_bfloat16* cur = net->pool_out;
+  size_t max_act = (size_t)net->stem.rows * 64;
+  for (int st = 0; st < num_stages; ++st) {
+    const int planes = 64 << st;
+    for (int b = 0; b < blocks_per_stage[st]; ++b) {
+      const int stride = (b == 0 && st > 0) ? 2 : 1;
+      net->blocks.emplace_back();
+      Block& B = net->blocks.back();
+      B.in = cur;
+      B.has_ds = (b == 0) && (stride != 1 || inplanes != planes * 4);
+      if (!setup_conv(net, B.c1, n, h, w, inplanes, planes, 1, 1, 0, false, true)) return false;
+      if (!setup_conv(net, B.c2, n, h, w, planes, planes, 3, stride, 1, false, true)) return false;
+      const int h2 = B.c2.s.ho, w2 = B.c2.s.wo;
+      if (!setup_conv(net, B.c3, n, h2, w2, planes, planes * 4, 1, 1, 0, false, false)) return false;
+      if (B.has_ds && !setup_conv(net, B.ds, n, h, w, inplanes, planes * 4, 1, stride, 0, false, false)) return false;
+      NET_ALLOC(B.out, (size_t)B.c3.rows * planes * 4 * 2);
+      max_act = std::max(max_act, (size_t)B.c1.rows * std::max(inplanes, planes));
+      max_act = std::max(max_act, (size_t)B.c3.rows * planes * 4);
+      cur = B.out;
+      inplanes = planes * 4;
+      h = h2; w = w2;
+    }
+  }
+  net->feat_c = inplanes;
+  net->feat_hw = h * w;
+  for (int i = 0; i < 8; ++i) NET_ALLOC(net->scratch[i], max_act * 2);
+  size_t ws = conv_wgrad_workspace_bytes(net->stem.s);
+  for (Block& B : net->blocks) {
+    ws = std::max(ws, conv_wgrad_workspace_bytes(B.c1.s));
+    ws = std::max(ws, conv_wgrad_workspace_bytes(B.c2.s));
+    ws = std::max(ws, conv_wgrad_workspace_bytes(B.c3.s));
+    if (B.has_ds) ws = std::max(ws, conv_wgrad_workspace_bytes(B.ds.s));
+  }
+  NET_ALLOC(net->wgrad_ws, ws);
+  return true;
+}
+
+#define RUN(expr)                    \
+  do {                               \
+    if (int _rc = (expr)) return _rc; \
+  } while (0)
+
+static int conv_bn_forward(ConvLayer& cv, const __nv_bfloat16* in, const float* params, float* running, bool training,
+                           cudaStream_t st) {
+  RUN(prep_weights(params + cv.w_off, cv.s.cout, cv.stem ? 3 : cv.s.cin, cv.stem ? 7 : cv.s.kh, cv.stem ? 7 : cv.s.kw,
+                   cv.stem, cv.wf, cv.wd, st));
+  RUN(conv_fprop(in, cv.wf, cv.y, cv.s, cv.stem, st));
+  BNLayer& bn = cv.bn;
+  if (training) {
+    RUN(bn_stats(cv.y, cv.rows, bn.c, bn.acc, bn.acc + bn.c, st));
+    RUN(bn_finalize(bn.acc, bn.acc + bn.c, cv.rows, bn.c, params + bn.gamma_off, params + bn.beta_off, 1e-5f, 0.1f,
+                    running ? running + bn.rm_off : nullptr, running ? running + bn.rv_off : nullptr, bn.mean,
+                    bn.invstd, bn.scale, bn.shift, st));
+  } else {
+    RUN(bn_eval_coeffs(bn.c, params + bn.gamma_off, params + bn.beta_off, 1e-5f, running + bn.rm_off,
+                       running + bn.rv_off, bn.scale, bn.shift, st));
+  }
+  if (cv.a) RUN(bn_apply(cv.y, bn.scale, bn.shift, nullptr, nullptr, nullptr, nullptr, true, cv.rows, bn.c, cv.a, st));
+  return DIRB200_OK;
+}
+
+// BN backward for a conv followed by BN+ReLU: g = d loss / d relu-output
+static int conv_bn_backward(ConvLayer& cv, const __nv_bfloat16* g, const float* params, float* grads,
+                            __nv_bfloat16* dy, cudaStream_t st) {
+  BNLayer& bn = cv.bn;
+  RUN(bn_bwd_reduce(g, nullptr, cv.a, cv.y, bn.mean, bn.invstd, nullptr, nullptr, nullptr, cv.rows, bn.c, bn.acc,
+                    bn.acc + bn.c, nullptr, st));
+  RUN(bn_bwd_apply(g, nullptr, cv.a, cv.y, bn.mean, bn.invstd, params + bn.gamma_off, bn.acc, bn.acc + bn.c, nullptr,
+                   nullptr, nullptr, nullptr, nullptr, cv.rows, bn.c, dy, nullptr, nullptr, st));
+  RUN(bn_param_grads(bn.acc, bn.acc + bn.c, bn.c, grads + bn.gamma_off, grads + bn.beta_off, true, st));
+  return DIRB200_OK;
+}
+
+}  // namespace dirb200
+
+extern "C" {
+
+int dirb200_resnet_create(int n, int h, int w, const int* blocks_per_stage, int num_stages, dirb200_net** out) {
+  DIRB_CHECK_ARG(out && blocks_per_stage && n > 0 && num_stages >= 1 && num_stages <= 4, "resnet_create: bad arguments");
+  DIRB_CHECK_ARG(h > 0 && w > 0 && h % 32 == 0 && w % 32 == 0, "resnet_create: H and W must be multiples of 32");
+  dirb200_net* net = new dirb200_net();
+  net->n = n; net->h = h; net->w = w;
+  if (!build(net, blocks_per_stage, num_stages)) {
+    for (void* p : net->allocs) cudaFree(p);
+    delete net;
+    return DIRB200_ERR_CUDA;
+  }
+  *out = net;
+  return DIRB200_OK;
+}
+
+void dirb200_resnet_destroy(dirb200_net* net) {
+  if (!net) return;
+  for (void* p : net->allocs) cudaFree(p);
+  delete net;
+}
+
+int64_t dirb200_resnet_param_count(const dirb200_net* net) { return net ? (int64_t)net->param_count : -1; }
+int64_t dirb200_resnet_running_count(const dirb200_net* net) { return net ? (int64_t)net->running_count : -1; }
+int64_t dirb200_resnet_feature_dim(const dirb200_net* net) { return net ? net->feat_c : -1; }
+int64_t dirb200_resnet_device_bytes(const dirb200_net* net) { return net ? (int64_t)net->activation_bytes : -1; }
+
+/* x fp32 NCHW [n,3,h,w] -> enc fp32 [n, feature_dim]  (conv1 ... avgpool + view, resnet.py:128-138).
+ * training != 0: batch statistics, running statistics updated (momentum 0.1); else running statistics. */
+int dirb200_resnet_forward(dirb200_net* net, const float* x_nchw, const float* params, float* bn_running, int training,
+                           float* enc_out, void* stream) {
+  DIRB_CHECK_ARG(net && x_nchw && params && enc_out, "resnet_forward: null pointer");
+  DIRB_CHECK_ARG(training || bn_running, "resnet_forward: eval mode needs the running statistics");
+  cudaStream_t st = as_stream(stream);
+  const bool tr = training != 0;
+  RUN(input_to_s2d(x_nchw, net->n, net->h, net->w, net->x_s2d, st));
+  RUN(conv_bn_forward(net->stem, net->x_s2d, params, bn_running, tr, st));
+  RUN(maxpool_fwd(net->stem.a, net->n, net->stem.s.ho, net->stem.s.wo, 64, net->pool_out, net->pool_idx, st));
+  for (Block& B : net->blocks) {
+    RUN(conv_bn_forward(B.c1, B.in, params, bn_running, tr, st));
+    RUN(conv_bn_forward(B.c2, B.c1.a, params, bn_running, tr, st));
+    RUN(conv_bn_forward(B.c3, B.c2.a, params, bn_running, tr, st));
+    if (B.has_ds) {
+      RUN(conv_bn_forward(B.ds, B.in, params, bn_running, tr, st));
+      RUN(bn_apply(B.c3.y, B.c3.bn.scale, B.c3.bn.shift, nullptr, B.ds.y, B.ds.bn.scale, B.ds.bn.shift, true, B.c3.rows,
+                   B.c3.bn.c, B.out, st));
+    } else {
+      RUN(bn_apply(B.c3.y, B.c3.bn.scale, B.c3.bn.shift, B.in, nullptr, nullptr, nullptr, true, B.c3.rows, B.c3.bn.c,
+                   B.out, st));
+    }
+  }
+  RUN(avgpool_fwd(net->blocks.back().out, net->n, net->feat_hw, net->feat_c, enc_out, st));
+  net->forward_was_training = tr;
+  return DIRB200_OK;
+}
+
+/* d_enc fp32 [n, feature_dim] -> ACCUMULATES d loss / d parameter into grads (flat fp32, same layout as params).
+ * Must follow a training-mode forward on the same net. */
+int dirb200_resnet_backward(dirb200_net* net, const float* d_enc, const float* params, float* grads, void* stream) {
+  DIRB_CHECK_ARG(net && d_enc && params && grads, "resnet_backward: null pointer");
+  DIRB_CHECK_ARG(net->forward_was_training, "resnet_backward: needs a preceding training-mode forward");
+  cudaStream_t st = as_stream(stream);
+  __nv_bfloat16 *gA = net->scratch[0], *gB = nullptr, *nA = net->scratch[2], *nB = net->scratch[3];
+  __nv_bfloat16 *t1 = net->scratch[4], *t2 = net->scratch[5], *t3 = net->scratch[6];
+  __nv_bfloat16* spareB = net->scratch[1];
+  float* ws = net->wgrad_ws;
+  RUN(avgpool_bwd(d_enc, net->n, net->feat_hw, net->feat_c, gA, st));
+  for (int bi = (int)net->blocks.size() - 1; bi >= 0; --bi) {
+    Block& B = net->blocks[bi];
+    BNLayer& b3 = B.c3.bn;
+    // ---- block output: out = relu(bn3(y3) + identity); dz = (gA + gB) * (out > 0)
+    RUN(bn_bwd_reduce(gA, gB, B.out, B.c3.y, b3.mean, b3.invstd, B.has_ds ? B.ds.y : nullptr,
+                      B.has_ds ? B.ds.bn.mean : nullptr, B.has_ds ? B.ds.bn.invstd : nullptr, B.c3.rows, b3.c, b3.acc,
+                      b3.acc + b3.c, B.has_ds ? B.ds.bn.acc + b3.c : nullptr, st));
+    RUN(bn_bwd_apply(gA, gB, B.out, B.c3.y, b3.mean, b3.invstd, params + b3.gamma_off, b3.acc, b3.acc + b3.c,
+                     B.has_ds ? B.ds.y : nullptr, B.has_ds ? B.ds.bn.mean : nullptr,
+                     B.has_ds ? B.ds.bn.invstd : nullptr, B.has_ds ? params + B.ds.bn.gamma_off : nullptr,
+                     B.has_ds ? B.ds.bn.acc + b3.c : nullptr, B.c3.rows, b3.c, t1, B.has_ds ? t2 : nullptr,
+                     B.has_ds ? nullptr : nB, st));
+    if (B.has_ds) {
+      RUN(bn_param_grads(b3.acc, B.ds.bn.acc + b3.c, b3.c, grads + B.ds.bn.gamma_off, grads + B.ds.bn.beta_off, false, st));
+    }
+    RUN(bn_param_grads(b3.acc, b3.acc + b3.c, b3.c, grads + b3.gamma_off, grads + b3.beta_off, true, st));
+    // ---- conv3
+    RUN(conv_wgrad(B.c2.a, t1, grads + B.c3.w_off, ws, B.c3.s, false, true, st));
+    RUN(conv_dgrad(t1, B.c3.wd, t3, B.c3.s, st));
+    // ---- bn2 + conv2
+    RUN(conv_bn_backward(B.c2, t3, params, grads, t1, st));
+    RUN(conv_wgrad(B.c1.a, t1, grads + B.c2.w_off, ws, B.c2.s, false, true, st));
+    RUN(conv_dgrad(t1, B.c2.wd, t3, B.c2.s, st));
+    // ---- bn1 + conv1
+    RUN(conv_bn_backward(B.c1, t3, params, grads, t1, st));
+    RUN(conv_wgrad(B.in, t1, grads + B.c1.w_off, ws, B.c1.s, false, true, st));
+    RUN(conv_dgrad(t1, B.c1.wd, nA, B.c1.s, st));
+    // ---- downsample branch
+    if (B.has_ds) {
+      RUN(conv_wgrad(B.in, t2, grads + B.ds.w_off, ws, B.ds.s, false, true, st));
+      RUN(conv_dgrad(t2, B.ds.wd, nB, B.ds.s, st));
+    }
+    // the two gradients w.r.t. this block's input become the next (earlier) block's incoming pair
+    __nv_bfloat16* oldA = gA;
+    __nv_bfloat16* oldB = gB ? gB : spareB;
+    gA = nA; gB = nB;
+    nA = oldA; nB = oldB;
+    spareB = nullptr;
+  }
+  // ---- stem: maxpool -> bn1+relu -> conv1 (no data gradient needed)
+  RUN(maxpool_bwd(gA, gB, net->pool_idx, net->n, net->stem.s.ho, net->stem.s.wo, 64, t3, st));
+  RUN(conv_bn_backward(net->stem, t3, params, grads, t1, st));
+  RUN(conv_wgrad(net->x_s2d, t1, grads + net->stem.w_off, ws, net->stem.s, true, true, st));
+  return DIRB200_OK;
+}
+
+}  // extern "C"

@@ -175,6 +175,49 @@ int dirb200_conv_wgrad(const void* x, const void* dy, float* dw, void* workspace
                        int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad,
                        int stem, int accumulate, void* stream);
 
+/* ------------------------------------------------ ResNet backbone runner ---- */
+/* Opaque native runner of the bottleneck ResNet of agedb-dir/resnet.py:41-70,
+ * 73-138 (conv1/bn1/relu/maxpool, layer1-4, avgpool, view) for one fixed
+ * input shape.  It owns every activation / gradient / operand buffer (NHWC
+ * bf16); parameters, their gradients and the BN running statistics stay in
+ * caller-owned flat fp32 buffers laid out in the reference's
+ * named_parameters() order: conv1.weight, bn1.weight, bn1.bias, then per
+ * block conv1.weight, bn1.{weight,bias}, conv2.weight, bn2.*, conv3.weight,
+ * bn3.*, [downsample.0.weight, downsample.1.{weight,bias}]; running stats per
+ * BN in the same order as (running_mean, running_var). */
+typedef struct dirb200_net dirb200_net;
+
+int dirb200_resnet_create(int n, int h, int w, const int* blocks_per_stage, int num_stages, dirb200_net** out);
+void dirb200_resnet_destroy(dirb200_net* net);
+int64_t dirb200_resnet_param_count(const dirb200_net* net);   /* floats in the flat parameter buffer */
+int64_t dirb200_resnet_running_count(const dirb200_net* net); /* floats in the flat BN running buffer */
+int64_t dirb200_resnet_feature_dim(const dirb200_net* net);   /* 2048 for ResNet-50 */
+int64_t dirb200_resnet_device_bytes(const dirb200_net* net);
+
+/* ResNet.forward up to `encoding` (resnet.py:128-138): x fp32 NCHW -> enc fp32
+ * [n, feature_dim].  training: batch statistics + running-stat update. */
+int dirb200_resnet_forward(dirb200_net* net, const float* x_nchw, const float* params, float* bn_running,
+                           int training, float* enc_out, void* stream);
+
+/* Backward of the above: d_enc fp32 [n, feature_dim]; ACCUMULATES into grads. */
+int dirb200_resnet_backward(dirb200_net* net, const float* d_enc, const float* params, float* grads, void* stream);
+
+/* nn.Linear(feature_dim, 1) (resnet.py:88,148): pred[n] = x[n,d] . w[d] + bias */
+int dirb200_linear1_fwd(const float* x, const float* w, const float* bias, int64_t n, int d, float* pred,
+                        void* stream);
+/* dx[n,d] (may be NULL), dw[d], dbias[1] (all overwritten) */
+int dirb200_linear1_bwd(const float* grad_pred, const float* x, const float* w, int64_t n, int d, float* dx,
+                        float* dw, float* dbias, void* stream);
+
+/* Fused optimizer steps over flat fp32 buffers (torch.optim.Adam / SGD semantics,
+ * agedb-dir/train.py:163-164,262); grads are multiplied by grad_scale first
+ * (1/world_size after a sum all-reduce). */
+int dirb200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                      void* stream);
+int dirb200_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr, float momentum,
+                     float weight_decay, int first_step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

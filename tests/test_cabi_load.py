@@ -15,6 +15,7 @@ def header_symbols():
 
 def test_library_exports_every_declared_symbol():
     import _lib
+    import _convlib, resnet  # noqa: F401  (register the conv-stack / runner bindings)
     lib = ctypes.CDLL(_lib.LIB_PATH)
     syms = header_symbols()
     assert len(syms) >= 15

@@ -110,3 +110,43 @@ def test_losses_match_reference():
             assert_close(gr, g[f"case{i}_w{use_w}_grad"], rtol=2e-5, atol=1e-7, what=f"{kind}{kw} grad")
         i += 1
     assert i == 10
+
+
+def test_resnet_ref_matches_reference():
+    """oracle/resnet_ref.py (fp32) vs the reference resnet50 fwd+bwd fixture."""
+    import torch
+    from util import det_param
+    from oracle import resnet_ref as R
+    g = golden("resnet")
+    shapes = R.param_shapes()
+    assert sum(int(np.prod(s)) for _, s in shapes) == int(g["n_params"]) == 23510081
+    p = {}
+    for n, s in shapes:
+        if len(s) == 4:
+            v = det_param(n, s, (2.0 / (s[0] * s[2] * s[3])) ** 0.5)
+        elif n == "linear.weight":
+            v = det_param(n, s, 0.02)
+        elif n == "linear.bias":
+            v = torch.full(s, 0.1)
+        elif n.endswith("weight"):
+            v = 1.0 + 0.1 * det_param(n, s, 1.0)
+        else:
+            v = 0.1 * det_param(n, s, 1.0)
+        p[n] = v.requires_grad_(True)
+    torch.set_num_threads(8)
+    x = det_param("input", (2, 3, 224, 224), 1.0)
+    t = torch.tensor([[31.0], [44.0]])
+    stats = {}
+    pred, enc = R.forward(p, x, stats=stats)
+    loss = ((pred - t).abs() * torch.tensor([[0.5], [1.5]])).mean()
+    loss.backward()
+    assert_close(pred.detach().numpy(), g["pred"], rtol=2e-4, atol=1e-4, what="pred")
+    assert_close(enc.detach().numpy(), g["enc"], rtol=2e-3, atol=2e-4, what="enc")
+    assert_close(loss.item(), g["loss"], rtol=1e-4)
+    assert_close(stats["bn1.running_mean"].numpy(), g["bn1_running_mean"], rtol=1e-4, atol=1e-6)
+    assert_close(stats["bn1.running_var"].numpy(), g["bn1_running_var"], rtol=1e-4, atol=1e-6)
+    for key in g.files:
+        if key.startswith("grad_abs/"):
+            n = key.split("/", 1)[1]
+            got = p[n].grad.double().abs().sum().item()
+            assert abs(got - float(g[key])) <= 3e-2 * float(g[key]) + 1e-6, (n, got, float(g[key]))  # batch-2 BN: fp32 noise flips ReLU masks
