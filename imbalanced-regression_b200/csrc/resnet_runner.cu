@@ -308,3 +308,39 @@ int dirb200_resnet_backward(dirb200_net* net, const float* d_enc, const float* p
 }
 
 }  // extern "C"
+
+extern "C" {
+/* Test / debugging aid: device pointer and shape of an internal activation.
+ * block = -1: stem (which 0 = conv1 raw, 1 = relu(bn1), 6 = max-pool output);
+ * block >= 0: which 0/1 = conv1 raw / act, 2/3 = conv2 raw / act, 4 = conv3 raw, 5 = downsample raw, 6 = block output. */
+int dirb200_resnet_peek(dirb200_net* net, int block, int which, void** ptr, int64_t* rows, int* channels) {
+  DIRB_CHECK_ARG(net && ptr && rows && channels, "resnet_peek: null pointer");
+  DIRB_CHECK_ARG(block >= -1 && block < (int)net->blocks.size(), "resnet_peek: bad block %d", block);
+  const ConvLayer* cv = nullptr;
+  bool act = false;
+  if (block < 0) {
+    if (which == 6) {
+      *ptr = net->pool_out; *rows = (int64_t)net->n * net->pool_h * net->pool_w; *channels = 64;
+      return DIRB200_OK;
+    }
+    cv = &net->stem; act = which == 1;
+  } else {
+    Block& B = net->blocks[block];
+    switch (which) {
+      case 0: cv = &B.c1; break;
+      case 1: cv = &B.c1; act = true; break;
+      case 2: cv = &B.c2; break;
+      case 3: cv = &B.c2; act = true; break;
+      case 4: cv = &B.c3; break;
+      case 5: DIRB_CHECK_ARG(B.has_ds, "resnet_peek: block has no downsample"); cv = &B.ds; break;
+      case 6: *ptr = B.out; *rows = B.c3.rows; *channels = B.c3.s.cout; return DIRB200_OK;
+      default: DIRB_CHECK_ARG(false, "resnet_peek: bad selector %d", which);
+    }
+  }
+  *ptr = act ? cv->a : cv->y;
+  *rows = cv->rows;
+  *channels = cv->s.cout;
+  DIRB_CHECK_ARG(*ptr, "resnet_peek: tensor not materialised");
+  return DIRB200_OK;
+}
+}

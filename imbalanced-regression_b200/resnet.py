@@ -37,6 +37,7 @@ _lib.register({
     "dirb200_resnet_device_bytes": (c_int64, [P]),
     "dirb200_resnet_forward": (c_int, [P, P, P, P, c_int, P, P]),
     "dirb200_resnet_backward": (c_int, [P, P, P, P, P]),
+    "dirb200_resnet_peek": (c_int, [P, c_int, c_int, P, P, P]),
     "dirb200_linear1_fwd": (c_int, [P, P, P, c_int64, c_int, P, P]),
     "dirb200_linear1_bwd": (c_int, [P, P, P, c_int64, c_int, P, P, P, P]),
     "dirb200_adam_step": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64,
@@ -324,6 +325,20 @@ class ResNet(nn.Module):
         g = g.detach().to(torch.float32).contiguous()
         _lib.call("dirb200_resnet_backward", self._net(shape), _lib.ptr(g), _lib.ptr(self._flat["params"]),
                   _lib.ptr(self._flat["grads"]), _lib.stream_ptr())
+
+    def peek(self, shape, block, which):
+        """Test aid: copy of an internal NHWC bf16 activation of the runner for input `shape`, as fp32 NCHW."""
+        ptr, rows, ch = c_void_p(), c_int64(), c_int()
+        _lib.call("dirb200_resnet_peek", self._net(tuple(shape)), block, which, ctypes.byref(ptr), ctypes.byref(rows),
+                  ctypes.byref(ch))
+
+        class _Arr:
+            __cuda_array_interface__ = dict(shape=(rows.value * ch.value,), typestr="<u2", data=(ptr.value, False),
+                                            version=2)
+        flat = torch.as_tensor(_Arr(), device=self._flat["params"].device).view(torch.bfloat16)
+        n = shape[0]
+        side = int(round((rows.value // n) ** 0.5))
+        return flat.float().view(n, side, side, ch.value).permute(0, 3, 1, 2).contiguous()
 
     # ---------------------------------------------------------------- forward
     def forward(self, x, targets=None, epoch=None):

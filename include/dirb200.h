@@ -202,6 +202,11 @@ int dirb200_resnet_forward(dirb200_net* net, const float* x_nchw, const float* p
 /* Backward of the above: d_enc fp32 [n, feature_dim]; ACCUMULATES into grads. */
 int dirb200_resnet_backward(dirb200_net* net, const float* d_enc, const float* params, float* grads, void* stream);
 
+/* Test / debugging aid: device pointer + shape ([rows][channels] bf16, NHWC) of an internal activation.
+ * block = -1: stem (0 = conv1 raw, 1 = relu(bn1), 6 = max-pool output); block >= 0: 0/1 = conv1 raw / act,
+ * 2/3 = conv2 raw / act, 4 = conv3 raw, 5 = downsample raw, 6 = block output. */
+int dirb200_resnet_peek(dirb200_net* net, int block, int which, void** ptr, int64_t* rows, int* channels);
+
 /* nn.Linear(feature_dim, 1) (resnet.py:88,148): pred[n] = x[n,d] . w[d] + bias */
 int dirb200_linear1_fwd(const float* x, const float* w, const float* bias, int64_t n, int d, float* pred,
                         void* stream);

@@ -46,45 +46,75 @@ def _bn(x, p, pre, stats, quant):
 
 
 def _q(x, quant):
-    """bf16 round trip of a stored activation (what the B200 path keeps in HBM)."""
+    """bf16 round trip of a stored activation (what the B200 path keeps in HBM);
+    straight-through in the backward."""
     if not quant:
         return x
     return x + (x.to(torch.bfloat16).float() - x).detach()
 
 
+class _RoundBoth(torch.autograd.Function):
+    """bf16 rounding of the value in the forward AND of the gradient in the
+    backward: the points where the B200 path stores a gradient tensor as bf16
+    (conv output grads dy, conv input grads from dgrad, the identity-branch dz,
+    the avg-pool / max-pool input grads)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).float()
+
+
+def _rb(x, quant):
+    return _RoundBoth.apply(x) if quant else x
+
+
 def _conv(x, w, stride, pad, quant):
     if quant:
         w = w + (w.to(torch.bfloat16).float() - w).detach()
-    return _q(F.conv2d(x, w, stride=stride, padding=pad), quant)
+    return _rb(F.conv2d(_rb(x, quant), w, stride=stride, padding=pad), quant)
 
 
-def forward_encoding(p, x, layers=LAYERS, stats=None, quant=False):
+def forward_encoding(p, x, layers=LAYERS, stats=None, quant=False, taps=None, force=None):
     """x [B,3,H,W] -> encoding [B,2048]; train-mode BN.  quant=True mimics the
     bf16 storage points of the B200 path (weights, conv outputs, activations)
     with straight-through rounding, so tolerances can be tight."""
+    def tap(name, t):
+        # `force`: teacher forcing -- substitute the value of a stored activation (keeping the gradient path), so
+        # that a backward comparison is not polluted by forward round-off flips of ReLU masks
+        if force is not None and name in force:
+            t = t + (force[name] - t).detach()
+        if taps is not None:
+            taps[name] = t.detach()
+        return t
     x = _q(x, quant)
-    x = _conv(x, p["conv1.weight"], 2, 3, quant)
-    x = _q(F.relu(_bn(x, p, "bn1.", stats, quant)), quant)
-    x = F.max_pool2d(x, 3, 2, 1)
+    x = tap("stem.y", _conv(x, p["conv1.weight"], 2, 3, quant))
+    x = tap("stem.a", _q(F.relu(_bn(x, p, "bn1.", stats, quant)), quant))
+    x = tap("stem.pool", F.max_pool2d(_rb(x, quant), 3, 2, 1))
+    bi = 0
     inplanes = 64
     for li, nblocks in enumerate(layers):
         planes = 64 << li
         for b in range(nblocks):
             stride = 2 if (b == 0 and li > 0) else 1
             pre = f"layer{li + 1}.{b}."
-            idn = x
-            o = _conv(x, p[pre + "conv1.weight"], 1, 0, quant)
-            o = _q(F.relu(_bn(o, p, pre + "bn1.", stats, quant)), quant)
-            o = _conv(o, p[pre + "conv2.weight"], stride, 1, quant)
-            o = _q(F.relu(_bn(o, p, pre + "bn2.", stats, quant)), quant)
-            o = _conv(o, p[pre + "conv3.weight"], 1, 0, quant)
+            idn = _rb(x, quant)
+            o = tap(f"{bi}.0", _conv(x, p[pre + "conv1.weight"], 1, 0, quant))
+            o = tap(f"{bi}.1", _q(F.relu(_bn(o, p, pre + "bn1.", stats, quant)), quant))
+            o = tap(f"{bi}.2", _conv(o, p[pre + "conv2.weight"], stride, 1, quant))
+            o = tap(f"{bi}.3", _q(F.relu(_bn(o, p, pre + "bn2.", stats, quant)), quant))
+            o = tap(f"{bi}.4", _conv(o, p[pre + "conv3.weight"], 1, 0, quant))
             o = _bn(o, p, pre + "bn3.", stats, quant)
             if pre + "downsample.0.weight" in p:
-                idn = _conv(x, p[pre + "downsample.0.weight"], stride, 0, quant)
+                idn = tap(f"{bi}.5", _conv(x, p[pre + "downsample.0.weight"], stride, 0, quant))
                 idn = _bn(idn, p, pre + "downsample.1.", stats, quant)
-            x = _q(F.relu(o + idn), quant)
+            x = tap(f"{bi}.6", _q(F.relu(o + idn), quant))
+            bi += 1
             inplanes = planes * 4
-    return x.mean(dim=(2, 3))          # AvgPool2d(7) on the 7x7 map + view
+    return _rb(x, quant).mean(dim=(2, 3))          # AvgPool2d(7) on the 7x7 map + view
 
 
 def forward(p, x, **kw):

@@ -13,13 +13,13 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def make_model(fds=False, **kw):
-    from resnet import resnet50
+def make_model(fds=False, layers=(3, 4, 6, 3), **kw):
+    from resnet import ResNet, Bottleneck
     args = dict(fds=fds, bucket_num=100, bucket_start=3, start_update=0, start_smooth=1, kernel="gaussian",
                 ks=9, sigma=1, momentum=0.9)
     args.update(kw)
     torch.manual_seed(0)
-    m = resnet50(**args)
+    m = ResNet(Bottleneck, list(layers), **args)
     with torch.no_grad():                       # non-trivial BN affine so its gradients are exercised
         for n, p in m.named_parameters():
             if p.dim() == 1 and ("bn" in n or "downsample.1" in n):
@@ -58,47 +58,150 @@ def test_state_dict_keys_match_reference_layout():
     assert m2.conv1.weight.data_ptr() == m2.flat_parameters().data_ptr()
 
 
-@pytest.mark.parametrize("n,hw", [(16, 64), (4, 224)])
-def test_forward_backward_vs_oracle(n, hw):
+def _fb(layers, n, hw):
     from oracle import resnet_ref as R
     import loss as L
-    m = make_model()
+    m = make_model(layers=layers)
     m.train()
     p = oracle_params(m)
     x = det_param(f"x{n}", (n, 3, hw, hw), 1.0).to(DEV)
     t = (torch.arange(n, dtype=torch.float32, device=DEV).reshape(n, 1) * 5 + 10)
     w = torch.linspace(0.5, 1.5, n, device=DEV).reshape(n, 1)
-
     pred = m(x, t, 0)
     loss = L.weighted_l1_loss(pred, t, w)
     loss.backward()
-
     stats = {}
-    rpred, renc = R.forward(p, x, stats=stats, quant=True)
+    rpred, renc = R.forward(p, x, layers=layers, stats=stats, quant=True)
     rloss = ((rpred - t).abs() * w).mean()
     rloss.backward()
-
     enc = m._run_forward(x, training=True)          # encoding (second pass, same batch statistics)
-    assert rel(enc, renc.detach()) < 2e-2, rel(enc, renc.detach())
-    assert cos(enc, renc.detach()) > 0.9995
-    assert abs(loss.item() - rloss.item()) < 2e-2 * abs(rloss.item()) + 1e-3
-    # BN running statistics of the first layer (momentum 0.1 from 0 / 1); two training forwards ran
-    rm = 0.9 * stats["bn1.running_mean"] + stats["bn1.running_mean"]
-    assert rel(m.bn1.running_mean, rm) < 2e-2
+    return m, p, stats, enc, renc.detach(), loss.item(), rloss.item()
+
+
+def test_forward_backward_vs_oracle_shallow():
+    """End-to-end fwd+bwd parity on a 6-block bottleneck net ([2,2,1,1]: identity blocks, stride-1 and stride-2
+    downsample blocks, stem, pools, regressor, loss).  A train-mode-BN ResNet at initialisation amplifies any
+    perturbation by ~1.15x per layer (measured with tests/debug_layers.py: 1e-4 after the first conv -> 0.3 after
+    all 16 blocks of ResNet-50 purely from bf16 round-off flips), so tight end-to-end tolerances are only
+    meaningful on a shallow stack; the full depth is covered layer by layer below."""
+    from oracle import resnet_ref as R
+    layers = (2, 2, 1, 1)
+    m, p, stats, enc, renc, loss, rloss = _fb(layers, 16, 64)
+    assert rel(enc, renc) < 4e-2 and cos(enc, renc) > 0.999, rel(enc, renc)
+    assert abs(loss - rloss) < 2e-2 * abs(rloss) + 1e-3
+    rm = 0.9 * stats["bn1.running_mean"] + stats["bn1.running_mean"]      # two training forwards
+    assert rel(m.bn1.running_mean, rm) < 1e-3
     assert int(m.bn1.num_batches_tracked) == 2
-    # gradients: every parameter tensor, relative L2 error and direction
     named = dict(m.named_parameters())
-    worst = 0.0
     for name, rp in p.items():
         g, rg = named[name].grad, rp.grad
         assert g is not None and torch.isfinite(g).all(), name
-        e = rel(g, rg)
-        worst = max(worst, e)
-        assert cos(g, rg) > 0.98, (name, cos(g, rg), e)
-    assert worst < 0.2, worst
-    # aggregate over the flat buffer is much tighter than the worst tensor
-    flat_ref = torch.cat([p[nm].grad.reshape(-1) for nm, _ in R.param_shapes()])
-    assert rel(m.flat_grads(), flat_ref) < 5e-2, rel(m.flat_grads(), flat_ref)
+        # 2 % forward round-off drift flips ~1.5 % of the ReLU masks => ~20-35 % gradient noise (see the
+        # teacher-forced test below for the tight comparison)
+        assert cos(g, rg) > 0.9 and rel(g, rg) < 0.5, (name, cos(g, rg), rel(g, rg))
+    flat_ref = torch.cat([p[nm].grad.reshape(-1) for nm, _ in R.param_shapes(layers)])
+    assert rel(m.flat_grads(), flat_ref) < 0.4, rel(m.flat_grads(), flat_ref)
+
+
+@pytest.mark.parametrize("n,hw", [(16, 64), (4, 224)])
+def test_resnet50_layerwise_forward_teacher_forced(n, hw):
+    """Every conv / BN+ReLU / residual stage of the full ResNet-50, each checked against the oracle op applied to
+    the runner's OWN input of that stage (so errors cannot compound): relative L2 error <= 4e-3 (a bf16 ulp)."""
+    from oracle import resnet_ref as R
+    import torch.nn.functional as F
+    m = make_model()
+    m.train()
+    p = {k: v.detach() for k, v in m.named_parameters()}
+    x = det_param(f"x{n}", (n, 3, hw, hw), 1.0).to(DEV)
+    m._run_forward(x, training=True)
+    shape = tuple(x.shape)
+    pk = lambda b, w: m.peek(shape, b, w)
+    q = lambda t: t.to(torch.bfloat16).float()
+    tol = 4e-3
+
+    def check(name, got, ref):
+        e = rel(got, ref)
+        assert e <= tol, (name, e)
+
+    with torch.no_grad():
+        check("stem.y", pk(-1, 0), R._conv(q(x), p["conv1.weight"], 2, 3, True))
+        check("stem.a", pk(-1, 1), q(F.relu(R._bn(pk(-1, 0), p, "bn1.", None, True))))
+        check("stem.pool", pk(-1, 6), F.max_pool2d(pk(-1, 1), 3, 2, 1))
+        bi = 0
+        for li, nblocks in enumerate((3, 4, 6, 3)):
+            for b in range(nblocks):
+                stride = 2 if (b == 0 and li > 0) else 1
+                pre = f"layer{li + 1}.{b}."
+                xin = pk(-1, 6) if bi == 0 else pk(bi - 1, 6)
+                check(pre + "conv1", pk(bi, 0), R._conv(xin, p[pre + "conv1.weight"], 1, 0, True))
+                check(pre + "bn1", pk(bi, 1), q(F.relu(R._bn(pk(bi, 0), p, pre + "bn1.", None, True))))
+                check(pre + "conv2", pk(bi, 2), R._conv(pk(bi, 1), p[pre + "conv2.weight"], stride, 1, True))
+                check(pre + "bn2", pk(bi, 3), q(F.relu(R._bn(pk(bi, 2), p, pre + "bn2.", None, True))))
+                check(pre + "conv3", pk(bi, 4), R._conv(pk(bi, 3), p[pre + "conv3.weight"], 1, 0, True))
+                o = R._bn(pk(bi, 4), p, pre + "bn3.", None, True)
+                if pre + "downsample.0.weight" in p:
+                    check(pre + "ds", pk(bi, 5), R._conv(xin, p[pre + "downsample.0.weight"], stride, 0, True))
+                    idn = R._bn(pk(bi, 5), p, pre + "downsample.1.", None, True)
+                else:
+                    idn = xin
+                check(pre + "out", pk(bi, 6), q(F.relu(o + idn)))
+                bi += 1
+        enc = m._run_forward(x, training=True)
+        check("avgpool", enc, pk(15, 6).mean(dim=(2, 3)))
+
+
+TAPS = [("stem.y", -1, 0), ("stem.a", -1, 1), ("stem.pool", -1, 6)]
+
+
+@pytest.mark.parametrize("layers,n,hw", [((3, 4, 6, 3), 16, 64), ((3, 4, 6, 3), 4, 224), ((2, 2, 1, 1), 16, 64)])
+def test_backward_vs_oracle_teacher_forced(layers, n, hw):
+    """Backward parity at full depth: the oracle's forward is teacher-forced to the runner's stored activations
+    (same ReLU masks, same BN inputs), its backward is torch autograd in fp32 with bf16 rounding at the points where
+    the runner stores bf16 gradients.  Every parameter gradient must then agree to bf16-level error."""
+    from oracle import resnet_ref as R
+    import loss as L
+    m = make_model(layers=layers)
+    m.train()
+    p = oracle_params(m)
+    x = det_param(f"x{n}", (n, 3, hw, hw), 1.0).to(DEV)
+    t = (torch.arange(n, dtype=torch.float32, device=DEV).reshape(n, 1) * 5 + 10)
+    w = torch.linspace(0.5, 1.5, n, device=DEV).reshape(n, 1)
+    pred = m(x, t, 0)
+    L.weighted_l1_loss(pred, t, w).backward()
+    force = {}
+    names = list(TAPS) + [(f"{b}.{k}", b, k) for b in range(sum(layers)) for k in range(7)]
+    for name, b, k in names:
+        try:
+            force[name] = m.peek(x.shape, b, k)
+        except Exception:
+            pass                                   # blocks without a downsample branch
+    assert len(force) == 3 + 6 * sum(layers) + 4
+    rpred, renc = R.forward(p, x, layers=layers, quant=True, force=force)
+    ((rpred - t).abs() * w).mean().backward()
+    assert rel(pred.detach(), rpred.detach()) < 2e-3
+    named = dict(m.named_parameters())
+    worst = ("", 1.0, 0.0)
+    for name, rp in p.items():
+        g, rg = named[name].grad, rp.grad
+        c, e = cos(g, rg), rel(g, rg)
+        if e > worst[2]:
+            worst = (name, c, e)
+    print('worst parameter gradient:', worst)
+    # bf16 round-off of the stored gradients is itself amplified ~1.1x per layer on the way back to the stem
+    assert worst[2] < 0.1 and worst[1] > 0.995, worst
+    flat_ref = torch.cat([p[nm].grad.reshape(-1) for nm, _ in R.param_shapes(layers)])
+    assert rel(m.flat_grads(), flat_ref) < 3e-2, rel(m.flat_grads(), flat_ref)
+
+
+def test_resnet50_end_to_end_sanity():
+    """Full depth, batch 4 at 224^2 (BASELINE config 1 shape): outputs and gradients stay aligned with the oracle
+    within what the chaotic amplification allows (see the shallow test's note)."""
+    m, p, stats, enc, renc, loss, rloss = _fb((3, 4, 6, 3), 4, 224)
+    assert cos(enc, renc) > 0.9 and np.isfinite(loss)
+    assert torch.isfinite(m.flat_grads()).all()
+    named = dict(m.named_parameters())
+    assert cos(named["linear.weight"].grad, p["linear.weight"].grad) > 0.9
+    assert rel(named["linear.bias"].grad, p["linear.bias"].grad) < 1e-3
 
 
 def test_eval_mode_and_no_grad_paths():
