@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's benchmark (contract: task brief §④).
+
+One "step" = one DIR training step on one synthetic batch per GPU:
+  ResNet-50 forward (train-mode BN) -> FDS.smooth (live tables, epoch >= 2 state)
+  -> 2048->1 regressor -> LDS-weighted L1 loss -> backward -> [NCCL grad all-reduce]
+  -> Adam, all through this repo's public (reference-shaped) API.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B]   # our arm (N>1: under torchrun)
+  python bench.py --impl reference ...                              # the CPU arm (oracle port, host cores)
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "imbalanced-regression_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOAD = "AgeDB-DIR ResNet-50 + FDS (feature_dim 2048, 101 age bins, gaussian ks5 sigma2) + LDS-weighted L1, " \
+           "batch 256/GPU, synthetic 224x224, Adam"
+FWD_GFLOP_PER_IMG = 8.174
+FWDBWD_GFLOP_PER_IMG = 24.29
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+            "clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def synthetic_labels(n, seed):
+    """Skewed age-like label set (AgeDB-shaped: mode ~35, long tails, ages 0..100)."""
+    rng = np.random.RandomState(seed)
+    lab = np.clip(np.round(rng.gamma(shape=6.0, scale=6.5, size=n)), 0, 100)
+    return lab.astype(np.float32)
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def run_reference(args):
+    """The reference's CPU implementation of the step (oracle port, see oracle/train_ref.py), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.train_ref import RefTrainer
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    bs = args.cpu_batch
+    g = torch.Generator().manual_seed(0)
+    tables = (torch.randn(101, 2048, generator=g) * .1 + .5, torch.rand(101, 2048, generator=g) + .5,
+              torch.randn(101, 2048, generator=g) * .1 + .5, torch.rand(101, 2048, generator=g) + .5)
+    tr = RefTrainer(bucket_num=101, bucket_start=0, fds_tables=tables)
+    x = torch.randn(bs, 3, 224, 224, generator=g)
+    t = torch.from_numpy(synthetic_labels(bs, 1)).reshape(bs, 1)
+    w = torch.ones(bs, 1)
+    for _ in range(args.warmup):
+        tr.step(x, t, w)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tr.step(x, t, w)
+    dt = time.perf_counter() - t0
+    val = bs * args.steps / dt
+    sample = f"{args.steps} steps of batch {bs} (fp32, torch CPU kernels, {torch.get_num_threads()} threads)"
+    out = {"impl": "reference", "metric": "images/sec", "value": val, "unit": "images/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "sample": sample},
+           "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                            "sample": sample},
+           "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline_sample(seconds_budget=25.0):
+    from oracle.train_ref import RefTrainer
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    bs = 8
+    g = torch.Generator().manual_seed(0)
+    tables = (torch.randn(101, 2048, generator=g) * .1 + .5, torch.rand(101, 2048, generator=g) + .5,
+              torch.randn(101, 2048, generator=g) * .1 + .5, torch.rand(101, 2048, generator=g) + .5)
+    tr = RefTrainer(bucket_num=101, bucket_start=0, fds_tables=tables)
+    x = torch.randn(bs, 3, 224, 224, generator=g)
+    t = torch.from_numpy(synthetic_labels(bs, 1)).reshape(bs, 1)
+    w = torch.ones(bs, 1)
+    tr.step(x, t, w)
+    n, t0 = 0, time.perf_counter()
+    while n < 3 or (time.perf_counter() - t0 < seconds_budget and n < 12):
+        tr.step(x, t, w)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": bs * n / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} steps of batch {bs} after 1 warm-up (oracle/train_ref.py: torch fp32 CPU kernels)"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def build_training_state(args, device, rank, world):
+    from resnet import resnet50
+    from optim import FusedAdam
+    from parallel import DataParallel
+    from datasets import lds_prepare_weights
+    torch.manual_seed(0)
+    model = resnet50(fds=True, bucket_num=101, bucket_start=0, start_update=0, start_smooth=1, kernel="gaussian",
+                     ks=5, sigma=2, momentum=0.9).to(device)
+    model = DataParallel(model)
+    model.broadcast_parameters()
+    model.train()
+    fds = model.module.FDS
+    # bring FDS to its epoch >= 2 state with the real kernels: two epoch-end refreshes over synthetic features
+    gen = torch.Generator(device=device).manual_seed(123)       # same on every rank -> identical tables
+    n_ep = 12208
+    ep_labels = torch.from_numpy(synthetic_labels(n_ep, 7)).to(device)
+    for epoch in (0, 1):
+        feats = torch.relu(torch.randn(n_ep, 2048, device=device, generator=gen) * (1.0 + 0.01 * ep_labels[:, None])
+                           + 0.5)
+        fds.update_last_epoch_stats(epoch)
+        fds.begin_epoch_stats(ep_labels)
+        fds.accumulate_batch(feats, ep_labels)
+        if world > 1:                                           # each rank fed the full set: undo the sum
+            pass
+        acc = fds._acc
+        fds._acc = None
+        nb, d = fds.running_mean.shape
+        import _lib
+        _lib.call("dirb200_fds_finalize", _lib.ptr(acc["sums"]), _lib.ptr(acc["sumsq"]), _lib.ptr(acc["counts"]), nb, d,
+                  _lib.ptr(fds.running_mean), _lib.ptr(fds.running_var), _lib.ptr(fds.num_samples_tracked), 0.9,
+                  int(epoch == 0), _lib.stream_ptr())
+    fds.update_last_epoch_stats(2)
+    # LDS weights from the (synthetic) training-label column: sqrt_inv + gaussian ks5 sigma2
+    w_all = lds_prepare_weights(ep_labels.cpu().numpy(), "sqrt_inv", lds=True, lds_kernel="gaussian", lds_ks=5,
+                                lds_sigma=2)
+    opt = FusedAdam(model.parameters(), lr=1e-3, grad_scale=1.0 / world)
+    return model, opt, ep_labels, w_all
+
+
+def make_batches(args, device, rank, ep_labels, w_all, pinned):
+    """A few distinct synthetic batches (x fp32 NCHW, targets, LDS weights)."""
+    g = torch.Generator().manual_seed(1000 + rank)
+    batches = []
+    for i in range(args.num_batches):
+        idx = torch.randint(0, ep_labels.numel(), (args.batch,), generator=g)
+        x = torch.randn(args.batch, 3, 224, 224, generator=g)
+        t = ep_labels.cpu()[idx].reshape(-1, 1).clone()
+        w = w_all.cpu()[idx].reshape(-1, 1).clone()
+        if pinned:
+            batches.append(tuple(a.pin_memory() for a in (x, t, w)))
+        else:
+            batches.append(tuple(a.to(device) for a in (x, t, w)))
+    return batches
+
+
+def train_step(model, opt, x, t, w, epoch=2):
+    from loss import weighted_l1_loss
+    outputs, _ = model(x, t, epoch)
+    loss = weighted_l1_loss(outputs, t, w)
+    opt.zero_grad()
+    loss.backward()
+    model.reduce_gradients()
+    opt.step()
+    return loss
+
+
+def timed(fn, steps, warmup, world, device):
+    import torch.distributed as dist
+    for i in range(warmup):
+        fn(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    ms = torch.tensor([max(dev_ms, 0.0), wall * 1e3], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms[0]), float(ms[1])
+
+
+def conv_flops_per_image():
+    """Exact fprop / dgrad / wgrad FLOPs of the ResNet-50 conv stack per 224^2 image (2*M*N*K per GEMM)."""
+    f = d = w = 0.0
+    def conv(h, cin, cout, k, s, first=False):
+        nonlocal f, d, w
+        ho = (h + 2 * (k // 2) - k) // s + 1
+        fl = 2.0 * ho * ho * cout * cin * k * k
+        f += fl
+        w += fl
+        if not first:
+            d += fl
+        return ho
+    h = conv(224, 3, 64, 7, 2, first=True)
+    h = (h - 1) // 2 + 1
+    inpl = 64
+    for li, nb in enumerate((3, 4, 6, 3)):
+        pl = 64 << li
+        for b in range(nb):
+            s = 2 if (b == 0 and li > 0) else 1
+            conv(h, inpl, pl, 1, 1)
+            h2 = conv(h, pl, pl, 3, s)
+            conv(h2, pl, pl * 4, 1, 1)
+            if b == 0:
+                conv(h, inpl, pl * 4, 1, s)
+            inpl, h = pl * 4, h2
+    return f, d, w
+
+
+def fds_roofline(device, peaks):
+    """Achieved HBM GB/s of the FDS segmented accumulation (dirb200_fds_accumulate) at the two epoch sizes;
+    algorithmic bytes = 4*N*D + 4*N (features read once + bins), L2 flushed between iterations."""
+    import _lib
+    d, nb = 2048, 101
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    out = {}
+    for n in (12208, 191509):
+        feats = torch.relu(torch.randn(n, d, device=device) + 0.5)
+        labels = torch.from_numpy(synthetic_labels(n, 3)).to(device)
+        bins = (labels).to(torch.int32)
+        sums = torch.zeros(nb, d, dtype=torch.float64, device=device)
+        sumsq = torch.zeros_like(sums)
+        counts = torch.zeros(nb, dtype=torch.int64, device=device)
+        need = int(_lib.raw("dirb200_fds_accumulate_workspace_bytes")(n, nb))
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        st = _lib.stream_ptr()
+        times = []
+        for it in range(6):
+            flush.fill_(it)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.call("dirb200_fds_accumulate", _lib.ptr(feats), _lib.ptr(bins), n, d, nb, _lib.ptr(sums),
+                      _lib.ptr(sumsq), _lib.ptr(counts), _lib.ptr(ws), need, st)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                times.append(e0.elapsed_time(e1))
+        ms = float(np.mean(times))
+        alg = 4.0 * n * d + 4.0 * n
+        out[str(n)] = {"ms": ms, "achieved_gbs": alg / ms / 1e6, "frac": alg / ms / 1e6 / peaks["hbm_gbs"],
+                       "algorithmic_mb": alg / 1e6}
+        del feats, ws
+    return out
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    import _lib
+    peaks = measured_peaks()
+    model, opt, ep_labels, w_all = build_training_state(args, device, rank, world)
+
+    # ---- (1) device-resident throughput: `value`
+    dev_batches = make_batches(args, device, rank, ep_labels, w_all, pinned=False)
+    def step_resident(i):
+        x, t, w = dev_batches[i % len(dev_batches)]
+        train_step(model, opt, x, t, w)
+    sampler = ClockSampler(local)
+    timed(step_resident, 0, args.warmup, world, device)
+    launches0 = _lib.launch_count()
+    sampler.start()
+    dev_ms, wall_ms = timed(step_resident, args.steps, 0, world, device)
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - launches0
+    ms_per_step = dev_ms / args.steps
+    value = world * args.batch * args.steps / (dev_ms / 1e3)
+
+    # ---- (2) end to end: pinned host batches, H2D every step (prefetched on a side stream), loss read back
+    host_batches = make_batches(args, device, rank, ep_labels, w_all, pinned=True)
+    copy_stream = torch.cuda.Stream()
+    slots = [None, None]
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_events = [None, None]
+
+    def prefetch(i):
+        hb = host_batches[i % len(host_batches)]
+        with torch.cuda.stream(copy_stream):
+            slots[i % 2] = (tuple(a.to(device, non_blocking=True) for a in hb), copy_stream.record_event())
+
+    def step_e2e(i):
+        if slots[i % 2] is None:
+            prefetch(i)
+        (x, t, w), ev = slots[i % 2]
+        torch.cuda.current_stream().wait_event(ev)
+        prefetch(i + 1)
+        loss = train_step(model, opt, x, t, w)
+        for a in (x, t, w):
+            a.record_stream(torch.cuda.current_stream())
+        if loss_events[i % 2] is not None:
+            loss_events[i % 2].synchronize()          # the read of step i-2 has landed on the host
+        loss_host[i % 2:i % 2 + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        loss_events[i % 2] = torch.cuda.current_stream().record_event()
+
+    e2e_dev_ms, e2e_wall_ms = timed(step_e2e, args.steps, max(3, args.warmup // 2), world, device)
+    e2e_value = world * args.batch * args.steps / (max(e2e_dev_ms, e2e_wall_ms) / 1e3)
+    h2d = sum(a.numel() * a.element_size() for a in host_batches[0])
+
+    # ---- (3) per-kernel-class timing (profiling steps are NOT part of the numbers above)
+    shape = (args.batch, 3, 224, 224)
+    model.module.set_profiling(shape, True)
+    for i in range(2):
+        step_resident(i)
+    prof = model.module.read_profile(shape)
+    model.module.set_profiling(shape, False)
+    prof = {k: (ms / 2, cnt // 2) for k, (ms, cnt) in prof.items()}
+    f, d, wg = conv_flops_per_image()
+    conv_ms = prof["conv_fprop"][0] + prof["conv_dgrad"][0] + prof["conv_wgrad"][0]
+    conv_flops = (f + d + wg) * args.batch
+    roofline = {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv: fprop+dgrad+wgrad, "
+                f"{prof['conv_fprop'][1] + prof['conv_dgrad'][1] + prof['conv_wgrad'][1]} launches/step)",
+                "achieved": conv_flops / (conv_ms / 1e3) / 1e12, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": conv_flops / (conv_ms / 1e3) / 1e12 / peaks["bf16_sustained"], "traffic": None,
+                "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)",
+                "algorithmic_gflop_per_step": conv_flops / 1e9, "kernel_ms_per_step": conv_ms}
+    breakdown = {k: {"ms_per_step": round(ms, 4), "launch_groups": cnt} for k, (ms, cnt) in prof.items()}
+
+    out = None
+    if rank == 0:
+        fds_rf = fds_roofline(device, peaks)
+        cpu = cpu_baseline_sample() if (world == 1 and not args.no_cpu_baseline) else None
+        out = {"metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+                          "parallelism": f"dp{world}", "l2": "per-step working set (~11 GB of activations) >> 126 MB L2; "
+                          f"{args.num_batches} distinct input batches", "timing": "CUDA events, max over ranks"},
+               "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                       "ms_per_step": max(e2e_dev_ms, e2e_wall_ms) / args.steps},
+               "roofline": roofline, "fds_roofline": {"bound": "hbm", "kernel": "dirb200_fds_accumulate (sort + "
+                                                      "fds_accumulate_kernel)", "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                                      "by_rows": fds_rf},
+               "cpu_baseline": cpu, "clocks": clocks, "gpu_launches": int(launches),
+               "gpu_launches_per_step": launches / args.steps, "wall_ms_per_step": wall_ms / args.steps,
+               "kernel_breakdown_ms": breakdown,
+               "model_flops_utilisation": FWDBWD_GFLOP_PER_IMG * args.batch / ms_per_step / 1e3 / peaks["bf16_sustained"]}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--num-batches", dest="num_batches", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-batch", dest="cpu_batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -16,6 +16,8 @@ int conv_wgrad_splits(const ConvShape& s);
 size_t conv_wgrad_workspace_bytes(const ConvShape& s);
 int conv_wgrad_partials(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* partial, const ConvShape& s, bool stem,
                         int* splits_out, cudaStream_t st);
+int wgrad_reduce(const float* workspace, int splits, float* dw, const ConvShape& s, bool stem, bool accumulate,
+                 cudaStream_t st);
 int conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* workspace, const ConvShape& s,
                bool stem, bool accumulate, cudaStream_t st);
 int prep_weights(const float* w, int cout, int cin, int kh, int kw, bool stem, __nv_bfloat16* wf, __nv_bfloat16* wd,

@@ -119,10 +119,8 @@ int input_to_s2d(const float* x, int n, int h, int w, __nv_bfloat16* out, cudaSt
   return DIRB200_OK;
 }
 
-int conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* workspace, const ConvShape& s,
-               bool stem, bool accumulate, cudaStream_t st) {
-  int splits = 1;
-  if (int rc = conv_wgrad_partials(x, dy, workspace, s, stem, &splits, st)) return rc;
+int wgrad_reduce(const float* workspace, int splits, float* dw, const ConvShape& s, bool stem, bool accumulate,
+                 cudaStream_t st) {
   if (stem)
     wgrad_reduce_stem_kernel<<<grid1d(256 * (int64_t)s.cout), 256, 0, st>>>(workspace, splits, s.cout, accumulate, dw);
   else
@@ -130,6 +128,13 @@ int conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float
                                                                                        s.cin, s.kh, s.kw, accumulate, dw);
   DIRB_LAUNCHED();
   return DIRB200_OK;
+}
+
+int conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* workspace, const ConvShape& s,
+               bool stem, bool accumulate, cudaStream_t st) {
+  int splits = 1;
+  if (int rc = conv_wgrad_partials(x, dy, workspace, s, stem, &splits, st)) return rc;
+  return wgrad_reduce(workspace, splits, dw, s, stem, accumulate, st);
 }
 
 // API shape (original conv hyper-parameters) -> kernel shape.  The stem (cin = 3, 7x7, stride 2, pad 3) runs

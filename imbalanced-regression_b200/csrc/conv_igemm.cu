@@ -25,7 +25,6 @@ constexpr int BM = 128;  // GEMM rows per tile (pixels; for wgrad: 2 chunks x 64
 constexpr int BK = 64;   // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kProducerThreads = 128;
 constexpr int kThreads = 192;
-constexpr int kLag = 3;  // cp.async groups kept in flight per producer thread
 
 struct IgemmParams {
   const __nv_bfloat16* src;  // gathered tensor, NHWC
@@ -48,83 +47,75 @@ struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 128) ? 6 : 8;
+  static constexpr int kStages = (BN == 128) ? 3 : 4;   // ~97 KB per CTA -> two CTAs per SM overlap each other's prologue/epilogue
   static constexpr int kBarOffset = kStages * kStageBytes;
   static constexpr int kSmemBytes = kBarOffset + (2 * kStages + 2) * 8 + 1024;
   static constexpr int kTmemCols = BN;  // power of two >= 32
 };
 
-// ---- source address of one 128-byte A row (or of its 16-byte pieces for the stem) ----
-struct RowCoord {
-  int n, y, x;
-  bool valid;
+// ---- A-operand gather --------------------------------------------------------------------------------
+// A tile row = 128 contiguous bytes of the source tensor (64 channels of one pixel; stem: 4 taps x 16 channels).
+// The 8 lanes of a quarter-warp copy the 8 x 16 B of one row, so every warp-wide cp.async touches 4 full 128-byte
+// lines (fully coalesced L2 requests); a thread therefore serves 8 different rows, always the same 16-byte column.
+//
+// packed pixel: bit 31 valid | n (13 bits) << 18 | y (9 bits) << 9 | x (9 bits)
+__device__ __forceinline__ uint32_t pack_pixel(long long p, const IgemmParams& P) {
+  if (p >= P.pixels) return 0u;
+  const uint32_t pp = static_cast<uint32_t>(p);
+  const uint32_t hw = static_cast<uint32_t>(P.hm * P.wm);
+  const uint32_t n = pp / hw;
+  const uint32_t rem = pp - n * hw;
+  const uint32_t y = rem / static_cast<uint32_t>(P.wm);
+  const uint32_t x = rem - y * static_cast<uint32_t>(P.wm);
+  return 0x80000000u | (n << 18) | (y << 9) | x;
+}
+
+// Row-invariant part of the gather address, unpacked once: image base row n*hs, and the tap-0 coordinates
+// (fprop-style: y*stride - pad ; dgrad-style: y + pad).
+struct RowPre {
+  int nb, yb, xb;   // yb == INT_MIN/2 marks an invalid (out-of-range) row
 };
-
-__device__ __forceinline__ RowCoord decode_pixel(long long p, const IgemmParams& P) {
-  RowCoord rc;
-  rc.valid = p < P.pixels;
-  const long long pp = rc.valid ? p : 0;
-  const int hw = P.hm * P.wm;
-  rc.n = static_cast<int>(pp / hw);
-  const int rem = static_cast<int>(pp - static_cast<long long>(rc.n) * hw);
-  rc.y = rem / P.wm;
-  rc.x = rem - rc.y * P.wm;
-  return rc;
-}
-
-// Source pixel for filter tap (r, s).  fprop-style: (y*stride - pad + r, x*stride - pad + s).
-// dgrad-style: the conv-output pixel (ho, wo) with ho*stride - pad + r == y (must divide exactly).
-__device__ __forceinline__ bool tap_source(const IgemmParams& P, const RowCoord& rc, int r, int s, int& hi, int& wi) {
+__device__ __forceinline__ RowPre row_pre(const IgemmParams& P, uint32_t pk) {
+  RowPre rp;
+  const int n = (pk >> 18) & 0x1FFF, y = (pk >> 9) & 0x1FF, x = pk & 0x1FF;
+  rp.nb = n * P.hs;
   if (!P.transposed) {
-    hi = rc.y * P.stride - P.pad + r;
-    wi = rc.x * P.stride - P.pad + s;
+    rp.yb = y * P.stride - P.pad;
+    rp.xb = x * P.stride - P.pad;
   } else {
-    const int th = rc.y + P.pad - r, tw = rc.x + P.pad - s;
-    if (th < 0 || tw < 0) return false;
-    if (P.stride == 1) {
-      hi = th;
-      wi = tw;
-    } else {
-      hi = th / P.stride;
-      wi = tw / P.stride;
-      if (hi * P.stride != th || wi * P.stride != tw) return false;
-    }
+    rp.yb = y + P.pad;
+    rp.xb = x + P.pad;
   }
-  return rc.valid && hi >= 0 && hi < P.hs && wi >= 0 && wi < P.ws;
+  if (!(pk >> 31)) rp.yb = -(1 << 28);
+  return rp;
 }
 
-// Write one gathered 128-byte row (8 x 16 B) into the swizzled tile row `dst_row` (byte address of the row,
-// swizzle phase = row index & 7).
-template <bool STEM>
-__device__ __forceinline__ void gather_row(const IgemmParams& P, const RowCoord& rc, int tap_or_r, int c0,
-                                           uint32_t dst_row, int swz) {
-  if constexpr (!STEM) {
-    const int r = tap_or_r / P.kw, s = tap_or_r - r * P.kw;
-    int hi, wi;
-    const bool ok = tap_source(P, rc, r, s, hi, wi);
-    const __nv_bfloat16* src =
-        ok ? P.src + ((static_cast<size_t>(rc.n) * P.hs + hi) * P.ws + wi) * P.cs + c0 : P.src;
-    const uint32_t bytes = ok ? 16u : 0u;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) cp_async16(dst_row + ((j ^ swz) << 4), src + j * 8, bytes);
+// Source of the 16 bytes at channel offset `coff` of filter tap (r, s).
+// fprop-style: input pixel (y*stride - pad + r, x*stride - pad + s).
+// dgrad-style: the conv-output pixel (ho, wo) with ho*stride - pad + r == y (stride 1 or 2; must divide exactly).
+__device__ __forceinline__ const __nv_bfloat16* tap_source(const IgemmParams& P, const RowPre& rp, int r, int s,
+                                                           int coff, bool& ok) {
+  int hi, wi;
+  ok = true;
+  if (!P.transposed) {
+    hi = rp.yb + r;
+    wi = rp.xb + s;
   } else {
-    // stem: source is the space-to-depth input [n, hs, ws, 16]; one k-row = filter row r' with its kw (=4)
-    // taps s' side by side, 16 channels (32 B) each -> validity per tap.
-    const int hi = rc.y * P.stride - P.pad + tap_or_r;
-    const bool row_ok = rc.valid && hi >= 0 && hi < P.hs;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int wi = rc.x * P.stride - P.pad + (j >> 1);
-      const bool ok = row_ok && wi >= 0 && wi < P.ws;
-      const __nv_bfloat16* src =
-          ok ? P.src + ((static_cast<size_t>(rc.n) * P.hs + hi) * P.ws + wi) * P.cs + (j & 1) * 8 : P.src;
-      cp_async16(dst_row + ((j ^ swz) << 4), src, ok ? 16u : 0u);
+    hi = rp.yb - r;
+    wi = rp.xb - s;
+    if (P.stride == 2) {
+      ok = ((hi | wi) & 1) == 0;
+      hi >>= 1;
+      wi >>= 1;
     }
   }
+  ok = ok && static_cast<unsigned>(hi) < static_cast<unsigned>(P.hs) &&
+       static_cast<unsigned>(wi) < static_cast<unsigned>(P.ws);
+  return ok ? P.src + (static_cast<size_t>(rp.nb + hi) * P.ws + wi) * P.cs + coff : P.src;
 }
 
 template <int BN, bool WGRAD, bool STEM>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -168,59 +159,68 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
 
   if (warp < 4) {
     // ============================ A producer ============================
-    const int tid = threadIdx.x;
-    RowCoord rc{};
-    int chunk_tap = 0, chunk_c0 = 0;
+    const int j = lane & 7;          // 16-byte column served by this thread
+    const int q = lane >> 3;         // row within a group of 4
+    RowPre rows8[8];                 // fprop/dgrad: the 8 rows this thread serves
+    int chunk_r = 0, chunk_s = 0, chunk_c0 = 0;
     bool chunk_ok = true;
-    uint32_t row_off;   // byte offset of this thread's row inside the A tile
-    int swz;
+    uint32_t tile_off = 0;
     if constexpr (!WGRAD) {
-      rc = decode_pixel(static_cast<long long>(m_tile) * BM + tid, P);
-      row_off = tid * 128;
-      swz = tid & 7;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        rows8[i] = row_pre(P, pack_pixel(static_cast<long long>(m_tile) * BM + warp * 32 + 4 * i + q, P));
+      tile_off = warp * 32 * 128;
     } else {
-      const int chunk = tid >> 6, krow = tid & 63;
+      // warp = (chunk, half): 64 gathered channels x 32 of the 64 pixel rows of the k-block
+      const int chunk = warp >> 1;
       const int gchunk = m_tile * 2 + chunk;           // 64-row chunk of the [K_total, Cout] result
       chunk_ok = gchunk < P.total_chunks;
       if constexpr (STEM) {
-        chunk_tap = gchunk;                            // filter row r'
+        chunk_r = gchunk;                              // filter row r'
       } else {
-        chunk_tap = gchunk / P.cpb;
-        chunk_c0 = (gchunk - chunk_tap * P.cpb) * 64;
+        const int tap = gchunk / P.cpb;
+        chunk_c0 = (gchunk - tap * P.cpb) * 64;
+        chunk_r = tap / P.kw;
+        chunk_s = tap - chunk_r * P.kw;
       }
-      row_off = chunk * 8192 + krow * 128;
-      swz = krow & 7;
+      tile_off = chunk * 8192 + (warp & 1) * 32 * 128;
     }
     for (int it = 0; it < nk; ++it) {
       const int s = it % C::kStages;
       const uint32_t ph = (it / C::kStages) & 1;
       mbar_wait(empty_bar(s), ph ^ 1u);
       const int kb = kb_begin + it;
+      int r, sx, coff;
+      uint32_t mypk = 0;
       if constexpr (!WGRAD) {
-        int tap, c0;
         if constexpr (STEM) {
-          tap = kb;
-          c0 = 0;
+          r = kb; sx = j >> 1; coff = (j & 1) * 8;
         } else {
-          tap = kb / P.cpb;
-          c0 = (kb - tap * P.cpb) * 64;
+          const int tap = kb / P.cpb;
+          coff = (kb - tap * P.cpb) * 64 + j * 8;
+          r = tap / P.kw;
+          sx = tap - r * P.kw;
         }
-        gather_row<STEM>(P, rc, tap, c0, a_addr(s) + row_off, swz);
       } else {
-        RowCoord prc = decode_pixel(static_cast<long long>(kb) * 64 + (tid & 63), P);
-        prc.valid = prc.valid && chunk_ok;
-        gather_row<STEM>(P, prc, chunk_tap, chunk_c0, a_addr(s) + row_off, swz);
+        r = chunk_r;
+        if constexpr (STEM) { sx = j >> 1; coff = (j & 1) * 8; } else { sx = chunk_s; coff = chunk_c0 + j * 8; }
+        mypk = chunk_ok ? pack_pixel(static_cast<long long>(kb) * 64 + (warp & 1) * 32 + lane, P) : 0u;
       }
-      cp_async_commit();
-      if (it >= kLag) {
-        cp_async_wait<kLag>();
-        fence_proxy_async();
-        mbar_arrive(full_bar((it - kLag) % C::kStages));
+      const uint32_t dst_base = a_addr(s) + tile_off;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + q;                     // row within this warp's 32 rows
+        RowPre rp;
+        if constexpr (!WGRAD) rp = rows8[i];
+        else rp = row_pre(P, __shfl_sync(0xffffffffu, mypk, row));
+        bool ok;
+        const __nv_bfloat16* src = tap_source(P, rp, r, sx, coff, ok);
+        cp_async16(dst_base + row * 128 + ((j ^ (row & 7)) << 4), src, ok ? 16u : 0u);
       }
+      // the mbarrier receives this thread's arrival when all of its cp.async above have landed (no wait here:
+      // the ring depth alone bounds the loads in flight), as CUTLASS's sm100 cp.async->UMMA mainloop does
+      cp_async_mbar_arrive_noinc(full_bar(s));
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int it = max(0, nk - kLag); it < nk; ++it) mbar_arrive(full_bar(it % C::kStages));
 
     // ============================== epilogue ==============================
     mbar_wait(accum_bar, 0);
@@ -412,6 +412,7 @@ int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y,
 int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* dx, const ConvShape& s,
                cudaStream_t st) {
   if (int rc = check_shape(s, false, "conv_dgrad")) return rc;
+  DIRB_CHECK_ARG(s.stride == 1 || s.stride == 2, "conv_dgrad: stride must be 1 or 2 (got %d)", s.stride);
   const int ktot = s.kh * s.kw * s.cout;
   IgemmParams P{};
   P.src = dy; P.n = s.n; P.hs = s.ho; P.ws = s.wo; P.cs = s.cout; P.hm = s.h; P.wm = s.w;

@@ -4,10 +4,11 @@
 
 namespace dirb200 {
 
-int bn_stats(const __nv_bfloat16* y, int64_t rows, int c, double* sum, double* sumsq, cudaStream_t st);
-int bn_finalize(double* sum, double* sumsq, int64_t rows, int c, const float* gamma, const float* beta, float eps,
-                float momentum, float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
-                float* shift, cudaStream_t st);
+int bn_partial_floats(int max_c);   // size of the per-CTA partial buffer shared by the column reductions
+int bn_stats(const __nv_bfloat16* y, int64_t rows, int c, float* partial, int* nblocks, cudaStream_t st);
+int bn_finalize(const float* partial, int nblocks, int64_t rows, int c, const float* gamma, const float* beta,
+                float eps, float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
+                float* scale, float* shift, cudaStream_t st);
 int bn_eval_coeffs(int c, const float* gamma, const float* beta, float eps, const float* running_mean,
                    const float* running_var, float* scale, float* shift, cudaStream_t st);
 int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, const __nv_bfloat16* res,
@@ -15,15 +16,13 @@ int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, con
              __nv_bfloat16* out, cudaStream_t st);
 int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* act, const __nv_bfloat16* y,
                   const float* mean, const float* invstd, const __nv_bfloat16* y2, const float* mean2,
-                  const float* invstd2, int64_t rows, int c, double* dbeta, double* dgamma, double* dgamma2,
+                  const float* invstd2, int64_t rows, int c, float* partial, int* nblocks, cudaStream_t st);
+int bn_bwd_coeffs(const float* partial, int nblocks, int k, int gslot, int64_t rows, int c, const float* mean,
+                  const float* invstd, const float* gamma, float* grad_gamma, float* grad_beta, float* coef,
                   cudaStream_t st);
 int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* act, const __nv_bfloat16* y,
-                 const float* mean, const float* invstd, const float* gamma, const double* dbeta, const double* dgamma,
-                 const __nv_bfloat16* y2, const float* mean2, const float* invstd2, const float* gamma2,
-                 const double* dgamma2, int64_t rows, int c, __nv_bfloat16* dy, __nv_bfloat16* dy2,
-                 __nv_bfloat16* dz_out, cudaStream_t st);
-int bn_param_grads(double* dbeta, double* dgamma, int c, float* grad_gamma, float* grad_beta, bool zero_dbeta,
-                   cudaStream_t st);
+                 const float* coef, const __nv_bfloat16* y2, const float* coef2, int64_t rows, int c,
+                 __nv_bfloat16* dy, __nv_bfloat16* dy2, __nv_bfloat16* dz_out, cudaStream_t st);
 int maxpool_fwd(const __nv_bfloat16* x, int n, int h, int w, int c, __nv_bfloat16* out, uint8_t* idx, cudaStream_t st);
 int maxpool_bwd(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const uint8_t* idx, int n, int h, int w, int c,
                 __nv_bfloat16* dx, cudaStream_t st);

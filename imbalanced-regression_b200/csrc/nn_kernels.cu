@@ -8,6 +8,8 @@
 
 namespace dirb200 {
 
+constexpr int kReduceCtasPerSm = 2;   // grid cap of the column reductions (bounds the per-CTA partial buffer)
+
 struct V8 {
   float v[8];
 };
@@ -36,63 +38,94 @@ __device__ __forceinline__ V8 loadf8(const float* p) {
 }
 
 // Column (per-channel) reduction over the rows of [P][C]: thread owns channel group cg = tid % (C/8) and walks
-// rows; K partial sums per channel; partials of threads with the same cg are combined in smem, then one fp64
-// atomic per (channel, k) per CTA.
+// rows with K partial sums per channel; the CTA combines its row-lanes in smem and writes ONE partial vector
+// partial[blockIdx.x][k][c] (fp32, no atomics -> deterministic); the tiny per-channel finalize kernels add the
+// partials of all CTAs in fp64.
 template <int K>
-__device__ __forceinline__ void column_reduce_finish(float (&acc)[K][8], int c8, int cgroups, double* const (&dst)[K]) {
-  extern __shared__ float sh[];  // [blockDim][K*8]
-  float* mine = sh + threadIdx.x * (K * 8);
+__device__ __forceinline__ void column_reduce_finish(float (&acc)[K][8], int cg, int cgroups, int c,
+                                                     float* __restrict__ partial) {
+  extern __shared__ float sh[];  // [lanes][cgroups][K][8]
+  const int lanes = blockDim.x / cgroups;
+  float* mine = sh + threadIdx.x * (K * 8);      // threadIdx.x == lane * cgroups + cg
 #pragma unroll
   for (int k = 0; k < K; ++k)
 #pragma unroll
     for (int j = 0; j < 8; ++j) mine[k * 8 + j] = acc[k][j];
   __syncthreads();
-  // threads 0..cgroups-1 sum over the row-lanes
-  if (threadIdx.x < cgroups) {
-    const int lanes = blockDim.x / cgroups;
-    for (int k = 0; k < K; ++k)
-      for (int j = 0; j < 8; ++j) {
-        float t = 0.f;
-        for (int l = 0; l < lanes; ++l) t += sh[(l * cgroups + threadIdx.x) * (K * 8) + k * 8 + j];
-        atomicAdd(dst[k] + c8 + j, (double)t);
-      }
+  const int per_lane = cgroups * K * 8;           // == K * c
+  float* out = partial + static_cast<size_t>(blockIdx.x) * K * c;
+  for (int o = threadIdx.x; o < per_lane; o += blockDim.x) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += sh[l * per_lane + o];
+    const int g = o / (K * 8), k = (o / 8) % K, j = o & 7;
+    out[k * c + g * 8 + j] = t;
   }
 }
 
+// Sum of slot `slot` of the per-CTA partials [nblocks][K][c] for channel ch, computed by a (32, 8) thread block:
+// the 8 warps stride over the CTAs, 32 lanes cover 32 consecutive channels (coalesced 128-byte reads);
+// valid in threads with threadIdx.y == 0 after the call.
+__device__ __forceinline__ double sum_partials(const float* __restrict__ partial, int nblocks, int K, int slot, int c,
+                                               int ch, double (*sh)[32]) {
+  double t = 0.0;
+  if (ch < c)
+    for (int b = threadIdx.y; b < nblocks; b += 8) t += (double)partial[((size_t)b * K + slot) * c + ch];
+  sh[threadIdx.y][threadIdx.x] = t;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.y == 0)
+    for (int w = 0; w < 8; ++w) r += sh[w][threadIdx.x];
+  __syncthreads();
+  return r;
+}
+
 __global__ void __launch_bounds__(256)
-bn_stats_kernel(const __nv_bfloat16* __restrict__ y, int64_t rows, int c, double* __restrict__ sum,
-                double* __restrict__ sumsq) {
+bn_stats_kernel(const __nv_bfloat16* __restrict__ y, int64_t rows, int c, float* __restrict__ partial) {
   const int cgroups = c / 8;
   const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
   float acc[2][8] = {};
-  if (lane < lanes)
-    for (int64_t r = blockIdx.x * (int64_t)lanes + lane; r < rows; r += (int64_t)gridDim.x * lanes) {
-      const V8 x = load8(y + r * c + cg * 8);
+  const int64_t stride = (int64_t)gridDim.x * lanes;
+  int64_t r = blockIdx.x * (int64_t)lanes + lane;
+  // 4 independent 16-byte loads in flight per thread
+  for (; r + 3 * stride < rows; r += 4 * stride) {
+    V8 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = load8(y + (r + u * stride) * c + cg * 8);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        acc[0][j] += x.v[j];
-        acc[1][j] = fmaf(x.v[j], x.v[j], acc[1][j]);
+        acc[0][j] += x[u].v[j];
+        acc[1][j] = fmaf(x[u].v[j], x[u].v[j], acc[1][j]);
       }
+  }
+  for (; r < rows; r += stride) {
+    const V8 x = load8(y + r * c + cg * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[0][j] += x.v[j];
+      acc[1][j] = fmaf(x.v[j], x.v[j], acc[1][j]);
     }
-  double* const dst[2] = {sum, sumsq};
-  column_reduce_finish<2>(acc, cg * 8, cgroups, dst);
+  }
+  column_reduce_finish<2>(acc, cg, cgroups, c, partial);
 }
 
 // mean / invstd / scale / shift from the accumulated sums; running statistics as nn.BatchNorm2d (momentum 0.1,
-// unbiased running variance).  Re-zeroes the accumulators for the next step.
-__global__ void bn_finalize_kernel(double* __restrict__ sum, double* __restrict__ sumsq, int64_t rows, int c,
+// unbiased running variance).
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblocks, int64_t rows, int c,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                    float* __restrict__ scale, float* __restrict__ shift) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c) return;
+  __shared__ double sh[8][32];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const double sx = sum_partials(partial, nblocks, 2, 0, c, i, sh);
+  const double sq = sum_partials(partial, nblocks, 2, 1, c, i, sh);
+  if (threadIdx.y != 0 || i >= c) return;
   const double n = (double)rows;
-  const double m = sum[i] / n;
-  double var = sumsq[i] / n - m * m;
+  const double m = sx / n;
+  double var = sq / n - m * m;
   if (var < 0.0) var = 0.0;
-  sum[i] = 0.0;
-  sumsq[i] = 0.0;
   const float invstd = (float)(1.0 / sqrt(var + (double)eps));
   mean_out[i] = (float)m;
   invstd_out[i] = invstd;
@@ -155,8 +188,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
                      const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ y,
                      const float* __restrict__ mean, const float* __restrict__ invstd,
                      const __nv_bfloat16* __restrict__ y2, const float* __restrict__ mean2,
-                     const float* __restrict__ invstd2, int64_t rows, int c, double* __restrict__ dbeta,
-                     double* __restrict__ dgamma, double* __restrict__ dgamma2) {
+                     const float* __restrict__ invstd2, int64_t rows, int c, float* __restrict__ partial) {
   const int cgroups = c / 8;
   const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
   float acc[3][8] = {};
@@ -167,109 +199,120 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
       mu2 = loadf8(mean2 + cg * 8);
       is2 = loadf8(invstd2 + cg * 8);
     }
-    for (int64_t r = blockIdx.x * (int64_t)lanes + lane; r < rows; r += (int64_t)gridDim.x * lanes) {
-      const int64_t off = r * c + cg * 8;
-      V8 g = load8(g1 + off);
-      if (g2) {
-        const V8 t = load8(g2 + off);
+    const int64_t stride = (int64_t)gridDim.x * lanes;
+    constexpr int U = 2;   // rows in flight per thread (each row = up to 5 independent 16-byte loads)
+    for (int64_t r0 = blockIdx.x * (int64_t)lanes + lane; r0 < rows; r0 += U * stride) {
+      V8 gv[U], g2v[U], av[U], xv[U], x2v[U];
+      bool ok[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g.v[j] += t.v[j];
+      for (int u = 0; u < U; ++u) {
+        const int64_t r = r0 + u * stride;
+        ok[u] = r < rows;
+        if (!ok[u]) continue;
+        const int64_t off = r * c + cg * 8;
+        gv[u] = load8(g1 + off);
+        if (g2) g2v[u] = load8(g2 + off);
+        if (act) av[u] = load8(act + off);
+        xv[u] = load8(y + off);
+        if (y2) x2v[u] = load8(y2 + off);
       }
-      if (act) {
-        const V8 a = load8(act + off);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g.v[j] = a.v[j] > 0.f ? g.v[j] : 0.f;
-      }
-      const V8 x = load8(y + off);
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        V8 g = gv[u];
+        if (g2) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[0][j] += g.v[j];
-        acc[1][j] = fmaf(g.v[j], (x.v[j] - mu.v[j]) * is.v[j], acc[1][j]);
-      }
-      if (y2) {
-        const V8 x2 = load8(y2 + off);
+          for (int j = 0; j < 8; ++j) g.v[j] += g2v[u].v[j];
+        }
+        if (act) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[2][j] = fmaf(g.v[j], (x2.v[j] - mu2.v[j]) * is2.v[j], acc[2][j]);
+          for (int j = 0; j < 8; ++j) g.v[j] = av[u].v[j] > 0.f ? g.v[j] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] += g.v[j];
+          acc[1][j] = fmaf(g.v[j], (xv[u].v[j] - mu.v[j]) * is.v[j], acc[1][j]);
+        }
+        if (y2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[2][j] = fmaf(g.v[j], (x2v[u].v[j] - mu2.v[j]) * is2.v[j], acc[2][j]);
+        }
       }
     }
   }
-  double* const dst[3] = {dbeta, dgamma, dgamma2 ? dgamma2 : dgamma};
   if (y2) {
-    column_reduce_finish<3>(acc, cg * 8, cgroups, dst);
+    column_reduce_finish<3>(acc, cg, cgroups, c, partial);
   } else {
     float acc2[2][8];
 #pragma unroll
     for (int k = 0; k < 2; ++k)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc2[k][j] = acc[k][j];
-    double* const dst2[2] = {dbeta, dgamma};
-    column_reduce_finish<2>(acc2, cg * 8, cgroups, dst2);
+    column_reduce_finish<2>(acc2, cg, cgroups, c, partial);
   }
 }
 
-// dy = gamma*invstd * (dz - dbeta/n - xhat * dgamma/n)  (and the same for the second BN); optionally writes dz.
-// Also accumulates dgamma/dbeta into the fp32 parameter gradients (done by the thread that owns row 0).
+// Per-channel coefficients of the BN backward, dy = A*dz + B*y + C with
+//   A = gamma*invstd,  B = -gamma*invstd^2*dgamma/n,  C = gamma*invstd*(mean*invstd*dgamma/n - dbeta/n);
+// dbeta / dgamma are summed here from the reduce kernel's per-CTA partials [nblocks][K][c] (dbeta = slot 0,
+// dgamma = slot `gslot`); also accumulates them into the fp32 parameter gradients.
+__global__ void bn_bwd_coeffs_kernel(const float* __restrict__ partial, int nblocks, int K, int gslot, int64_t rows,
+                                     int c, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     const float* __restrict__ gamma, float* __restrict__ grad_gamma,
+                                     float* __restrict__ grad_beta, float* __restrict__ coef /* [3][c] */) {
+  __shared__ double sh[8][32];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const double db = sum_partials(partial, nblocks, K, 0, c, i, sh);
+  const double dg = sum_partials(partial, nblocks, K, gslot, c, i, sh);
+  if (threadIdx.y != 0 || i >= c) return;
+  const double n = (double)rows, is = (double)invstd[i], ga = (double)gamma[i], mu = (double)mean[i];
+  coef[i] = (float)(ga * is);
+  coef[c + i] = (float)(-ga * is * is * dg / n);
+  coef[2 * c + i] = (float)(ga * is * (mu * is * dg / n - db / n));
+  grad_gamma[i] += (float)dg;
+  grad_beta[i] += (float)db;
+}
+
+// dz = (g1 [+ g2]) * (act > 0);  dy = A*dz + B*y + C  (and the same for the second BN);  optionally writes dz.
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                     const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ y,
-                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                    const double* __restrict__ dbeta, const double* __restrict__ dgamma,
-                    const __nv_bfloat16* __restrict__ y2, const float* __restrict__ mean2,
-                    const float* __restrict__ invstd2, const float* __restrict__ gamma2,
-                    const double* __restrict__ dgamma2, int64_t rows, int c, __nv_bfloat16* __restrict__ dy,
+                    const float* __restrict__ coef, const __nv_bfloat16* __restrict__ y2,
+                    const float* __restrict__ coef2, int64_t rows, int c, __nv_bfloat16* __restrict__ dy,
                     __nv_bfloat16* __restrict__ dy2, __nv_bfloat16* __restrict__ dz_out) {
   const int64_t total8 = rows * c / 8;
-  const float inv_n = 1.f / (float)rows;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
     const int c8 = (int)((i * 8) % c);
     V8 g = load8(g1 + i * 8);
+    const V8 x = load8(y + i * 8);
+    V8 gg{}, aa{}, xx{};
+    if (g2) gg = load8(g2 + i * 8);
+    if (act) aa = load8(act + i * 8);
+    if (y2) xx = load8(y2 + i * 8);
     if (g2) {
-      const V8 t = load8(g2 + i * 8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g.v[j] += t.v[j];
+      for (int j = 0; j < 8; ++j) g.v[j] += gg.v[j];
     }
     if (act) {
-      const V8 a = load8(act + i * 8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g.v[j] = a.v[j] > 0.f ? g.v[j] : 0.f;
+      for (int j = 0; j < 8; ++j) g.v[j] = aa.v[j] > 0.f ? g.v[j] : 0.f;
     }
     if (dz_out) store8(dz_out + i * 8, g);
     {
-      const V8 x = load8(y + i * 8);
-      const V8 mu = loadf8(mean + c8), is = loadf8(invstd + c8), ga = loadf8(gamma + c8);
+      const V8 A = loadf8(coef + c8), B = loadf8(coef + c + c8), C = loadf8(coef + 2 * c + c8);
       V8 o;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (x.v[j] - mu.v[j]) * is.v[j];
-        const float db = (float)dbeta[c8 + j] * inv_n, dg = (float)dgamma[c8 + j] * inv_n;
-        o.v[j] = ga.v[j] * is.v[j] * (g.v[j] - db - xh * dg);
-      }
+      for (int j = 0; j < 8; ++j) o.v[j] = fmaf(A.v[j], g.v[j], fmaf(B.v[j], x.v[j], C.v[j]));
       store8(dy + i * 8, o);
     }
     if (y2) {
-      const V8 x = load8(y2 + i * 8);
-      const V8 mu = loadf8(mean2 + c8), is = loadf8(invstd2 + c8), ga = loadf8(gamma2 + c8);
+      const V8 A = loadf8(coef2 + c8), B = loadf8(coef2 + c + c8), C = loadf8(coef2 + 2 * c + c8);
       V8 o;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (x.v[j] - mu.v[j]) * is.v[j];
-        const float db = (float)dbeta[c8 + j] * inv_n, dg = (float)dgamma2[c8 + j] * inv_n;
-        o.v[j] = ga.v[j] * is.v[j] * (g.v[j] - db - xh * dg);
-      }
+      for (int j = 0; j < 8; ++j) o.v[j] = fmaf(A.v[j], g.v[j], fmaf(B.v[j], xx.v[j], C.v[j]));
       store8(dy2 + i * 8, o);
     }
   }
-}
-
-// grad_gamma += dgamma, grad_beta += dbeta (fp32 parameter gradients); re-zero the fp64 accumulators
-__global__ void bn_param_grads_kernel(double* __restrict__ dbeta, double* __restrict__ dgamma, int c,
-                                      float* __restrict__ grad_gamma, float* __restrict__ grad_beta, int zero_dbeta) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c) return;
-  grad_gamma[i] += (float)dgamma[i];
-  grad_beta[i] += (float)dbeta[i];
-  dgamma[i] = 0.0;
-  if (zero_dbeta) dbeta[i] = 0.0;
 }
 
 // ------------------------------------------------------------------ pooling
@@ -480,27 +523,30 @@ static inline int grid1d(int64_t n, int block = 256, int per_sm = 8) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+int bn_partial_floats(int max_c) { return kReduceCtasPerSm * num_sms() * 3 * max_c; }
+
 static inline int reduce_grid(int64_t rows, int lanes) {
   int64_t g = (rows + (int64_t)lanes * 16 - 1) / ((int64_t)lanes * 16);   // >= ~16 rows per thread
-  const int64_t cap = 4 * (int64_t)num_sms();
+  const int64_t cap = kReduceCtasPerSm * (int64_t)num_sms();
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
 // ------------------------------------------------------------- host wrappers
-int bn_stats(const __nv_bfloat16* y, int64_t rows, int c, double* sum, double* sumsq, cudaStream_t st) {
+int bn_stats(const __nv_bfloat16* y, int64_t rows, int c, float* partial, int* nblocks, cudaStream_t st) {
   const int cgroups = c / 8;
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_stats: unsupported channel count %d", c);
   const int lanes = 256 / cgroups;
-  bn_stats_kernel<<<reduce_grid(rows, lanes), 256, 256 * 16 * sizeof(float), st>>>(y, rows, c, sum, sumsq);
+  *nblocks = reduce_grid(rows, lanes);
+  bn_stats_kernel<<<*nblocks, 256, 256 * 16 * sizeof(float), st>>>(y, rows, c, partial);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
 
-int bn_finalize(double* sum, double* sumsq, int64_t rows, int c, const float* gamma, const float* beta, float eps,
-                float momentum, float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
-                float* shift, cudaStream_t st) {
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(sum, sumsq, rows, c, gamma, beta, eps, momentum, running_mean,
-                                                      running_var, mean, invstd, scale, shift);
+int bn_finalize(const float* partial, int nblocks, int64_t rows, int c, const float* gamma, const float* beta,
+                float eps, float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
+                float* scale, float* shift, cudaStream_t st) {
+  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 8), 0, st>>>(partial, nblocks, rows, c, gamma, beta, eps, momentum, running_mean,
+                                                    running_var, mean, invstd, scale, shift);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
@@ -524,31 +570,30 @@ int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, con
 
 int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* act, const __nv_bfloat16* y,
                   const float* mean, const float* invstd, const __nv_bfloat16* y2, const float* mean2,
-                  const float* invstd2, int64_t rows, int c, double* dbeta, double* dgamma, double* dgamma2,
-                  cudaStream_t st) {
+                  const float* invstd2, int64_t rows, int c, float* partial, int* nblocks, cudaStream_t st) {
   const int cgroups = c / 8;
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_bwd_reduce: unsupported channel count %d", c);
   const int lanes = 256 / cgroups;
-  bn_bwd_reduce_kernel<<<reduce_grid(rows, lanes), 256, 256 * 24 * sizeof(float), st>>>(
-      g1, g2, act, y, mean, invstd, y2, mean2, invstd2, rows, c, dbeta, dgamma, dgamma2);
+  *nblocks = reduce_grid(rows, lanes);
+  bn_bwd_reduce_kernel<<<*nblocks, 256, 256 * 24 * sizeof(float), st>>>(g1, g2, act, y, mean, invstd, y2, mean2,
+                                                                         invstd2, rows, c, partial);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+int bn_bwd_coeffs(const float* partial, int nblocks, int k, int gslot, int64_t rows, int c, const float* mean,
+                  const float* invstd, const float* gamma, float* grad_gamma, float* grad_beta, float* coef,
+                  cudaStream_t st) {
+  bn_bwd_coeffs_kernel<<<(c + 31) / 32, dim3(32, 8), 0, st>>>(partial, nblocks, k, gslot, rows, c, mean, invstd, gamma,
+                                                      grad_gamma, grad_beta, coef);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
 
 int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* act, const __nv_bfloat16* y,
-                 const float* mean, const float* invstd, const float* gamma, const double* dbeta, const double* dgamma,
-                 const __nv_bfloat16* y2, const float* mean2, const float* invstd2, const float* gamma2,
-                 const double* dgamma2, int64_t rows, int c, __nv_bfloat16* dy, __nv_bfloat16* dy2,
-                 __nv_bfloat16* dz_out, cudaStream_t st) {
-  bn_bwd_apply_kernel<<<grid1d(rows * c / 8), 256, 0, st>>>(g1, g2, act, y, mean, invstd, gamma, dbeta, dgamma, y2,
-                                                           mean2, invstd2, gamma2, dgamma2, rows, c, dy, dy2, dz_out);
-  DIRB_LAUNCHED();
-  return DIRB200_OK;
-}
-
-int bn_param_grads(double* dbeta, double* dgamma, int c, float* grad_gamma, float* grad_beta, bool zero_dbeta,
-                   cudaStream_t st) {
-  bn_param_grads_kernel<<<(c + 127) / 128, 128, 0, st>>>(dbeta, dgamma, c, grad_gamma, grad_beta, zero_dbeta ? 1 : 0);
+                 const float* coef, const __nv_bfloat16* y2, const float* coef2, int64_t rows, int c,
+                 __nv_bfloat16* dy, __nv_bfloat16* dy2, __nv_bfloat16* dz_out, cudaStream_t st) {
+  bn_bwd_apply_kernel<<<grid1d(rows * c / 8), 256, 0, st>>>(g1, g2, act, y, coef, y2, coef2, rows, c, dy, dy2, dz_out);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }

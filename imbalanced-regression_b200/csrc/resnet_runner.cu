@@ -17,8 +17,7 @@ struct BNLayer {
   int c = 0;
   size_t gamma_off = 0, beta_off = 0;  // in the flat parameter buffer (floats)
   size_t rm_off = 0, rv_off = 0;       // in the flat BN running-statistics buffer (floats)
-  float *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr;
-  double* acc = nullptr;               // [2][c] fp64: (sum, sumsq) forward / (dbeta, dgamma) backward; kept zero between uses
+  float *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr, *coef = nullptr;  // coef: [3][c] BN-backward
 };
 
 struct ConvLayer {
@@ -53,9 +52,15 @@ struct dirb200_net {
   int feat_c = 0, feat_hw = 0;
   __nv_bfloat16* scratch[8] = {};
   float* wgrad_ws = nullptr;
+  float* bn_partial = nullptr;   // per-CTA partial sums of the BN column reductions
   size_t param_count = 0, running_count = 0, activation_bytes = 0;
   std::vector<void*> allocs;
   bool forward_was_training = false;
+  // optional per-kernel-class timing (CUDA events around every launch group)
+  bool profiling = false;
+  struct ProfRec { int kind; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> event_pool;
 };
 
 namespace dirb200 {
@@ -84,10 +89,9 @@ static bool setup_bn(dirb200_net* net, BNLayer& bn, int c) {
   bn.rv_off = net->running_count + c;
   net->running_count += 2 * (size_t)c;
   float* f = nullptr;
-  NET_ALLOC(f, sizeof(float) * 4 * c);
-  bn.mean = f; bn.invstd = f + c; bn.scale = f + 2 * c; bn.shift = f + 3 * c;
-  NET_ALLOC(bn.acc, sizeof(double) * 2 * c);
-  return cudaMemset(bn.acc, 0, sizeof(double) * 2 * c) == cudaSuccess;
+  NET_ALLOC(f, sizeof(float) * 7 * c);
+  bn.mean = f; bn.invstd = f + c; bn.scale = f + 2 * c; bn.shift = f + 3 * c; bn.coef = f + 4 * c;
+  return true;
 }
 
 static bool setup_conv(dirb200_net* net, ConvLayer& cv, int n, int h, int w, int cin, int cout, int k, int stride,
@@ -153,6 +157,7 @@ static bool build(dirb200_net* net, const int* blocks_per_stage, int num_stages)
     if (B.has_ds) ws = std::max(ws, conv_wgrad_workspace_bytes(B.ds.s));
   }
   NET_ALLOC(net->wgrad_ws, ws);
+  NET_ALLOC(net->bn_partial, sizeof(float) * bn_partial_floats(net->feat_c));
   return true;
 }
 
@@ -161,34 +166,78 @@ static bool build(dirb200_net* net, const int* blocks_per_stage, int num_stages)
     if (int _rc = (expr)) return _rc; \
   } while (0)
 
-static int conv_bn_forward(ConvLayer& cv, const __nv_bfloat16* in, const float* params, float* running, bool training,
-                           cudaStream_t st) {
-  RUN(prep_weights(params + cv.w_off, cv.s.cout, cv.stem ? 3 : cv.s.cin, cv.stem ? 7 : cv.s.kh, cv.stem ? 7 : cv.s.kw,
-                   cv.stem, cv.wf, cv.wd, st));
-  RUN(conv_fprop(in, cv.wf, cv.y, cv.s, cv.stem, st));
+enum ProfKind { kPrep = 0, kFprop, kDgrad, kWgrad, kWgradReduce, kBnStats, kBnApply, kBnBwdReduce, kBnBwdApply, kPool,
+                kNumProfKinds };
+
+static cudaEvent_t prof_event(dirb200_net* net) {
+  if (!net->event_pool.empty()) {
+    cudaEvent_t e = net->event_pool.back();
+    net->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+static inline void prof_begin(dirb200_net* net, int kind, cudaStream_t st) {
+  if (!net->profiling) return;
+  dirb200_net::ProfRec r{kind, prof_event(net), prof_event(net)};
+  cudaEventRecord(r.a, st);
+  net->prof.push_back(r);
+}
+static inline void prof_end(dirb200_net* net, cudaStream_t st) {
+  if (!net->profiling) return;
+  cudaEventRecord(net->prof.back().b, st);
+}
+// RUN with the launch(es) attributed to a kernel class when profiling is on
+#define RUNP(kind, expr)          \
+  do {                            \
+    prof_begin(net, (kind), st);  \
+    int _rc = (expr);             \
+    prof_end(net, st);            \
+    if (_rc) return _rc;          \
+  } while (0)
+
+static int conv_bn_forward(dirb200_net* net, ConvLayer& cv, const __nv_bfloat16* in, const float* params,
+                           float* running, bool training, cudaStream_t st) {
+  RUNP(kPrep, prep_weights(params + cv.w_off, cv.s.cout, cv.stem ? 3 : cv.s.cin, cv.stem ? 7 : cv.s.kh,
+                           cv.stem ? 7 : cv.s.kw, cv.stem, cv.wf, cv.wd, st));
+  RUNP(kFprop, conv_fprop(in, cv.wf, cv.y, cv.s, cv.stem, st));
   BNLayer& bn = cv.bn;
   if (training) {
-    RUN(bn_stats(cv.y, cv.rows, bn.c, bn.acc, bn.acc + bn.c, st));
-    RUN(bn_finalize(bn.acc, bn.acc + bn.c, cv.rows, bn.c, params + bn.gamma_off, params + bn.beta_off, 1e-5f, 0.1f,
+    int nblk = 0;
+    RUNP(kBnStats, bn_stats(cv.y, cv.rows, bn.c, net->bn_partial, &nblk, st));
+    RUNP(kBnStats, bn_finalize(net->bn_partial, nblk, cv.rows, bn.c, params + bn.gamma_off, params + bn.beta_off, 1e-5f, 0.1f,
                     running ? running + bn.rm_off : nullptr, running ? running + bn.rv_off : nullptr, bn.mean,
                     bn.invstd, bn.scale, bn.shift, st));
   } else {
-    RUN(bn_eval_coeffs(bn.c, params + bn.gamma_off, params + bn.beta_off, 1e-5f, running + bn.rm_off,
-                       running + bn.rv_off, bn.scale, bn.shift, st));
+    RUNP(kBnStats, bn_eval_coeffs(bn.c, params + bn.gamma_off, params + bn.beta_off, 1e-5f, running + bn.rm_off,
+                                  running + bn.rv_off, bn.scale, bn.shift, st));
   }
-  if (cv.a) RUN(bn_apply(cv.y, bn.scale, bn.shift, nullptr, nullptr, nullptr, nullptr, true, cv.rows, bn.c, cv.a, st));
+  if (cv.a)
+    RUNP(kBnApply, bn_apply(cv.y, bn.scale, bn.shift, nullptr, nullptr, nullptr, nullptr, true, cv.rows, bn.c, cv.a, st));
+  return DIRB200_OK;
+}
+
+static int wgrad_step(dirb200_net* net, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, const ConvShape& s,
+                      bool stem, cudaStream_t st) {
+  int splits = 1;
+  RUNP(kWgrad, conv_wgrad_partials(x, dy, net->wgrad_ws, s, stem, &splits, st));
+  RUNP(kWgradReduce, wgrad_reduce(net->wgrad_ws, splits, dw, s, stem, true, st));
   return DIRB200_OK;
 }
 
 // BN backward for a conv followed by BN+ReLU: g = d loss / d relu-output
-static int conv_bn_backward(ConvLayer& cv, const __nv_bfloat16* g, const float* params, float* grads,
+static int conv_bn_backward(dirb200_net* net, ConvLayer& cv, const __nv_bfloat16* g, const float* params, float* grads,
                             __nv_bfloat16* dy, cudaStream_t st) {
   BNLayer& bn = cv.bn;
-  RUN(bn_bwd_reduce(g, nullptr, cv.a, cv.y, bn.mean, bn.invstd, nullptr, nullptr, nullptr, cv.rows, bn.c, bn.acc,
-                    bn.acc + bn.c, nullptr, st));
-  RUN(bn_bwd_apply(g, nullptr, cv.a, cv.y, bn.mean, bn.invstd, params + bn.gamma_off, bn.acc, bn.acc + bn.c, nullptr,
-                   nullptr, nullptr, nullptr, nullptr, cv.rows, bn.c, dy, nullptr, nullptr, st));
-  RUN(bn_param_grads(bn.acc, bn.acc + bn.c, bn.c, grads + bn.gamma_off, grads + bn.beta_off, true, st));
+  int nblk = 0;
+  RUNP(kBnBwdReduce, bn_bwd_reduce(g, nullptr, cv.a, cv.y, bn.mean, bn.invstd, nullptr, nullptr, nullptr, cv.rows,
+                                   bn.c, net->bn_partial, &nblk, st));
+  RUNP(kBnBwdApply, bn_bwd_coeffs(net->bn_partial, nblk, 2, 1, cv.rows, bn.c, bn.mean, bn.invstd,
+                                  params + bn.gamma_off, grads + bn.gamma_off, grads + bn.beta_off, bn.coef, st));
+  RUNP(kBnBwdApply, bn_bwd_apply(g, nullptr, cv.a, cv.y, bn.coef, nullptr, nullptr, cv.rows, bn.c, dy, nullptr, nullptr,
+                                 st));
   return DIRB200_OK;
 }
 
@@ -221,6 +270,32 @@ int64_t dirb200_resnet_running_count(const dirb200_net* net) { return net ? (int
 int64_t dirb200_resnet_feature_dim(const dirb200_net* net) { return net ? net->feat_c : -1; }
 int64_t dirb200_resnet_device_bytes(const dirb200_net* net) { return net ? (int64_t)net->activation_bytes : -1; }
 
+/* Per-kernel-class device timing (CUDA events around every launch group of forward/backward).
+ * Classes: 0 prep (weight re-layout, s2d), 1 conv fprop, 2 conv dgrad, 3 conv wgrad GEMM, 4 wgrad split-K reduce,
+ * 5 BN statistics, 6 BN apply, 7 BN backward reduce, 8 BN backward apply, 9 pooling. */
+int dirb200_resnet_set_profiling(dirb200_net* net, int enabled) {
+  DIRB_CHECK_ARG(net, "resnet_set_profiling: null net");
+  net->profiling = enabled != 0;
+  return DIRB200_OK;
+}
+
+/* Synchronises, sums the recorded intervals per class into ms_by_kind[10] / launches_by_kind[10], clears the log. */
+int dirb200_resnet_read_profile(dirb200_net* net, double* ms_by_kind, int64_t* groups_by_kind) {
+  DIRB_CHECK_ARG(net && ms_by_kind && groups_by_kind, "resnet_read_profile: null pointer");
+  for (int i = 0; i < kNumProfKinds; ++i) { ms_by_kind[i] = 0.0; groups_by_kind[i] = 0; }
+  for (auto& r : net->prof) {
+    DIRB_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    DIRB_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_by_kind[r.kind] += ms;
+    groups_by_kind[r.kind] += 1;
+    net->event_pool.push_back(r.a);
+    net->event_pool.push_back(r.b);
+  }
+  net->prof.clear();
+  return DIRB200_OK;
+}
+
 /* x fp32 NCHW [n,3,h,w] -> enc fp32 [n, feature_dim]  (conv1 ... avgpool + view, resnet.py:128-138).
  * training != 0: batch statistics, running statistics updated (momentum 0.1); else running statistics. */
 int dirb200_resnet_forward(dirb200_net* net, const float* x_nchw, const float* params, float* bn_running, int training,
@@ -229,23 +304,23 @@ int dirb200_resnet_forward(dirb200_net* net, const float* x_nchw, const float* p
   DIRB_CHECK_ARG(training || bn_running, "resnet_forward: eval mode needs the running statistics");
   cudaStream_t st = as_stream(stream);
   const bool tr = training != 0;
-  RUN(input_to_s2d(x_nchw, net->n, net->h, net->w, net->x_s2d, st));
-  RUN(conv_bn_forward(net->stem, net->x_s2d, params, bn_running, tr, st));
-  RUN(maxpool_fwd(net->stem.a, net->n, net->stem.s.ho, net->stem.s.wo, 64, net->pool_out, net->pool_idx, st));
+  RUNP(kPrep, input_to_s2d(x_nchw, net->n, net->h, net->w, net->x_s2d, st));
+  RUN(conv_bn_forward(net, net->stem, net->x_s2d, params, bn_running, tr, st));
+  RUNP(kPool, maxpool_fwd(net->stem.a, net->n, net->stem.s.ho, net->stem.s.wo, 64, net->pool_out, net->pool_idx, st));
   for (Block& B : net->blocks) {
-    RUN(conv_bn_forward(B.c1, B.in, params, bn_running, tr, st));
-    RUN(conv_bn_forward(B.c2, B.c1.a, params, bn_running, tr, st));
-    RUN(conv_bn_forward(B.c3, B.c2.a, params, bn_running, tr, st));
+    RUN(conv_bn_forward(net, B.c1, B.in, params, bn_running, tr, st));
+    RUN(conv_bn_forward(net, B.c2, B.c1.a, params, bn_running, tr, st));
+    RUN(conv_bn_forward(net, B.c3, B.c2.a, params, bn_running, tr, st));
     if (B.has_ds) {
-      RUN(conv_bn_forward(B.ds, B.in, params, bn_running, tr, st));
-      RUN(bn_apply(B.c3.y, B.c3.bn.scale, B.c3.bn.shift, nullptr, B.ds.y, B.ds.bn.scale, B.ds.bn.shift, true, B.c3.rows,
-                   B.c3.bn.c, B.out, st));
+      RUN(conv_bn_forward(net, B.ds, B.in, params, bn_running, tr, st));
+      RUNP(kBnApply, bn_apply(B.c3.y, B.c3.bn.scale, B.c3.bn.shift, nullptr, B.ds.y, B.ds.bn.scale, B.ds.bn.shift, true,
+                              B.c3.rows, B.c3.bn.c, B.out, st));
     } else {
-      RUN(bn_apply(B.c3.y, B.c3.bn.scale, B.c3.bn.shift, B.in, nullptr, nullptr, nullptr, true, B.c3.rows, B.c3.bn.c,
-                   B.out, st));
+      RUNP(kBnApply, bn_apply(B.c3.y, B.c3.bn.scale, B.c3.bn.shift, B.in, nullptr, nullptr, nullptr, true, B.c3.rows,
+                              B.c3.bn.c, B.out, st));
     }
   }
-  RUN(avgpool_fwd(net->blocks.back().out, net->n, net->feat_hw, net->feat_c, enc_out, st));
+  RUNP(kPool, avgpool_fwd(net->blocks.back().out, net->n, net->feat_hw, net->feat_c, enc_out, st));
   net->forward_was_training = tr;
   return DIRB200_OK;
 }
@@ -259,39 +334,41 @@ int dirb200_resnet_backward(dirb200_net* net, const float* d_enc, const float* p
   __nv_bfloat16 *gA = net->scratch[0], *gB = nullptr, *nA = net->scratch[2], *nB = net->scratch[3];
   __nv_bfloat16 *t1 = net->scratch[4], *t2 = net->scratch[5], *t3 = net->scratch[6];
   __nv_bfloat16* spareB = net->scratch[1];
-  float* ws = net->wgrad_ws;
-  RUN(avgpool_bwd(d_enc, net->n, net->feat_hw, net->feat_c, gA, st));
+  RUNP(kPool, avgpool_bwd(d_enc, net->n, net->feat_hw, net->feat_c, gA, st));
   for (int bi = (int)net->blocks.size() - 1; bi >= 0; --bi) {
     Block& B = net->blocks[bi];
     BNLayer& b3 = B.c3.bn;
     // ---- block output: out = relu(bn3(y3) + identity); dz = (gA + gB) * (out > 0)
-    RUN(bn_bwd_reduce(gA, gB, B.out, B.c3.y, b3.mean, b3.invstd, B.has_ds ? B.ds.y : nullptr,
-                      B.has_ds ? B.ds.bn.mean : nullptr, B.has_ds ? B.ds.bn.invstd : nullptr, B.c3.rows, b3.c, b3.acc,
-                      b3.acc + b3.c, B.has_ds ? B.ds.bn.acc + b3.c : nullptr, st));
-    RUN(bn_bwd_apply(gA, gB, B.out, B.c3.y, b3.mean, b3.invstd, params + b3.gamma_off, b3.acc, b3.acc + b3.c,
-                     B.has_ds ? B.ds.y : nullptr, B.has_ds ? B.ds.bn.mean : nullptr,
-                     B.has_ds ? B.ds.bn.invstd : nullptr, B.has_ds ? params + B.ds.bn.gamma_off : nullptr,
-                     B.has_ds ? B.ds.bn.acc + b3.c : nullptr, B.c3.rows, b3.c, t1, B.has_ds ? t2 : nullptr,
-                     B.has_ds ? nullptr : nB, st));
+    int nblk = 0;
+    const int kparts = B.has_ds ? 3 : 2;
+    RUNP(kBnBwdReduce, bn_bwd_reduce(gA, gB, B.out, B.c3.y, b3.mean, b3.invstd, B.has_ds ? B.ds.y : nullptr,
+                                     B.has_ds ? B.ds.bn.mean : nullptr, B.has_ds ? B.ds.bn.invstd : nullptr, B.c3.rows,
+                                     b3.c, net->bn_partial, &nblk, st));
     if (B.has_ds) {
-      RUN(bn_param_grads(b3.acc, B.ds.bn.acc + b3.c, b3.c, grads + B.ds.bn.gamma_off, grads + B.ds.bn.beta_off, false, st));
+      BNLayer& bd = B.ds.bn;
+      RUNP(kBnBwdApply, bn_bwd_coeffs(net->bn_partial, nblk, kparts, 2, B.c3.rows, b3.c, bd.mean, bd.invstd,
+                                      params + bd.gamma_off, grads + bd.gamma_off, grads + bd.beta_off, bd.coef, st));
     }
-    RUN(bn_param_grads(b3.acc, b3.acc + b3.c, b3.c, grads + b3.gamma_off, grads + b3.beta_off, true, st));
+    RUNP(kBnBwdApply, bn_bwd_coeffs(net->bn_partial, nblk, kparts, 1, B.c3.rows, b3.c, b3.mean, b3.invstd,
+                                    params + b3.gamma_off, grads + b3.gamma_off, grads + b3.beta_off, b3.coef, st));
+    RUNP(kBnBwdApply, bn_bwd_apply(gA, gB, B.out, B.c3.y, b3.coef, B.has_ds ? B.ds.y : nullptr,
+                                   B.has_ds ? B.ds.bn.coef : nullptr, B.c3.rows, b3.c, t1, B.has_ds ? t2 : nullptr,
+                                   B.has_ds ? nullptr : nB, st));
     // ---- conv3
-    RUN(conv_wgrad(B.c2.a, t1, grads + B.c3.w_off, ws, B.c3.s, false, true, st));
-    RUN(conv_dgrad(t1, B.c3.wd, t3, B.c3.s, st));
+    RUN(wgrad_step(net, B.c2.a, t1, grads + B.c3.w_off, B.c3.s, false, st));
+    RUNP(kDgrad, conv_dgrad(t1, B.c3.wd, t3, B.c3.s, st));
     // ---- bn2 + conv2
-    RUN(conv_bn_backward(B.c2, t3, params, grads, t1, st));
-    RUN(conv_wgrad(B.c1.a, t1, grads + B.c2.w_off, ws, B.c2.s, false, true, st));
-    RUN(conv_dgrad(t1, B.c2.wd, t3, B.c2.s, st));
+    RUN(conv_bn_backward(net, B.c2, t3, params, grads, t1, st));
+    RUN(wgrad_step(net, B.c1.a, t1, grads + B.c2.w_off, B.c2.s, false, st));
+    RUNP(kDgrad, conv_dgrad(t1, B.c2.wd, t3, B.c2.s, st));
     // ---- bn1 + conv1
-    RUN(conv_bn_backward(B.c1, t3, params, grads, t1, st));
-    RUN(conv_wgrad(B.in, t1, grads + B.c1.w_off, ws, B.c1.s, false, true, st));
-    RUN(conv_dgrad(t1, B.c1.wd, nA, B.c1.s, st));
+    RUN(conv_bn_backward(net, B.c1, t3, params, grads, t1, st));
+    RUN(wgrad_step(net, B.in, t1, grads + B.c1.w_off, B.c1.s, false, st));
+    RUNP(kDgrad, conv_dgrad(t1, B.c1.wd, nA, B.c1.s, st));
     // ---- downsample branch
     if (B.has_ds) {
-      RUN(conv_wgrad(B.in, t2, grads + B.ds.w_off, ws, B.ds.s, false, true, st));
-      RUN(conv_dgrad(t2, B.ds.wd, nB, B.ds.s, st));
+      RUN(wgrad_step(net, B.in, t2, grads + B.ds.w_off, B.ds.s, false, st));
+      RUNP(kDgrad, conv_dgrad(t2, B.ds.wd, nB, B.ds.s, st));
     }
     // the two gradients w.r.t. this block's input become the next (earlier) block's incoming pair
     __nv_bfloat16* oldA = gA;
@@ -301,9 +378,9 @@ int dirb200_resnet_backward(dirb200_net* net, const float* d_enc, const float* p
     spareB = nullptr;
   }
   // ---- stem: maxpool -> bn1+relu -> conv1 (no data gradient needed)
-  RUN(maxpool_bwd(gA, gB, net->pool_idx, net->n, net->stem.s.ho, net->stem.s.wo, 64, t3, st));
-  RUN(conv_bn_backward(net->stem, t3, params, grads, t1, st));
-  RUN(conv_wgrad(net->x_s2d, t1, grads + net->stem.w_off, ws, net->stem.s, true, true, st));
+  RUNP(kPool, maxpool_bwd(gA, gB, net->pool_idx, net->n, net->stem.s.ho, net->stem.s.wo, 64, t3, st));
+  RUN(conv_bn_backward(net, net->stem, t3, params, grads, t1, st));
+  RUN(wgrad_step(net, net->x_s2d, t1, grads + net->stem.w_off, net->stem.s, true, st));
   return DIRB200_OK;
 }
 

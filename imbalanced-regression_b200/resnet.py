@@ -37,6 +37,8 @@ _lib.register({
     "dirb200_resnet_device_bytes": (c_int64, [P]),
     "dirb200_resnet_forward": (c_int, [P, P, P, P, c_int, P, P]),
     "dirb200_resnet_backward": (c_int, [P, P, P, P, P]),
+    "dirb200_resnet_set_profiling": (c_int, [P, c_int]),
+    "dirb200_resnet_read_profile": (c_int, [P, P, P]),
     "dirb200_resnet_peek": (c_int, [P, c_int, c_int, P, P, P]),
     "dirb200_linear1_fwd": (c_int, [P, P, P, c_int64, c_int, P, P]),
     "dirb200_linear1_bwd": (c_int, [P, P, P, c_int64, c_int, P, P, P, P]),
@@ -325,6 +327,20 @@ class ResNet(nn.Module):
         g = g.detach().to(torch.float32).contiguous()
         _lib.call("dirb200_resnet_backward", self._net(shape), _lib.ptr(g), _lib.ptr(self._flat["params"]),
                   _lib.ptr(self._flat["grads"]), _lib.stream_ptr())
+
+    PROFILE_KINDS = ("prep", "conv_fprop", "conv_dgrad", "conv_wgrad", "wgrad_reduce", "bn_stats", "bn_apply",
+                     "bn_bwd_reduce", "bn_bwd_apply", "pool")
+
+    def set_profiling(self, shape, enabled):
+        _lib.call("dirb200_resnet_set_profiling", self._net(tuple(shape)), int(enabled))
+
+    def read_profile(self, shape):
+        """{kernel class: (milliseconds, launch groups)} recorded since the last read (synchronises)."""
+        from ctypes import c_double
+        ms = (c_double * 10)()
+        cnt = (c_int64 * 10)()
+        _lib.call("dirb200_resnet_read_profile", self._net(tuple(shape)), ms, cnt)
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(self.PROFILE_KINDS)}
 
     def peek(self, shape, block, which):
         """Test aid: copy of an internal NHWC bf16 activation of the runner for input `shape`, as fp32 NCHW."""

@@ -202,6 +202,13 @@ int dirb200_resnet_forward(dirb200_net* net, const float* x_nchw, const float* p
 /* Backward of the above: d_enc fp32 [n, feature_dim]; ACCUMULATES into grads. */
 int dirb200_resnet_backward(dirb200_net* net, const float* d_enc, const float* params, float* grads, void* stream);
 
+/* Per-kernel-class device timing of forward/backward (CUDA events around every launch group).  Classes:
+ * 0 prep (weight re-layout, s2d), 1 conv fprop, 2 conv dgrad, 3 conv wgrad GEMM, 4 wgrad split-K reduce,
+ * 5 BN statistics, 6 BN apply, 7 BN backward reduce, 8 BN backward apply, 9 pooling.
+ * read_profile synchronises, fills ms_by_kind[10] / groups_by_kind[10] and clears the log. */
+int dirb200_resnet_set_profiling(dirb200_net* net, int enabled);
+int dirb200_resnet_read_profile(dirb200_net* net, double* ms_by_kind, int64_t* groups_by_kind);
+
 /* Test / debugging aid: device pointer + shape ([rows][channels] bf16, NHWC) of an internal activation.
  * block = -1: stem (0 = conv1 raw, 1 = relu(bn1), 6 = max-pool output); block >= 0: 0/1 = conv1 raw / act,
  * 2/3 = conv2 raw / act, 4 = conv3 raw, 5 = downsample raw, 6 = block output. */
