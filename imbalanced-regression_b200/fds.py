@@ -194,13 +194,20 @@ class FDS(nn.Module):
         _lib.call("dirb200_fds_accumulate", _lib.ptr(features), _lib.ptr(bins), n, d, nb, _lib.ptr(acc["sums"]),
                   _lib.ptr(acc["sumsq"]), _lib.ptr(acc["counts"]), _lib.ptr(acc["ws"]), acc["ws"].numel(), st)
 
-    def finish_epoch_stats(self, epoch):
-        acc, self._acc = self._acc, None
-        assert acc is not None
-        dist = self._dist()
+    @classmethod
+    def reduce_accumulators(cls, acc):
+        """Merge the per-rank (count, sum x, sum x^2) accumulators: plain SUM all-reduces (the fp64 sums make
+        the merge exact to rounding, independent of how rows were sharded)."""
+        dist = cls._dist()
         if dist is not None:
             for k in ("sums", "sumsq", "counts"):
                 dist.all_reduce(acc[k], op=dist.ReduceOp.SUM)
+        return acc
+
+    def finish_epoch_stats(self, epoch):
+        acc, self._acc = self._acc, None
+        assert acc is not None
+        self.reduce_accumulators(acc)
         nb, d = self.running_mean.shape
         _lib.call("dirb200_fds_finalize", _lib.ptr(acc["sums"]), _lib.ptr(acc["sumsq"]), _lib.ptr(acc["counts"]),
                   nb, d, _lib.ptr(self.running_mean), _lib.ptr(self.running_var),

@@ -1,0 +1,270 @@
+"""train.py -- host driver mirroring agedb-dir/train.py / imdb-wiki-dir/train.py
+(same flags, same store-name rule, same train / validate / checkpoint flow)
+on top of the B200-native modules of this directory.
+
+Differences that matter:
+  * one process per GPU (`torchrun --nproc-per-node N train.py ...`): the
+    gradient all-reduce goes over NCCL (parallel.DataParallel), the optimizer
+    is the fused flat-buffer Adam / SGD (optim.py);
+  * the epoch-end FDS refresh (train.py:269-281 of the reference) streams each
+    batch's features into the on-device per-bin accumulators -- no
+    GPU->CPU->GPU round trip of the feature matrix, statistics all-reduced
+    across ranks;
+  * arguments are parsed inside main() (importing this file has no side
+    effects) and `--synthetic N` trains on N synthetic samples (no dataset /
+    network needed);
+  * tensorboard_logger is optional.
+"""
+import argparse
+import logging
+import os
+import time
+from collections import defaultdict
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader, Dataset
+
+from resnet import resnet50
+from loss import *  # noqa: F401,F403  (looked up by name, as the reference does at train.py:255)
+from datasets import AgeDB, IMDBWIKI, lds_prepare_weights
+from utils import AverageMeter, ProgressMeter, adjust_learning_rate, prepare_folders, save_checkpoint
+from optim import FusedAdam, FusedSGD
+from parallel import DataParallel, is_distributed
+
+print = logging.info
+
+
+def build_parser():
+    p = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    p.add_argument('--lds', action='store_true', default=False, help='whether to enable LDS')
+    p.add_argument('--lds_kernel', type=str, default='gaussian', choices=['gaussian', 'triang', 'laplace'])
+    p.add_argument('--lds_ks', type=int, default=9, help='LDS kernel size: should be odd number')
+    p.add_argument('--lds_sigma', type=float, default=1, help='LDS gaussian/laplace kernel sigma')
+    p.add_argument('--fds', action='store_true', default=False, help='whether to enable FDS')
+    p.add_argument('--fds_kernel', type=str, default='gaussian', choices=['gaussian', 'triang', 'laplace'])
+    p.add_argument('--fds_ks', type=int, default=9, help='FDS kernel size: should be odd number')
+    p.add_argument('--fds_sigma', type=float, default=1, help='FDS gaussian/laplace kernel sigma')
+    p.add_argument('--start_update', type=int, default=0, help='which epoch to start FDS updating')
+    p.add_argument('--start_smooth', type=int, default=1, help='which epoch to start using FDS to smooth features')
+    p.add_argument('--bucket_num', type=int, default=100, help='maximum bucket considered for FDS')
+    p.add_argument('--bucket_start', type=int, default=3, choices=[0, 3], help='0 for IMDBWIKI, 3 for AgeDB')
+    p.add_argument('--fds_mmt', type=float, default=0.9, help='FDS momentum')
+    p.add_argument('--reweight', type=str, default='none', choices=['none', 'sqrt_inv', 'inverse'])
+    p.add_argument('--retrain_fc', action='store_true', default=False, help='retrain last regression layer only')
+    p.add_argument('--dataset', type=str, default='agedb', choices=['imdb_wiki', 'agedb'])
+    p.add_argument('--data_dir', type=str, default='./data')
+    p.add_argument('--model', type=str, default='resnet50')
+    p.add_argument('--store_root', type=str, default='checkpoint')
+    p.add_argument('--store_name', type=str, default='')
+    p.add_argument('--gpu', type=int, default=None)
+    p.add_argument('--optimizer', type=str, default='adam', choices=['adam', 'sgd'])
+    p.add_argument('--loss', type=str, default='l1', choices=['mse', 'l1', 'focal_l1', 'focal_mse', 'huber'])
+    p.add_argument('--lr', type=float, default=1e-3)
+    p.add_argument('--epoch', type=int, default=90)
+    p.add_argument('--momentum', type=float, default=0.9)
+    p.add_argument('--weight_decay', type=float, default=1e-4)
+    p.add_argument('--schedule', type=int, nargs='*', default=[60, 80])
+    p.add_argument('--batch_size', type=int, default=256, help='batch size PER GPU (one process per GPU)')
+    p.add_argument('--print_freq', type=int, default=10)
+    p.add_argument('--img_size', type=int, default=224)
+    p.add_argument('--workers', type=int, default=32)
+    p.add_argument('--resume', type=str, default='')
+    p.add_argument('--pretrained', type=str, default='')
+    p.add_argument('--evaluate', action='store_true')
+    p.add_argument('--synthetic', type=int, default=0, help='train on this many synthetic samples (no dataset needed)')
+    return p
+
+
+def store_name(args):
+    """Experiment directory name, same rule as the reference (train.py:78-93)."""
+    name = f'_{args.store_name}' if len(args.store_name) else ''
+    if not args.lds and args.reweight != 'none':
+        name += f'_{args.reweight}'
+    if args.lds:
+        name += f'_lds_{args.lds_kernel[:3]}_{args.lds_ks}'
+        if args.lds_kernel in ['gaussian', 'laplace']:
+            name += f'_{args.lds_sigma}'
+    if args.fds:
+        name += f'_fds_{args.fds_kernel[:3]}_{args.fds_ks}'
+        if args.fds_kernel in ['gaussian', 'laplace']:
+            name += f'_{args.fds_sigma}'
+        name += f'_{args.start_update}_{args.start_smooth}_{args.fds_mmt}'
+    if args.retrain_fc:
+        name += '_retrain_fc'
+    return f"{args.dataset}_{args.model}{name}_{args.optimizer}_{args.loss}_{args.lr}_{args.batch_size}"
+
+
+class SyntheticAges(Dataset):
+    """N(0,1) images with an age-like skewed label column; weights from the GPU LDS path."""
+
+    def __init__(self, n, img_size, args, seed=0, train=True):
+        rng = np.random.RandomState(seed)
+        self.labels = np.clip(np.round(rng.gamma(6.0, 6.5, size=n)), 0, 100).astype(np.float32)
+        self.img_size, self.seed = img_size, seed
+        w = lds_prepare_weights(self.labels, args.reweight, lds=args.lds, lds_kernel=args.lds_kernel,
+                                lds_ks=args.lds_ks, lds_sigma=args.lds_sigma) if train else None
+        self.weights = None if w is None else w.cpu().numpy()
+
+    def __len__(self):
+        return len(self.labels)
+
+    def __getitem__(self, i):
+        g = torch.Generator().manual_seed(self.seed * 1000003 + i)
+        w = np.float32(1.) if self.weights is None else self.weights[i]
+        return torch.randn(3, self.img_size, self.img_size, generator=g), np.asarray([self.labels[i]], np.float32), \
+            np.asarray([w], np.float32)
+
+
+def train(train_loader, model, optimizer, epoch, args):
+    batch_time, data_time = AverageMeter('Time', ':6.2f'), AverageMeter('Data', ':6.4f')
+    losses = AverageMeter(f'Loss ({args.loss.upper()})', ':.3f')
+    progress = ProgressMeter(len(train_loader), [batch_time, data_time, losses], prefix="Epoch: [{}]".format(epoch))
+    loss_fn = globals()[f"weighted_{args.loss}_loss"]
+    model.train()
+    end = time.time()
+    for idx, (inputs, targets, weights) in enumerate(train_loader):
+        data_time.update(time.time() - end)
+        inputs, targets, weights = (t.cuda(non_blocking=True) for t in (inputs, targets, weights))
+        outputs = model(inputs, targets, epoch)
+        if args.fds:
+            outputs, _ = outputs
+        loss = loss_fn(outputs, targets, weights)
+        optimizer.zero_grad()
+        loss.backward()
+        model.reduce_gradients()
+        optimizer.step()
+        if idx % args.print_freq == 0:            # the only host sync of the loop (reference: every step)
+            value = loss.item()
+            assert not (np.isnan(value) or value > 1e6), f"Loss explosion: {value}"
+            losses.update(value, inputs.size(0))
+            batch_time.update(time.time() - end)
+            progress.display(idx)
+        end = time.time()
+
+    if args.fds and epoch >= args.start_update:
+        print(f"Create Epoch [{epoch}] features of all training data...")
+        fds = model.module.FDS
+        fds.update_last_epoch_stats(epoch)                       # order as the reference: train.py:280-281
+        if epoch >= fds._epoch_host:
+            all_labels = torch.as_tensor(np.asarray(train_loader.dataset.labels if hasattr(train_loader.dataset, 'labels')
+                                                    else train_loader.dataset.df['age'].values), dtype=torch.float32)
+            fds.begin_epoch_stats(all_labels.cuda())
+            with torch.no_grad():
+                for (inputs, targets, _) in train_loader:
+                    _, feature = model(inputs.cuda(non_blocking=True), targets.cuda(non_blocking=True), epoch)
+                    fds.accumulate_batch(feature, targets.cuda(non_blocking=True))
+            fds.finish_epoch_stats(epoch)
+    return losses.avg
+
+
+def validate(val_loader, model, prefix='Val'):
+    model.eval()
+    se, ae, n, logs = 0., 0., 0, []
+    with torch.no_grad():
+        for (inputs, targets, _) in val_loader:
+            inputs, targets = inputs.cuda(non_blocking=True), targets.cuda(non_blocking=True)
+            err = (model(inputs) - targets).abs().reshape(-1)
+            se += float((err ** 2).sum())
+            ae += float(err.sum())
+            logs.append(torch.log(err.clamp_min(1e-10)).cpu())
+            n += err.numel()
+    gmean = float(torch.exp(torch.cat(logs).mean())) if logs else float('nan')
+    print(f" * {prefix}: MSE {se / max(n, 1):.3f}\tL1 {ae / max(n, 1):.3f}\tG-Mean {gmean:.3f}")
+    return se / max(n, 1), ae / max(n, 1), gmean
+
+
+def main(argv=None):
+    args, _ = build_parser().parse_known_args(argv)
+    args.start_epoch, args.best_loss = 0, 1e5
+    args.store_name = store_name(args)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", args.gpu or 0)))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl")
+    prepare_folders(args)
+    handlers = [logging.StreamHandler()] if rank else \
+        [logging.FileHandler(os.path.join(args.store_root, args.store_name, 'training.log')), logging.StreamHandler()]
+    logging.root.handlers = []
+    logging.basicConfig(level=logging.INFO if rank == 0 else logging.WARNING, format="%(asctime)s | %(message)s",
+                        handlers=handlers)
+    print(f"Args: {args}")
+    print(f"Store name: {args.store_name}")
+
+    print('=====> Preparing data...')
+    if args.synthetic:
+        train_dataset = SyntheticAges(args.synthetic, args.img_size, args, seed=rank)
+        val_dataset = SyntheticAges(max(args.synthetic // 8, args.batch_size), args.img_size, args, seed=999, train=False)
+        test_dataset = val_dataset
+    else:
+        import pandas as pd
+        df = pd.read_csv(os.path.join(args.data_dir, f"{args.dataset}.csv"))
+        cls = AgeDB if args.dataset == 'agedb' else IMDBWIKI
+        parts = {s: df[df['split'] == s] for s in ('train', 'val', 'test')}
+        train_dataset = cls(data_dir=args.data_dir, df=parts['train'][rank::world], img_size=args.img_size, split='train',
+                            reweight=args.reweight, lds=args.lds, lds_kernel=args.lds_kernel, lds_ks=args.lds_ks,
+                            lds_sigma=args.lds_sigma)
+        val_dataset = cls(data_dir=args.data_dir, df=parts['val'], img_size=args.img_size, split='val')
+        test_dataset = cls(data_dir=args.data_dir, df=parts['test'], img_size=args.img_size, split='test')
+    mk = lambda ds, sh: DataLoader(ds, batch_size=args.batch_size, shuffle=sh, num_workers=args.workers,
+                                   pin_memory=True, drop_last=False)
+    train_loader, val_loader, test_loader = mk(train_dataset, True), mk(val_dataset, False), mk(test_dataset, False)
+    print(f"Training data size: {len(train_dataset)}")
+
+    print('=====> Building model...')
+    model = resnet50(fds=args.fds, bucket_num=args.bucket_num, bucket_start=args.bucket_start,
+                     start_update=args.start_update, start_smooth=args.start_smooth,
+                     kernel=args.fds_kernel, ks=args.fds_ks, sigma=args.fds_sigma, momentum=args.fds_mmt)
+    model = DataParallel(model.cuda())
+    model.broadcast_parameters()
+
+    if args.evaluate:
+        assert args.resume, 'Specify a trained model using [args.resume]'
+        checkpoint = torch.load(args.resume)
+        model.load_state_dict(checkpoint['state_dict'], strict=False)
+        validate(test_loader, model, prefix='Test')
+        return
+
+    if args.retrain_fc:
+        assert args.reweight != 'none' and args.pretrained
+        for name, param in model.named_parameters():
+            if 'fc' not in name and 'linear' not in name:
+                param.requires_grad = False
+
+    params = [p for p in model.parameters() if p.requires_grad]
+    gs = 1.0 / world
+    optimizer = FusedAdam(params, lr=args.lr, grad_scale=gs) if args.optimizer == 'adam' else \
+        FusedSGD(params, lr=args.lr, momentum=args.momentum, weight_decay=args.weight_decay, grad_scale=gs)
+
+    if args.pretrained:
+        checkpoint = torch.load(args.pretrained, map_location="cpu")
+        state = {k: v for k, v in checkpoint['state_dict'].items() if 'linear' not in k and 'fc' not in k}
+        model.load_state_dict(state, strict=False)
+        print(f'===> Pre-trained model loaded: {args.pretrained} ({len(state)} tensors)')
+    if args.resume and os.path.isfile(args.resume):
+        checkpoint = torch.load(args.resume, map_location='cuda')
+        args.start_epoch, args.best_loss = checkpoint['epoch'], checkpoint['best_loss']
+        model.load_state_dict(checkpoint['state_dict'])
+        optimizer.load_state_dict(checkpoint['optimizer'])
+        print(f"===> Loaded checkpoint '{args.resume}' (Epoch [{checkpoint['epoch']}])")
+
+    for epoch in range(args.start_epoch, args.epoch):
+        adjust_learning_rate(optimizer, epoch, args)
+        train_loss = train(train_loader, model, optimizer, epoch, args)
+        val_mse, val_l1, val_gmean = validate(val_loader, model)
+        metric = val_mse if args.loss == 'mse' else val_l1
+        is_best = metric < args.best_loss
+        args.best_loss = min(metric, args.best_loss)
+        if rank == 0:
+            save_checkpoint(args, {'epoch': epoch + 1, 'model': args.model, 'best_loss': args.best_loss,
+                                   'state_dict': model.state_dict(), 'optimizer': optimizer.state_dict()}, is_best)
+        print(f"Epoch #{epoch}: Train loss [{train_loss:.4f}]; Val loss: MSE [{val_mse:.4f}], L1 [{val_l1:.4f}], "
+              f"G-Mean [{val_gmean:.4f}]")
+    if is_distributed():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
