@@ -3,13 +3,14 @@
 // replaces the cuDNN convolutions behind agedb-dir/resnet.py:46-51,79,112-118
 // (forward) and their autograd backward (data and weight gradients).
 //
-// One CTA computes one 128 x BN output tile:
-//   warps 0-3  gather the A operand (im2col rows) global -> swizzled smem with
-//              16-byte cp.async (zero-fill = padding), then run the epilogue
-//              (tcgen05.ld TMEM -> registers -> global);
+// Persistent kernel: one CTA per SM walks the 128 x BN output tiles round-robin; the smem ring and the two
+// TMEM accumulators run across tile boundaries, so loads, MMAs and epilogues of neighbouring tiles overlap:
+//   warps 0-3  gather the A operand (im2col rows) global -> swizzled smem with 16-byte cp.async
+//              (zero-fill = padding);
 //   warp 4     streams the B operand (weights, or dY for wgrad) with TMA;
-//   warp 5     owns TMEM and issues tcgen05.mma from one elected thread.
-// A ring of STAGES smem slots is handed between them with mbarriers.
+//   warp 5     owns TMEM and issues tcgen05.mma from one elected thread;
+//   warps 6-9  epilogue: tcgen05.ld TMEM -> registers -> global, then hand the accumulator back.
+// mbarriers: full/empty per smem stage, full/empty per TMEM accumulator.
 //
 //   FPROP  Y[p, co]  = sum_k  A[p, k] W[co, k]      A, W K-major      (k = (r, s, c))
 //   DGRAD  dX[p, c]  = sum_k  A'[p, k] Wt[c, k]     same kernel, transposed gather (k = (r, s, co))
@@ -23,8 +24,9 @@ using namespace tc;
 
 constexpr int BM = 128;  // GEMM rows per tile (pixels; for wgrad: 2 chunks x 64 gathered channels)
 constexpr int BK = 64;   // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int kProducerThreads = 128;
-constexpr int kThreads = 192;
+constexpr int kProducerThreads = 128;   // warps 0-3
+constexpr int kTmaWarp = 4, kMmaWarp = 5; // warps 6-9: epilogue (warp & 3 = TMEM lane quarter)
+constexpr int kThreads = 320;
 
 struct IgemmParams {
   const __nv_bfloat16* src;  // gathered tensor, NHWC
@@ -37,7 +39,8 @@ struct IgemmParams {
   int num_kblocks;           // fprop/dgrad: kh*kw*cpb ; wgrad: ceil(pixels / 64)
   int kblocks_per_split;     // wgrad split-K
   int total_chunks;          // wgrad: kh*kw*cpb (64-row chunks of the K_total x Cout result)
-  int n_tiles;               // tiles along GEMM N
+  int m_tiles, n_tiles;      // tiles along GEMM M / N
+  int num_tiles;             // m_tiles * n_tiles * splits (persistent CTAs walk them round-robin)
   int ldc;                   // output row stride in elements (Cout for fprop, Cin for dgrad, Cout for wgrad partials)
   void* out;                 // bf16 [pixels][ldc]   or   fp32 [splits][total_chunks*64][ldc]
 };
@@ -47,10 +50,10 @@ struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 128) ? 3 : 4;   // ~97 KB per CTA -> two CTAs per SM overlap each other's prologue/epilogue
+  static constexpr int kStages = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);   // 192 KB ring, one persistent CTA per SM
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kSmemBytes = kBarOffset + (2 * kStages + 2) * 8 + 1024;
-  static constexpr int kTmemCols = BN;  // power of two >= 32
+  static constexpr int kSmemBytes = kBarOffset + (2 * kStages + 5) * 8 + 1024;
+  static constexpr int kTmemCols = 2 * BN;  // two accumulators (epilogue of tile i overlaps the MMAs of tile i+1)
 };
 
 // ---- A-operand gather --------------------------------------------------------------------------------
@@ -115,7 +118,7 @@ __device__ __forceinline__ const __nv_bfloat16* tap_source(const IgemmParams& P,
 }
 
 template <int BN, bool WGRAD, bool STEM>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -125,27 +128,38 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
   auto b_addr = [&](int s) { return smem_base + s * C::kStageBytes + C::kABytes; };
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
-  const uint32_t accum_bar = bar_base + 8u * (2 * C::kStages);
-  const uint32_t tmem_holder = bar_base + 8u * (2 * C::kStages + 1);
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
+  const uint32_t tmem_holder = bar_base + 8u * (2 * C::kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x % P.n_tiles;
-  const int m_tile = blockIdx.x / P.n_tiles;
-  const int split = blockIdx.y;
-  int kb_begin = 0, kb_end = P.num_kblocks;
-  if constexpr (WGRAD) {
-    kb_begin = split * P.kblocks_per_split;
-    kb_end = min(P.num_kblocks, kb_begin + P.kblocks_per_split);
-  }
-  const int nk = max(0, kb_end - kb_begin);
 
-  if (warp == 5) {
+  // tile id -> (split, m_tile, n_tile); consecutive ids share the A rows (n fastest) for L2 reuse
+  auto decode_tile = [&](int t, int& split, int& m_tile, int& n_tile, int& kb_begin, int& nk) {
+    const int per_split = P.m_tiles * P.n_tiles;
+    split = t / per_split;
+    const int rem = t - split * per_split;
+    m_tile = rem / P.n_tiles;
+    n_tile = rem - m_tile * P.n_tiles;
+    kb_begin = 0;
+    int kb_end = P.num_kblocks;
+    if constexpr (WGRAD) {
+      kb_begin = split * P.kblocks_per_split;
+      kb_end = min(P.num_kblocks, kb_begin + P.kblocks_per_split);
+    }
+    nk = max(0, kb_end - kb_begin);
+  };
+
+  if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < C::kStages; ++s) {
         mbar_init(full_bar(s), kProducerThreads + 1);
         mbar_init(empty_bar(s), 1);
       }
-      mbar_init(accum_bar, 1);
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), 4);      // one arrival per epilogue warp
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -158,164 +172,255 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_holder));
 
   if (warp < 4) {
-    // ============================ A producer ============================
+    // ============================ A producer (4 warps) ============================
+    // Address generation is hoisted out of the k-loop: per tile each thread precomputes, for its 8 rows, the
+    // element offset of the filter-tap origin and a bit mask of the taps that fall inside the image; per k-block
+    // only a (warp-uniform) tap offset is added.  wgrad rows change every k-block, so there each lane resolves ONE
+    // pixel and the quarter-warps fetch it with shuffles.
     const int j = lane & 7;          // 16-byte column served by this thread
     const int q = lane >> 3;         // row within a group of 4
-    RowPre rows8[8];                 // fprop/dgrad: the 8 rows this thread serves
-    int chunk_r = 0, chunk_s = 0, chunk_c0 = 0;
-    bool chunk_ok = true;
-    uint32_t tile_off = 0;
-    if constexpr (!WGRAD) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        rows8[i] = row_pre(P, pack_pixel(static_cast<long long>(m_tile) * BM + warp * 32 + 4 * i + q, P));
-      tile_off = warp * 32 * 128;
-    } else {
-      // warp = (chunk, half): 64 gathered channels x 32 of the 64 pixel rows of the k-block
-      const int chunk = warp >> 1;
-      const int gchunk = m_tile * 2 + chunk;           // 64-row chunk of the [K_total, Cout] result
-      chunk_ok = gchunk < P.total_chunks;
-      if constexpr (STEM) {
-        chunk_r = gchunk;                              // filter row r'
-      } else {
-        const int tap = gchunk / P.cpb;
-        chunk_c0 = (gchunk - tap * P.cpb) * 64;
-        chunk_r = tap / P.kw;
-        chunk_s = tap - chunk_r * P.kw;
-      }
-      tile_off = chunk * 8192 + (warp & 1) * 32 * 128;
-    }
-    for (int it = 0; it < nk; ++it) {
-      const int s = it % C::kStages;
-      const uint32_t ph = (it / C::kStages) & 1;
-      mbar_wait(empty_bar(s), ph ^ 1u);
-      const int kb = kb_begin + it;
-      int r, sx, coff;
-      uint32_t mypk = 0;
+    const int ntaps = STEM ? P.kh : P.kh * P.kw;
+    uint32_t cnt = 0;                // k-blocks produced so far (ring position)
+    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
+      int split, m_tile, n_tile, kb_begin, nk;
+      decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
+      long long off8[8];             // fprop/dgrad: origin offsets (elements) of the 8 rows this thread serves
+      uint32_t mask8[8];             //              valid-tap bit masks
+      int chunk_r = 0, chunk_s = 0, chunk_c0 = 0;
+      bool chunk_ok = true;
+      uint32_t tile_off = 0;
       if constexpr (!WGRAD) {
-        if constexpr (STEM) {
-          r = kb; sx = j >> 1; coff = (j & 1) * 8;
-        } else {
-          const int tap = kb / P.cpb;
-          coff = (kb - tap * P.cpb) * 64 + j * 8;
-          r = tap / P.kw;
-          sx = tap - r * P.kw;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const RowPre rp = row_pre(P, pack_pixel(static_cast<long long>(m_tile) * BM + warp * 32 + 4 * i + q, P));
+          const bool rvalid = rp.yb > -(1 << 27);
+          int oy = rp.yb, ox = rp.xb;
+          if (P.transposed && P.stride == 2) { oy >>= 1; ox >>= 1; }
+          if constexpr (STEM) ox += (j >> 1);
+          off8[i] = (static_cast<long long>(rp.nb + oy) * P.ws + ox) * P.cs + (STEM ? (j & 1) * 8 : j * 8);
+          uint32_t m = 0;
+          if (rvalid) {
+            for (int tp = 0; tp < ntaps; ++tp) {
+              int r, sx;
+              if constexpr (STEM) { r = tp; sx = j >> 1; } else { r = tp / P.kw; sx = tp - r * P.kw; }
+              bool ok;
+              (void)tap_source(P, rp, r, sx, 0, ok);
+              m |= (ok ? 1u : 0u) << tp;
+            }
+          }
+          mask8[i] = m;
         }
+        tile_off = warp * 32 * 128;
       } else {
-        r = chunk_r;
-        if constexpr (STEM) { sx = j >> 1; coff = (j & 1) * 8; } else { sx = chunk_s; coff = chunk_c0 + j * 8; }
-        mypk = chunk_ok ? pack_pixel(static_cast<long long>(kb) * 64 + (warp & 1) * 32 + lane, P) : 0u;
-      }
-      const uint32_t dst_base = a_addr(s) + tile_off;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = 4 * i + q;                     // row within this warp's 32 rows
-        RowPre rp;
-        if constexpr (!WGRAD) rp = rows8[i];
-        else rp = row_pre(P, __shfl_sync(0xffffffffu, mypk, row));
-        bool ok;
-        const __nv_bfloat16* src = tap_source(P, rp, r, sx, coff, ok);
-        cp_async16(dst_base + row * 128 + ((j ^ (row & 7)) << 4), src, ok ? 16u : 0u);
-      }
-      // the mbarrier receives this thread's arrival when all of its cp.async above have landed (no wait here:
-      // the ring depth alone bounds the loads in flight), as CUTLASS's sm100 cp.async->UMMA mainloop does
-      cp_async_mbar_arrive_noinc(full_bar(s));
-    }
-
-    // ============================== epilogue ==============================
-    mbar_wait(accum_bar, 0);
-    tcgen05_fence_after();
-    const int row = warp * 32 + lane;
-    const int n0 = n_tile * BN;
-    if constexpr (!WGRAD) {
-      const long long p = static_cast<long long>(m_tile) * BM + row;
-      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(P.out) + p * P.ldc + n0;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
-        tmem_ld_wait();
-        if (p < P.pixels && nk > 0) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-            pk[j] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          uint4* o = reinterpret_cast<uint4*>(out + c * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        // warp = (chunk, half): 64 gathered channels x 32 of the 64 pixel rows of the k-block
+        const int chunk = warp >> 1;
+        const int gchunk = m_tile * 2 + chunk;           // 64-row chunk of the [K_total, Cout] result
+        chunk_ok = gchunk < P.total_chunks;
+        if constexpr (STEM) {
+          chunk_r = gchunk;                              // filter row r'
+        } else {
+          const int tap = gchunk / P.cpb;
+          chunk_c0 = (gchunk - tap * P.cpb) * 64;
+          chunk_r = tap / P.kw;
+          chunk_s = tap - chunk_r * P.kw;
         }
+        tile_off = chunk * 8192 + (warp & 1) * 32 * 128;
       }
-    } else {
-      const int krow = m_tile * BM + row;            // row of the [K_total, Cout] result
-      const int ktot = P.total_chunks * 64;
-      float* out = reinterpret_cast<float*>(P.out) + (static_cast<size_t>(split) * ktot + krow) * P.ldc + n0;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
-        tmem_ld_wait();
-        if (krow < ktot) {
-          float4* o = reinterpret_cast<float4*>(out + c * 32);
+      for (int it = 0; it < nk; ++it, ++cnt) {
+        const int s = cnt % C::kStages;
+        const uint32_t ph = (cnt / C::kStages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const int kb = kb_begin + it;
+        const uint32_t dst_base = a_addr(s) + tile_off;
+        if constexpr (!WGRAD) {
+          // warp-uniform tap offset
+          int tp;
+          long long toff;
+          if constexpr (STEM) {
+            tp = kb;
+            toff = static_cast<long long>(kb) * P.ws * P.cs;
+          } else {
+            tp = kb / P.cpb;
+            const int c0 = (kb - tp * P.cpb) * 64;
+            int r = tp / P.kw, sx = tp - r * P.kw;
+            if (P.transposed) {
+              if (P.stride == 2) { r >>= 1; sx >>= 1; }
+              toff = c0 - static_cast<long long>(r * P.ws + sx) * P.cs;
+            } else {
+              toff = c0 + static_cast<long long>(r * P.ws + sx) * P.cs;
+            }
+          }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 t;
-            if (nk > 0)
-              t = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                              __uint_as_float(v[4 * j + 3]));
-            else
-              t = make_float4(0.f, 0.f, 0.f, 0.f);
-            o[j] = t;
+          for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + q;                   // row within this warp's 32 rows
+            const bool ok = (mask8[i] >> tp) & 1u;
+            const __nv_bfloat16* src = ok ? P.src + (off8[i] + toff) : P.src;
+            cp_async16(dst_base + row * 128 + ((j ^ (row & 7)) << 4), src, ok ? 16u : 0u);
+          }
+        } else {
+          // each lane resolves one of the warp's 32 pixels for this thread's fixed tap ...
+          const uint32_t mypk = chunk_ok ? pack_pixel(static_cast<long long>(kb) * 64 + (warp & 1) * 32 + lane, P) : 0u;
+          const RowPre rp = row_pre(P, mypk);
+          bool myok;
+          const __nv_bfloat16* myptr = tap_source(P, rp, chunk_r, STEM ? 0 : chunk_s, STEM ? 0 : chunk_c0, myok);
+          const unsigned long long myaddr = reinterpret_cast<unsigned long long>(myptr);
+          uint32_t okbits;                               // stem: validity per tap s' (4 bits); else 1 bit
+          if constexpr (STEM) {
+            okbits = 0;
+            const bool rowok = (mypk >> 31) && static_cast<unsigned>(rp.yb + chunk_r) < static_cast<unsigned>(P.hs);
+            for (int sp = 0; sp < 4; ++sp)
+              okbits |= (rowok && static_cast<unsigned>(rp.xb + sp) < static_cast<unsigned>(P.ws) ? 1u : 0u) << sp;
+          } else {
+            okbits = myok ? 1u : 0u;
+          }
+          unsigned long long rowaddr = myaddr;
+          if constexpr (STEM)   // origin of the filter row (tap s' = 0), may lie outside the image: used only when valid
+            rowaddr = reinterpret_cast<unsigned long long>(
+                P.src + ((static_cast<long long>(rp.nb + rp.yb + chunk_r) * P.ws + rp.xb) * P.cs));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + q;                   // ... and the quarter-warp serving that row fetches it
+            const unsigned long long a = __shfl_sync(0xffffffffu, rowaddr, row);
+            const uint32_t okb = __shfl_sync(0xffffffffu, okbits, row);
+            bool ok;
+            const __nv_bfloat16* src;
+            if constexpr (STEM) {
+              ok = (okb >> (j >> 1)) & 1u;
+              src = reinterpret_cast<const __nv_bfloat16*>(a) + j * 8;    // 4 taps x 16 channels are contiguous
+            } else {
+              ok = okb & 1u;
+              src = reinterpret_cast<const __nv_bfloat16*>(a) + j * 8;
+            }
+            cp_async16(dst_base + row * 128 + ((j ^ (row & 7)) << 4), ok ? src : P.src, ok ? 16u : 0u);
           }
         }
+        // the mbarrier receives this thread's arrival when all of its cp.async above have landed (no wait here:
+        // the ring depth alone bounds the loads in flight), as CUTLASS's sm100 cp.async->UMMA mainloop does
+        cp_async_mbar_arrive_noinc(full_bar(s));
       }
     }
-    tcgen05_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == kTmaWarp) {
     // ============================ B producer (TMA) ============================
     if (lane == 0) {
-      const int n0 = n_tile * BN;
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % C::kStages;
-        const uint32_t ph = (it / C::kStages) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_arrive_expect_tx(full_bar(s), C::kBBytes);
-        const int kb = kb_begin + it;
-        if constexpr (!WGRAD) {
-          tma_load_2d(b_addr(s), &tmap_b, full_bar(s), kb * BK, n0);
-        } else {
+      uint32_t cnt = 0;
+      for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
+        int split, m_tile, n_tile, kb_begin, nk;
+        decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
+        const int n0 = n_tile * BN;
+        for (int it = 0; it < nk; ++it, ++cnt) {
+          const int s = cnt % C::kStages;
+          const uint32_t ph = (cnt / C::kStages) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(s), C::kBBytes);
+          const int kb = kb_begin + it;
+          if constexpr (!WGRAD) {
+            tma_load_2d(b_addr(s), &tmap_b, full_bar(s), kb * BK, n0);
+          } else {
 #pragma unroll
-          for (int i = 0; i < BN / 64; ++i) tma_load_2d(b_addr(s) + i * 8192, &tmap_b, full_bar(s), n0 + 64 * i, kb * 64);
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(b_addr(s) + i * 8192, &tmap_b, full_bar(s), n0 + 64 * i, kb * 64);
+          }
         }
       }
     }
-  } else {
+  } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ==============================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN, WGRAD ? 1 : 0, WGRAD ? 1 : 0);
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % C::kStages;
-        const uint32_t ph = (it / C::kStages) & 1;
-        mbar_wait(full_bar(s), ph);
+      uint32_t cnt = 0, tcount = 0;
+      for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++tcount) {
+        int split, m_tile, n_tile, kb_begin, nk;
+        decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
+        const int acc = tcount & 1;
+        mbar_wait(tempty_bar(acc), ((tcount >> 1) & 1) ^ 1u);     // epilogue has drained this accumulator
         tcgen05_fence_after();
-        // K-major: 8-row atoms 1024 B apart; MN-major: 64-wide chunks 8192 B apart (LBO), 8-k atoms 1024 B (SBO)
-        const uint64_t adesc = make_smem_desc(a_addr(s), WGRAD ? 8192u : 16u, 1024u);
-        const uint64_t bdesc = make_smem_desc(b_addr(s), WGRAD ? 8192u : 16u, 1024u);
-        constexpr uint32_t kadv = WGRAD ? (2048u >> 4) : (32u >> 4);   // one UMMA_K (=16) step, in 16-byte units
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int it = 0; it < nk; ++it, ++cnt) {
+          const int s = cnt % C::kStages;
+          const uint32_t ph = (cnt / C::kStages) & 1;
+          mbar_wait(full_bar(s), ph);
+          tcgen05_fence_after();
+          // K-major: 8-row atoms 1024 B apart; MN-major: 64-wide chunks 8192 B apart (LBO), 8-k atoms 1024 B (SBO)
+          const uint64_t adesc = make_smem_desc(a_addr(s), WGRAD ? 8192u : 16u, 1024u);
+          const uint64_t bdesc = make_smem_desc(b_addr(s), WGRAD ? 8192u : 16u, 1024u);
+          constexpr uint32_t kadv = WGRAD ? (2048u >> 4) : (32u >> 4);   // one UMMA_K (=16) step, in 16-byte units
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          umma_bf16(tmem_base, adesc + static_cast<uint64_t>(k * kadv), bdesc + static_cast<uint64_t>(k * kadv), idesc,
-                    (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit(empty_bar(s));
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_d, adesc + static_cast<uint64_t>(k * kadv), bdesc + static_cast<uint64_t>(k * kadv), idesc,
+                      (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(acc));
       }
-      umma_commit(accum_bar);
     }
     __syncwarp();
+  } else {
+    // ============================== epilogue (4 warps) ==============================
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32)
+    const int row = quarter * 32 + lane;
+    uint32_t tcount = 0;
+    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++tcount) {
+      int split, m_tile, n_tile, kb_begin, nk;
+      decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
+      const int acc = tcount & 1;
+      mbar_wait(tfull_bar(acc), (tcount >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      const int n0 = n_tile * BN;
+      if constexpr (!WGRAD) {
+        const long long p = static_cast<long long>(m_tile) * BM + row;
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(P.out) + p * P.ldc + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (p < P.pixels && nk > 0) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * jj]), __uint_as_float(v[2 * jj + 1]));
+              pk[jj] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            uint4* o = reinterpret_cast<uint4*>(out + c * 32);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) o[jj] = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+          }
+        }
+      } else {
+        const int krow = m_tile * BM + row;            // row of the [K_total, Cout] result
+        const int ktot = P.total_chunks * 64;
+        float* out = reinterpret_cast<float*>(P.out) + (static_cast<size_t>(split) * ktot + krow) * P.ldc + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (krow < ktot) {
+            float4* o = reinterpret_cast<float4*>(out + c * 32);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              float4 tt;
+              if (nk > 0)
+                tt = make_float4(__uint_as_float(v[4 * jj]), __uint_as_float(v[4 * jj + 1]),
+                                 __uint_as_float(v[4 * jj + 2]), __uint_as_float(v[4 * jj + 3]));
+              else
+                tt = make_float4(0.f, 0.f, 0.f, 0.f);
+              o[jj] = tt;
+            }
+          }
+        }
+      }
+      // accumulator drained: hand it back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
   }
 
+  tcgen05_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
   }
@@ -370,11 +475,26 @@ static int launch_igemm(const CUtensorMap& tm, const IgemmParams& P, int m_tiles
                                    C::kSmemBytes));
     configured = true;
   }
-  dim3 grid(static_cast<unsigned>(m_tiles * P.n_tiles), static_cast<unsigned>(splits));
-  igemm_kernel<BN, WGRAD, STEM><<<grid, kThreads, C::kSmemBytes, st>>>(tm, P);
+  IgemmParams Q = P;
+  Q.m_tiles = m_tiles;
+  Q.num_tiles = m_tiles * P.n_tiles * splits;
+  const int grid = Q.num_tiles < num_sms() ? Q.num_tiles : num_sms();
+  igemm_kernel<BN, WGRAD, STEM><<<grid, kThreads, C::kSmemBytes, st>>>(tm, Q);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
+
+// GEMM-N tile width: 256 halves the A-operand traffic per FLOP (the conv kernels are bound by L2->SM operand
+// bandwidth), used when it still leaves >= 2 tiles per SM; else 128; 64 for 64-channel layers.
+static int pick_bn(int n_dim, long long m_tiles, int splits = 1) {
+  if (n_dim % 256 == 0 && m_tiles * (n_dim / 256) * splits >= 2LL * num_sms()) return 256;
+  if (n_dim % 128 == 0) return 128;
+  return 64;
+}
+
+#define DISPATCH_BN(bn, WG, ST, ...)                                        \
+  ((bn) == 256 ? launch_igemm<256, WG, ST>(__VA_ARGS__)                     \
+               : ((bn) == 128 ? launch_igemm<128, WG, ST>(__VA_ARGS__) : launch_igemm<64, WG, ST>(__VA_ARGS__)))
 
 static int check_shape(const ConvShape& s, bool stem, const char* who) {
   DIRB_CHECK_ARG(s.n > 0 && s.h > 0 && s.w > 0 && s.kh > 0 && s.kw > 0 && s.stride > 0 && s.pad >= 0,
@@ -399,13 +519,13 @@ int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y,
   P.pixels = static_cast<long long>(s.n) * s.ho * s.wo;
   P.num_kblocks = ktot / 64;
   P.ldc = s.cout; P.out = y;
-  const int bn = (s.cout % 128 == 0) ? 128 : 64;
-  P.n_tiles = s.cout / bn;
   const int m_tiles = static_cast<int>((P.pixels + BM - 1) / BM);
+  const int bn = pick_bn(s.cout, m_tiles);
+  P.n_tiles = s.cout / bn;
   CUtensorMap tm;
   if (int rc = make_tmap_bf16_2d(&tm, w, ktot, s.cout, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
-  if (stem) return bn == 128 ? launch_igemm<128, false, true>(tm, P, m_tiles, 1, st) : launch_igemm<64, false, true>(tm, P, m_tiles, 1, st);
-  return bn == 128 ? launch_igemm<128, false, false>(tm, P, m_tiles, 1, st) : launch_igemm<64, false, false>(tm, P, m_tiles, 1, st);
+  if (stem) return DISPATCH_BN(bn, false, true, tm, P, m_tiles, 1, st);
+  return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st);
 }
 
 // dX[n,h,w,cin] = conv_transpose(dY[n,ho,wo,cout], Wt[cin][kh][kw][cout])
@@ -421,19 +541,21 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
   P.pixels = static_cast<long long>(s.n) * s.h * s.w;
   P.num_kblocks = ktot / 64;
   P.ldc = s.cin; P.out = dx;
-  const int bn = (s.cin % 128 == 0) ? 128 : 64;
-  P.n_tiles = s.cin / bn;
   const int m_tiles = static_cast<int>((P.pixels + BM - 1) / BM);
+  const int bn = pick_bn(s.cin, m_tiles);
+  P.n_tiles = s.cin / bn;
   CUtensorMap tm;
   if (int rc = make_tmap_bf16_2d(&tm, wt, ktot, s.cin, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
-  return bn == 128 ? launch_igemm<128, false, false>(tm, P, m_tiles, 1, st) : launch_igemm<64, false, false>(tm, P, m_tiles, 1, st);
+  return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st);
 }
+
+static int wgrad_bn(const ConvShape& s) { return s.cout % 256 == 0 ? 256 : (s.cout % 128 == 0 ? 128 : 64); }
 
 int conv_wgrad_splits(const ConvShape& s) {
   const long long pixels = static_cast<long long>(s.n) * s.ho * s.wo;
   const int kblocks = static_cast<int>((pixels + 63) / 64);
   const int chunks = s.kh * s.kw * s.cin / 64;
-  const int bn = (s.cout % 128 == 0) ? 128 : 64;
+  const int bn = wgrad_bn(s);
   const int tiles = ((chunks + 1) / 2) * (s.cout / bn);
   int splits = (2 * num_sms() + tiles - 1) / tiles;
   if (splits < 1) splits = 1;
@@ -460,15 +582,15 @@ int conv_wgrad_partials(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
   const int splits = conv_wgrad_splits(s);
   P.kblocks_per_split = (P.num_kblocks + splits - 1) / splits;
   P.ldc = s.cout; P.out = partial;
-  const int bn = (s.cout % 128 == 0) ? 128 : 64;
+  const int bn = wgrad_bn(s);
   P.n_tiles = s.cout / bn;
   const int m_tiles = (P.total_chunks + 1) / 2;
   *splits_out = splits;
   CUtensorMap tm;
   if (int rc = make_tmap_bf16_2d(&tm, dy, s.cout, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cout) * 2, 64))
     return rc;
-  if (stem) return bn == 128 ? launch_igemm<128, true, true>(tm, P, m_tiles, splits, st) : launch_igemm<64, true, true>(tm, P, m_tiles, splits, st);
-  return bn == 128 ? launch_igemm<128, true, false>(tm, P, m_tiles, splits, st) : launch_igemm<64, true, false>(tm, P, m_tiles, splits, st);
+  if (stem) return DISPATCH_BN(bn, true, true, tm, P, m_tiles, splits, st);
+  return DISPATCH_BN(bn, true, false, tm, P, m_tiles, splits, st);
 }
 
 }  // namespace dirb200
