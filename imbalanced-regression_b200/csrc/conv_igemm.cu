@@ -190,25 +190,50 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
       bool chunk_ok = true;
       uint32_t tile_off = 0;
       if constexpr (!WGRAD) {
+        // lane l resolves row l of this warp's 32 rows (one pixel decode per lane, not per served row) ...
+        const RowPre rp = row_pre(P, pack_pixel(static_cast<long long>(m_tile) * BM + warp * 32 + lane, P));
+        const bool rvalid = rp.yb > -(1 << 27);
+        int oy = rp.yb, ox = rp.xb;
+        if (P.transposed && P.stride == 2) { oy >>= 1; ox >>= 1; }
+        const long long my_off = (static_cast<long long>(rp.nb + oy) * P.ws + ox) * P.cs;
+        // per-axis tap validity (bit r of vy: filter row r lands inside the image; likewise vx for columns)
+        uint32_t vy = 0, vx = 0;
+        if (rvalid) {
+          const int nky = P.kh, nkx = STEM ? 4 : P.kw;
+          for (int r = 0; r < nky; ++r) {
+            int h = P.transposed ? rp.yb - r : rp.yb + r;
+            bool ok = true;
+            if (P.transposed && P.stride == 2) { ok = (h & 1) == 0; h >>= 1; }
+            vy |= (ok && static_cast<unsigned>(h) < static_cast<unsigned>(P.hs) ? 1u : 0u) << r;
+          }
+          for (int c = 0; c < nkx; ++c) {
+            int w = P.transposed ? rp.xb - c : rp.xb + c;
+            bool ok = true;
+            if (P.transposed && P.stride == 2) { ok = (w & 1) == 0; w >>= 1; }
+            vx |= (ok && static_cast<unsigned>(w) < static_cast<unsigned>(P.ws) ? 1u : 0u) << c;
+          }
+        }
+        uint32_t my_mask;
+        if constexpr (STEM) {
+          my_mask = vy | (vx << 8);                     // taps r' in bits 0-3, column validity per s' in bits 8-11
+        } else {
+          my_mask = 0;
+          for (int r = 0; r < P.kh; ++r)
+            if ((vy >> r) & 1u) my_mask |= vx << (r * P.kw);
+        }
+        // ... and every thread fetches the 8 rows it serves
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const RowPre rp = row_pre(P, pack_pixel(static_cast<long long>(m_tile) * BM + warp * 32 + 4 * i + q, P));
-          const bool rvalid = rp.yb > -(1 << 27);
-          int oy = rp.yb, ox = rp.xb;
-          if (P.transposed && P.stride == 2) { oy >>= 1; ox >>= 1; }
-          if constexpr (STEM) ox += (j >> 1);
-          off8[i] = (static_cast<long long>(rp.nb + oy) * P.ws + ox) * P.cs + (STEM ? (j & 1) * 8 : j * 8);
-          uint32_t m = 0;
-          if (rvalid) {
-            for (int tp = 0; tp < ntaps; ++tp) {
-              int r, sx;
-              if constexpr (STEM) { r = tp; sx = j >> 1; } else { r = tp / P.kw; sx = tp - r * P.kw; }
-              bool ok;
-              (void)tap_source(P, rp, r, sx, 0, ok);
-              m |= (ok ? 1u : 0u) << tp;
-            }
+          const int row = 4 * i + q;
+          const long long o = __shfl_sync(0xffffffffu, my_off, row);
+          const uint32_t m = __shfl_sync(0xffffffffu, my_mask, row);
+          if constexpr (STEM) {
+            off8[i] = o + (j >> 1) * P.cs + (j & 1) * 8;
+            mask8[i] = ((m >> (8 + (j >> 1))) & 1u) ? (m & 0xFu) : 0u;
+          } else {
+            off8[i] = o + j * 8;
+            mask8[i] = m;
           }
-          mask8[i] = m;
         }
         tile_off = warp * 32 * 128;
       } else {
