@@ -20,6 +20,12 @@ int wgrad_reduce(const float* workspace, int splits, float* dw, const ConvShape&
                  cudaStream_t st);
 int conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* workspace, const ConvShape& s,
                bool stem, bool accumulate, cudaStream_t st);
+struct PrepDesc {               // one conv layer's weight re-layout job (see prep_weights_all)
+  size_t w_off;                 // fp32 [Cout][Cin][KH][KW] at params + w_off
+  int cout, cin, kh, kw, stem;
+  __nv_bfloat16 *wf, *wd;       // outputs (wd may be null)
+};
+int prep_weights_all(const float* params, const PrepDesc* descs_dev, int nlayers, cudaStream_t st);
 int prep_weights(const float* w, int cout, int cin, int kh, int kw, bool stem, __nv_bfloat16* wf, __nv_bfloat16* wd,
                  cudaStream_t st);
 int input_to_s2d(const float* x, int n, int h, int w, __nv_bfloat16* out, cudaStream_t st);

@@ -64,6 +64,7 @@ __global__ void input_to_s2d_kernel(const float* __restrict__ x, int n, int h, i
 }
 
 // dW[co][c][r][s] (fp32, reference layout) (+)= sum_split partial[split][(r*kw+s)*cin + c][co]
+// (one thread per element: reads coalesced along co; the transposing writes are absorbed by L2)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int cout, int cin, int kh, int kw,
                                     int accumulate, float* __restrict__ dw) {
   const int64_t ktot = (int64_t)kh * kw * cin;
@@ -94,6 +95,41 @@ __global__ void wgrad_reduce_stem_kernel(const float* __restrict__ partial, int 
     float* o = dw + ((co * 3 + c) * 7 + r) * 7 + s;
     *o = accumulate ? *o + acc : acc;
   }
+}
+
+// All conv weights of a network in ONE launch: blockIdx.y selects the layer.
+__global__ void prep_weights_all_kernel(const float* __restrict__ params, const PrepDesc* __restrict__ descs) {
+  const PrepDesc d = descs[blockIdx.y];
+  const float* w = params + d.w_off;
+  if (d.stem) {
+    const int total = d.cout * 256;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int co = i >> 8, k = i & 255;
+      const int rp = k >> 6, sp = (k >> 4) & 3, ph = (k >> 3) & 1, pw = (k >> 2) & 1, c = k & 3;
+      const int r = 2 * rp + ph - 1, s = 2 * sp + pw - 1;
+      float v = 0.f;
+      if (c < 3 && r >= 0 && s >= 0 && r < 7 && s < 7) v = w[((co * 3 + c) * 7 + r) * 7 + s];
+      d.wf[i] = __float2bfloat16_rn(v);
+    }
+    return;
+  }
+  const int64_t total = (int64_t)d.cout * d.cin * d.kh * d.kw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % d.cin);
+    int64_t t = i / d.cin;
+    int s = (int)(t % d.kw); t /= d.kw;
+    int r = (int)(t % d.kh);
+    int co = (int)(t / d.kh);
+    const __nv_bfloat16 b = __float2bfloat16_rn(w[(((int64_t)co * d.cin + c) * d.kh + r) * d.kw + s]);
+    d.wf[i] = b;
+    if (d.wd) d.wd[(((int64_t)c * d.kh + r) * d.kw + s) * d.cout + co] = b;
+  }
+}
+
+int prep_weights_all(const float* params, const PrepDesc* descs_dev, int nlayers, cudaStream_t st) {
+  prep_weights_all_kernel<<<dim3(96, nlayers), 256, 0, st>>>(params, descs_dev);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
 }
 
 static inline int grid1d(int64_t n, int block = 256) {

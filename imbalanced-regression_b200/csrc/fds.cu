@@ -394,12 +394,12 @@ int dirb200_fds_accumulate(const float* features, const int32_t* bins, int64_t n
   DIRB_LAUNCHED();
   bin_scatter_kernel<<<g, 256, 0, st>>>(bins, n, nb, offsets, cursor, perm, sbin);
   DIRB_LAUNCHED();
-  const int rows_per_chunk = n >= 65536 ? 128 : (n >= 8192 ? 32 : 8);
+  const int rows_per_chunk = n >= 65536 ? 128 : (n >= 8192 ? 16 : 8);
   const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(features) & 15) == 0);
   const int cols_per_block = 256 * (vec4 ? 4 : 1);
   dim3 grid((unsigned)((n + rows_per_chunk - 1) / rows_per_chunk), (unsigned)((d + cols_per_block - 1) / cols_per_block));
   if (vec4)
-    fds_accumulate_kernel<4, 4><<<grid, 256, 0, st>>>(features, perm, sbin, offsets, nb, d, rows_per_chunk, sums, sumsq);
+    fds_accumulate_kernel<4, 8><<<grid, 256, 0, st>>>(features, perm, sbin, offsets, nb, d, rows_per_chunk, sums, sumsq);
   else
     fds_accumulate_kernel<1, 4><<<grid, 256, 0, st>>>(features, perm, sbin, offsets, nb, d, rows_per_chunk, sums, sumsq);
   DIRB_LAUNCHED();

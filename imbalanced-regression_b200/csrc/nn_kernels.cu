@@ -8,7 +8,7 @@
 
 namespace dirb200 {
 
-constexpr int kReduceCtasPerSm = 2;   // grid cap of the column reductions (bounds the per-CTA partial buffer)
+constexpr int kReduceCtasPerSm = 4;   // grid cap of the column reductions (bounds the per-CTA partial buffer)
 
 struct V8 {
   float v[8];
@@ -62,24 +62,30 @@ __device__ __forceinline__ void column_reduce_finish(float (&acc)[K][8], int cg,
   }
 }
 
-// Sum of slot `slot` of the per-CTA partials [nblocks][K][c] for channel ch, computed by a (32, 8) thread block:
-// the 8 warps stride over the CTAs, 32 lanes cover 32 consecutive channels (coalesced 128-byte reads);
-// valid in threads with threadIdx.y == 0 after the call.
+// Sum of slot `slot` of the per-CTA partials [nblocks][K][c] for channel ch, computed by a (32, 32) thread block:
+// the 32 warps stride over the CTAs (two independent loads in flight each), 32 lanes cover 32 consecutive channels
+// (coalesced 128-byte reads); valid in threads with threadIdx.y == 0 after the call.
 __device__ __forceinline__ double sum_partials(const float* __restrict__ partial, int nblocks, int K, int slot, int c,
                                                int ch, double (*sh)[32]) {
-  double t = 0.0;
-  if (ch < c)
-    for (int b = threadIdx.y; b < nblocks; b += 8) t += (double)partial[((size_t)b * K + slot) * c + ch];
-  sh[threadIdx.y][threadIdx.x] = t;
+  double t0 = 0.0, t1 = 0.0;
+  if (ch < c) {
+    int b = threadIdx.y;
+    for (; b + 32 < nblocks; b += 64) {
+      t0 += (double)partial[((size_t)b * K + slot) * c + ch];
+      t1 += (double)partial[((size_t)(b + 32) * K + slot) * c + ch];
+    }
+    if (b < nblocks) t0 += (double)partial[((size_t)b * K + slot) * c + ch];
+  }
+  sh[threadIdx.y][threadIdx.x] = t0 + t1;
   __syncthreads();
   double r = 0.0;
   if (threadIdx.y == 0)
-    for (int w = 0; w < 8; ++w) r += sh[w][threadIdx.x];
+    for (int w = 0; w < 32; ++w) r += sh[w][threadIdx.x];
   __syncthreads();
   return r;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bn_stats_kernel(const __nv_bfloat16* __restrict__ y, int64_t rows, int c, float* __restrict__ partial) {
   const int cgroups = c / 8;
   const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
@@ -117,7 +123,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblock
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                    float* __restrict__ scale, float* __restrict__ shift) {
-  __shared__ double sh[8][32];
+  __shared__ double sh[32][32];
   const int i = blockIdx.x * 32 + threadIdx.x;
   const double sx = sum_partials(partial, nblocks, 2, 0, c, i, sh);
   const double sq = sum_partials(partial, nblocks, 2, 1, c, i, sh);
@@ -183,7 +189,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
 
 // ---- backward.  dz = (g1 [+ g2]) * (act > 0); per channel: dbeta = sum dz, dgamma = sum dz * xhat.
 // Optional second BN (the downsample branch) shares dz.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                      const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ y,
                      const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -200,7 +206,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
       is2 = loadf8(invstd2 + cg * 8);
     }
     const int64_t stride = (int64_t)gridDim.x * lanes;
-    constexpr int U = 2;   // rows in flight per thread (each row = up to 5 independent 16-byte loads)
+    constexpr int U = 1;   // one row (up to 5 independent 16-byte loads) in flight per thread; 4 CTAs per SM
     for (int64_t r0 = blockIdx.x * (int64_t)lanes + lane; r0 < rows; r0 += U * stride) {
       V8 gv[U], g2v[U], av[U], xv[U], x2v[U];
       bool ok[U];
@@ -260,7 +266,7 @@ __global__ void bn_bwd_coeffs_kernel(const float* __restrict__ partial, int nblo
                                      int c, const float* __restrict__ mean, const float* __restrict__ invstd,
                                      const float* __restrict__ gamma, float* __restrict__ grad_gamma,
                                      float* __restrict__ grad_beta, float* __restrict__ coef /* [3][c] */) {
-  __shared__ double sh[8][32];
+  __shared__ double sh[32][32];
   const int i = blockIdx.x * 32 + threadIdx.x;
   const double db = sum_partials(partial, nblocks, K, 0, c, i, sh);
   const double dg = sum_partials(partial, nblocks, K, gslot, c, i, sh);
@@ -545,7 +551,7 @@ int bn_stats(const __nv_bfloat16* y, int64_t rows, int c, float* partial, int* n
 int bn_finalize(const float* partial, int nblocks, int64_t rows, int c, const float* gamma, const float* beta,
                 float eps, float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
                 float* scale, float* shift, cudaStream_t st) {
-  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 8), 0, st>>>(partial, nblocks, rows, c, gamma, beta, eps, momentum, running_mean,
+  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, st>>>(partial, nblocks, rows, c, gamma, beta, eps, momentum, running_mean,
                                                     running_var, mean, invstd, scale, shift);
   DIRB_LAUNCHED();
   return DIRB200_OK;
@@ -584,7 +590,7 @@ int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_b
 int bn_bwd_coeffs(const float* partial, int nblocks, int k, int gslot, int64_t rows, int c, const float* mean,
                   const float* invstd, const float* gamma, float* grad_gamma, float* grad_beta, float* coef,
                   cudaStream_t st) {
-  bn_bwd_coeffs_kernel<<<(c + 31) / 32, dim3(32, 8), 0, st>>>(partial, nblocks, k, gslot, rows, c, mean, invstd, gamma,
+  bn_bwd_coeffs_kernel<<<(c + 31) / 32, dim3(32, 32), 0, st>>>(partial, nblocks, k, gslot, rows, c, mean, invstd, gamma,
                                                       grad_gamma, grad_beta, coef);
   DIRB_LAUNCHED();
   return DIRB200_OK;

@@ -53,6 +53,8 @@ struct dirb200_net {
   __nv_bfloat16* scratch[8] = {};
   float* wgrad_ws = nullptr;
   float* bn_partial = nullptr;   // per-CTA partial sums of the BN column reductions
+  PrepDesc* prep_descs = nullptr; // device table for the single weight re-layout launch
+  int num_convs = 0;
   size_t param_count = 0, running_count = 0, activation_bytes = 0;
   std::vector<void*> allocs;
   bool forward_was_training = false;
@@ -158,7 +160,20 @@ static bool build(dirb200_net* net, const int* blocks_per_stage, int num_stages)
   }
   NET_ALLOC(net->wgrad_ws, ws);
   NET_ALLOC(net->bn_partial, sizeof(float) * bn_partial_floats(net->feat_c));
-  return true;
+  std::vector<PrepDesc> descs;
+  auto add = [&](const ConvLayer& cv) {
+    descs.push_back(PrepDesc{cv.w_off, cv.s.cout, cv.stem ? 3 : cv.s.cin, cv.stem ? 7 : cv.s.kh, cv.stem ? 7 : cv.s.kw,
+                             cv.stem ? 1 : 0, cv.wf, cv.wd});
+  };
+  add(net->stem);
+  for (Block& B : net->blocks) {
+    add(B.c1); add(B.c2); add(B.c3);
+    if (B.has_ds) add(B.ds);
+  }
+  net->num_convs = (int)descs.size();
+  NET_ALLOC(net->prep_descs, sizeof(PrepDesc) * descs.size());
+  return cudaMemcpy(net->prep_descs, descs.data(), sizeof(PrepDesc) * descs.size(), cudaMemcpyHostToDevice) ==
+         cudaSuccess;
 }
 
 #define RUN(expr)                    \
@@ -200,8 +215,6 @@ static inline void prof_end(dirb200_net* net, cudaStream_t st) {
 
 static int conv_bn_forward(dirb200_net* net, ConvLayer& cv, const __nv_bfloat16* in, const float* params,
                            float* running, bool training, cudaStream_t st) {
-  RUNP(kPrep, prep_weights(params + cv.w_off, cv.s.cout, cv.stem ? 3 : cv.s.cin, cv.stem ? 7 : cv.s.kh,
-                           cv.stem ? 7 : cv.s.kw, cv.stem, cv.wf, cv.wd, st));
   RUNP(kFprop, conv_fprop(in, cv.wf, cv.y, cv.s, cv.stem, st));
   BNLayer& bn = cv.bn;
   if (training) {
@@ -304,6 +317,7 @@ int dirb200_resnet_forward(dirb200_net* net, const float* x_nchw, const float* p
   DIRB_CHECK_ARG(training || bn_running, "resnet_forward: eval mode needs the running statistics");
   cudaStream_t st = as_stream(stream);
   const bool tr = training != 0;
+  RUNP(kPrep, prep_weights_all(params, net->prep_descs, net->num_convs, st));
   RUNP(kPrep, input_to_s2d(x_nchw, net->n, net->h, net->w, net->x_s2d, st));
   RUN(conv_bn_forward(net, net->stem, net->x_s2d, params, bn_running, tr, st));
   RUNP(kPool, maxpool_fwd(net->stem.a, net->n, net->stem.s.ho, net->stem.s.wo, 64, net->pool_out, net->pool_idx, st));
