@@ -187,62 +187,54 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
   }
 }
 
-// ---- backward.  dz = (g1 [+ g2]) * (act > 0); per channel: dbeta = sum dz, dgamma = sum dz * xhat.
-// Optional second BN (the downsample branch) shares dz.
+// ---- backward.  dz = (g1 [+ g2]) * (act > 0).  The reduction accumulates the raw moments
+//   S0 = sum dz,  S1 = sum dz*y  [, S2 = sum dz*y2 for the downsample-branch BN that shares dz];
+// dbeta = S0 and dgamma = invstd * (S1 - mean*S0) are formed in fp64 by bn_bwd_coeffs_kernel.  Keeping mean/invstd
+// out of the streaming loop keeps the kernel within 64 registers (no local-memory spills: the first version was
+// L1-bound on spill traffic, ncu profiles/).
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+
 __global__ void __launch_bounds__(256, 4)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                      const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ y,
-                     const float* __restrict__ mean, const float* __restrict__ invstd,
-                     const __nv_bfloat16* __restrict__ y2, const float* __restrict__ mean2,
-                     const float* __restrict__ invstd2, int64_t rows, int c, float* __restrict__ partial) {
+                     const __nv_bfloat16* __restrict__ y2, int64_t rows, int c, float* __restrict__ partial) {
   const int cgroups = c / 8;
   const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
   float acc[3][8] = {};
-  if (lane < lanes) {
-    const V8 mu = loadf8(mean + cg * 8), is = loadf8(invstd + cg * 8);
-    V8 mu2{}, is2{};
-    if (y2) {
-      mu2 = loadf8(mean2 + cg * 8);
-      is2 = loadf8(invstd2 + cg * 8);
-    }
-    const int64_t stride = (int64_t)gridDim.x * lanes;
-    constexpr int U = 1;   // one row (up to 5 independent 16-byte loads) in flight per thread; 4 CTAs per SM
-    for (int64_t r0 = blockIdx.x * (int64_t)lanes + lane; r0 < rows; r0 += U * stride) {
-      V8 gv[U], g2v[U], av[U], xv[U], x2v[U];
-      bool ok[U];
+  const int64_t stride = (int64_t)gridDim.x * lanes;
+  for (int64_t r = blockIdx.x * (int64_t)lanes + lane; r < rows; r += stride) {
+    const int64_t off = r * c + cg * 8;
+    const uint4 G = *reinterpret_cast<const uint4*>(g1 + off);
+    const uint4 Y = *reinterpret_cast<const uint4*>(y + off);
+    uint4 G2 = make_uint4(0, 0, 0, 0), A = make_uint4(0, 0, 0, 0), Y2 = make_uint4(0, 0, 0, 0);
+    if (g2) G2 = *reinterpret_cast<const uint4*>(g2 + off);
+    if (act) A = *reinterpret_cast<const uint4*>(act + off);
+    if (y2) Y2 = *reinterpret_cast<const uint4*>(y2 + off);
+    const uint32_t gw[4] = {G.x, G.y, G.z, G.w}, g2w[4] = {G2.x, G2.y, G2.z, G2.w}, aw[4] = {A.x, A.y, A.z, A.w};
+    const uint32_t yw[4] = {Y.x, Y.y, Y.z, Y.w}, y2w[4] = {Y2.x, Y2.y, Y2.z, Y2.w};
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t r = r0 + u * stride;
-        ok[u] = r < rows;
-        if (!ok[u]) continue;
-        const int64_t off = r * c + cg * 8;
-        gv[u] = load8(g1 + off);
-        if (g2) g2v[u] = load8(g2 + off);
-        if (act) av[u] = load8(act + off);
-        xv[u] = load8(y + off);
-        if (y2) x2v[u] = load8(y2 + off);
+    for (int w = 0; w < 4; ++w) {
+      float2 g = bf2_to_f2(gw[w]);
+      if (g2) {
+        const float2 t = bf2_to_f2(g2w[w]);
+        g.x += t.x;
+        g.y += t.y;
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (!ok[u]) continue;
-        V8 g = gv[u];
-        if (g2) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g.v[j] += g2v[u].v[j];
-        }
-        if (act) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g.v[j] = av[u].v[j] > 0.f ? g.v[j] : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[0][j] += g.v[j];
-          acc[1][j] = fmaf(g.v[j], (xv[u].v[j] - mu.v[j]) * is.v[j], acc[1][j]);
-        }
-        if (y2) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[2][j] = fmaf(g.v[j], (x2v[u].v[j] - mu2.v[j]) * is2.v[j], acc[2][j]);
-        }
+      if (act) {   // relu output > 0  <=>  magnitude bits non-zero (handles -0)
+        if ((aw[w] & 0x00007fffu) == 0u) g.x = 0.f;
+        if ((aw[w] & 0x7fff0000u) == 0u) g.y = 0.f;
+      }
+      const float2 yv = bf2_to_f2(yw[w]);
+      acc[0][2 * w] += g.x;
+      acc[0][2 * w + 1] += g.y;
+      acc[1][2 * w] = fmaf(g.x, yv.x, acc[1][2 * w]);
+      acc[1][2 * w + 1] = fmaf(g.y, yv.y, acc[1][2 * w + 1]);
+      if (y2) {
+        const float2 y2v = bf2_to_f2(y2w[w]);
+        acc[2][2 * w] = fmaf(g.x, y2v.x, acc[2][2 * w]);
+        acc[2][2 * w + 1] = fmaf(g.y, y2v.y, acc[2][2 * w + 1]);
       }
     }
   }
@@ -269,9 +261,10 @@ __global__ void bn_bwd_coeffs_kernel(const float* __restrict__ partial, int nblo
   __shared__ double sh[32][32];
   const int i = blockIdx.x * 32 + threadIdx.x;
   const double db = sum_partials(partial, nblocks, K, 0, c, i, sh);
-  const double dg = sum_partials(partial, nblocks, K, gslot, c, i, sh);
+  const double s1 = sum_partials(partial, nblocks, K, gslot, c, i, sh);
   if (threadIdx.y != 0 || i >= c) return;
   const double n = (double)rows, is = (double)invstd[i], ga = (double)gamma[i], mu = (double)mean[i];
+  const double dg = is * (s1 - mu * db);          // sum dz * xhat from the raw moments
   coef[i] = (float)(ga * is);
   coef[c + i] = (float)(-ga * is * is * dg / n);
   coef[2 * c + i] = (float)(ga * is * (mu * is * dg / n - db / n));
@@ -581,8 +574,8 @@ int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_b
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_bwd_reduce: unsupported channel count %d", c);
   const int lanes = 256 / cgroups;
   *nblocks = reduce_grid(rows, lanes);
-  bn_bwd_reduce_kernel<<<*nblocks, 256, 256 * 24 * sizeof(float), st>>>(g1, g2, act, y, mean, invstd, y2, mean2,
-                                                                         invstd2, rows, c, partial);
+  (void)mean; (void)invstd; (void)mean2; (void)invstd2;   // the moments are centred in bn_bwd_coeffs
+  bn_bwd_reduce_kernel<<<*nblocks, 256, 256 * 24 * sizeof(float), st>>>(g1, g2, act, y, y2, rows, c, partial);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
