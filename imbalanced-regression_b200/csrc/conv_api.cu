@@ -63,30 +63,30 @@ __global__ void input_to_s2d_kernel(const float* __restrict__ x, int n, int h, i
   }
 }
 
-// dW[co][c][r][s] (fp32, reference layout) (+)= sum_split partial[split][(r*kw+s)*cin + c][co]
-// (one thread per element: reads coalesced along co; the transposing writes are absorbed by L2)
+// dW[co][c][r][s] (fp32, reference layout) (+)= sum_split partial[split][co][(r*kw+s)*cin + c]
+// (partials arrive transposed from the wgrad epilogue: reads are coalesced along k, writes permute (tap, c) -> (c, tap)
+// inside one filter's contiguous run)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int cout, int cin, int kh, int kw,
                                     int accumulate, float* __restrict__ dw) {
   const int64_t ktot = (int64_t)kh * kw * cin;
   const int64_t total = ktot * cout;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int co = (int)(i % cout);
-    const int64_t k = i / cout;
-    float acc = 0.f;
-    for (int sp = 0; sp < splits; ++sp) acc += partial[(int64_t)sp * total + i];
-    const int c = (int)(k % cin);
-    const int t = (int)(k / cin);
-    const int r = t / kw, s = t - r * kw;
-    float* o = dw + (((int64_t)co * cin + c) * kh + r) * kw + s;
-    *o = accumulate ? *o + acc : acc;
-  }
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;     // = co * ktot + k
+  if (i >= total) return;
+  const int co = (int)(i / ktot);
+  const int64_t k = i - (int64_t)co * ktot;
+  float acc = 0.f;
+  for (int sp = 0; sp < splits; ++sp) acc += partial[(int64_t)sp * total + i];
+  const int c = (int)(k % cin);
+  const int t = (int)(k / cin);
+  float* o = dw + ((int64_t)co * cin + c) * (kh * kw) + t;
+  *o = accumulate ? *o + acc : acc;
 }
 
 __global__ void wgrad_reduce_stem_kernel(const float* __restrict__ partial, int splits, int cout, int accumulate,
                                          float* __restrict__ dw) {
-  const int total = 256 * cout;
+  const int total = 256 * cout;                   // partial[split][co][k], k = (r', s', ph, pw, c4)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int co = i % cout, k = i / cout;
+    const int co = i >> 8, k = i & 255;
     const int rp = k >> 6, sp_ = (k >> 4) & 3, ph = (k >> 3) & 1, pw = (k >> 2) & 1, c = k & 3;
     const int r = 2 * rp + ph - 1, s = 2 * sp_ + pw - 1;
     if (c >= 3 || r < 0 || s < 0) continue;
@@ -160,8 +160,12 @@ int wgrad_reduce(const float* workspace, int splits, float* dw, const ConvShape&
   if (stem)
     wgrad_reduce_stem_kernel<<<grid1d(256 * (int64_t)s.cout), 256, 0, st>>>(workspace, splits, s.cout, accumulate, dw);
   else
-    wgrad_reduce_kernel<<<grid1d((int64_t)s.kh * s.kw * s.cin * s.cout), 256, 0, st>>>(workspace, splits, s.cout,
-                                                                                       s.cin, s.kh, s.kw, accumulate, dw);
+  {
+    // latency-bound gather/scatter: one thread per weight so that every load is in flight at once
+    const int64_t total = (int64_t)s.kh * s.kw * s.cin * s.cout;
+    wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(workspace, splits, s.cout, s.cin, s.kh, s.kw,
+                                                                         accumulate, dw);
+  }
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }

@@ -15,6 +15,7 @@
 //   FPROP  Y[p, co]  = sum_k  A[p, k] W[co, k]      A, W K-major      (k = (r, s, c))
 //   DGRAD  dX[p, c]  = sum_k  A'[p, k] Wt[c, k]     same kernel, transposed gather (k = (r, s, co))
 //   WGRAD  dW[k, co] = sum_p  A[p, k] dY[p, co]     both operands MN-major, K = pixels, split-K partials
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc.cuh"
 #include "conv.cuh"
@@ -34,6 +35,13 @@ struct IgemmParams {
   int hm, wm;                // pixel grid that indexes GEMM rows (fprop/wgrad: conv output grid; dgrad: conv input grid)
   int kh, kw, stride, pad;
   int transposed;            // 0: fprop-style gather, 1: dgrad-style (source = dY of a strided conv)
+  // stride-2 dgrad runs as 4 launches, one per output-pixel parity class (py, px): rows index the class grid
+  // (hm x wm), the real pixel is (2y'+py, 2x'+px) of the full_h x full_w image, and only the filter taps whose
+  // parity matches (tap_list) are visited -- 9 tap-passes over quarter-size grids instead of 9 over the full one.
+  int cls_on, cls_py, cls_px, full_h, full_w;
+  int nstages;               // B-stationary mode: A-ring depth that fits beside the resident weights
+  int ntaps_c;               // taps visited by this launch
+  int tap_list[9];           // their indices r*kw + s (identity when cls_on == 0)
   int cpb;                   // 64-channel blocks per filter tap (cs / 64); stem: unused
   long long pixels;          // n * hm * wm
   int num_kblocks;           // fprop/dgrad: kh*kw*cpb ; wgrad: ceil(pixels / 64)
@@ -52,7 +60,8 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);   // 192 KB ring, one persistent CTA per SM
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kSmemBytes = kBarOffset + (2 * kStages + 5) * 8 + 1024;
+  static constexpr int kSmemBytes = kBarOffset + (2 * kStages + 6) * 8 + 1024;
+  // B-stationary layout: nstages (<= kStages) A slots, then the whole B matrix; barriers stay at kBarOffset
   static constexpr int kTmemCols = 2 * BN;  // two accumulators (epilogue of tile i overlaps the MMAs of tile i+1)
 };
 
@@ -80,7 +89,12 @@ struct RowPre {
 };
 __device__ __forceinline__ RowPre row_pre(const IgemmParams& P, uint32_t pk) {
   RowPre rp;
-  const int n = (pk >> 18) & 0x1FFF, y = (pk >> 9) & 0x1FF, x = pk & 0x1FF;
+  const int n = (pk >> 18) & 0x1FFF;
+  int y = (pk >> 9) & 0x1FF, x = pk & 0x1FF;
+  if (P.cls_on) {
+    y = 2 * y + P.cls_py;
+    x = 2 * x + P.cls_px;
+  }
   rp.nb = n * P.hs;
   if (!P.transposed) {
     rp.yb = y * P.stride - P.pad;
@@ -117,15 +131,23 @@ __device__ __forceinline__ const __nv_bfloat16* tap_source(const IgemmParams& P,
   return ok ? P.src + (static_cast<size_t>(rp.nb + hi) * P.ws + wi) * P.cs + coff : P.src;
 }
 
-template <int BN, bool WGRAD, bool STEM>
+// BSTAT ("B stationary"): when every tile of the launch uses the same B matrix (one N tile) and it fits in smem, the
+// whole weight matrix is loaded once per CTA and the ring carries only the gathered A rows -- removes the per-tile
+// re-fetch of the weights through L2 for the narrow layers (stem, 64/128-channel convs).
+template <int BN, bool WGRAD, bool STEM, bool BSTAT = false>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
   using C = Cfg<BN>;
+  static_assert(!(BSTAT && WGRAD), "B-stationary mode is for fprop/dgrad");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + C::kBarOffset;
-  auto a_addr = [&](int s) { return smem_base + s * C::kStageBytes; };
+  // BSTAT layout: [kStages x A (16 KB)] [B: num_kblocks x kBBytes] ; else [kStages x (A | B)]
+  auto a_addr = [&](int s) { return smem_base + s * (BSTAT ? C::kABytes : C::kStageBytes); };
   auto b_addr = [&](int s) { return smem_base + s * C::kStageBytes + C::kABytes; };
+  const uint32_t nstages = BSTAT ? static_cast<uint32_t>(P.nstages) : static_cast<uint32_t>(C::kStages);
+  const uint32_t bstat_base = smem_base + nstages * C::kABytes;
+  const uint32_t bstat_bar = bar_base + 8u * (2 * C::kStages + 5);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
@@ -153,9 +175,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < C::kStages; ++s) {
-        mbar_init(full_bar(s), kProducerThreads + 1);
+        mbar_init(full_bar(s), kProducerThreads + (BSTAT ? 0 : 1));
         mbar_init(empty_bar(s), 1);
       }
+      mbar_init(bstat_bar, 1);
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);
         mbar_init(tempty_bar(a), 4);      // one arrival per epilogue warp
@@ -252,8 +275,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
         tile_off = chunk * 8192 + (warp & 1) * 32 * 128;
       }
       for (int it = 0; it < nk; ++it, ++cnt) {
-        const int s = cnt % C::kStages;
-        const uint32_t ph = (cnt / C::kStages) & 1;
+        const int s = static_cast<int>(cnt % nstages);
+        const uint32_t ph = (cnt / nstages) & 1;
         mbar_wait(empty_bar(s), ph ^ 1u);
         const int kb = kb_begin + it;
         const uint32_t dst_base = a_addr(s) + tile_off;
@@ -265,8 +288,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
             tp = kb;
             toff = static_cast<long long>(kb) * P.ws * P.cs;
           } else {
-            tp = kb / P.cpb;
-            const int c0 = (kb - tp * P.cpb) * 64;
+            const int tc = kb / P.cpb;
+            tp = P.tap_list[tc];
+            const int c0 = (kb - tc * P.cpb) * 64;
             int r = tp / P.kw, sx = tp - r * P.kw;
             if (P.transposed) {
               if (P.stride == 2) { r >>= 1; sx >>= 1; }
@@ -326,20 +350,36 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
     }
   } else if (warp == kTmaWarp) {
     // ============================ B producer (TMA) ============================
-    if (lane == 0) {
+    if (lane == 0 && BSTAT) {
+      // the whole B matrix, once
+      mbar_arrive_expect_tx(bstat_bar, static_cast<uint32_t>(P.num_kblocks) * C::kBBytes);
+      for (int kb = 0; kb < P.num_kblocks; ++kb) {
+        int kcoord = kb;
+        if constexpr (!STEM) {
+          const int tc = kb / P.cpb;
+          kcoord = P.tap_list[tc] * P.cpb + (kb - tc * P.cpb);
+        }
+        tma_load_2d(bstat_base + kb * C::kBBytes, &tmap_b, bstat_bar, kcoord * BK, 0);
+      }
+    } else if (lane == 0) {
       uint32_t cnt = 0;
       for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
         int split, m_tile, n_tile, kb_begin, nk;
         decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
         const int n0 = n_tile * BN;
         for (int it = 0; it < nk; ++it, ++cnt) {
-          const int s = cnt % C::kStages;
-          const uint32_t ph = (cnt / C::kStages) & 1;
+          const int s = static_cast<int>(cnt % nstages);
+          const uint32_t ph = (cnt / nstages) & 1;
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_arrive_expect_tx(full_bar(s), C::kBBytes);
           const int kb = kb_begin + it;
           if constexpr (!WGRAD) {
-            tma_load_2d(b_addr(s), &tmap_b, full_bar(s), kb * BK, n0);
+            int kcoord = kb;
+            if constexpr (!STEM) {
+              const int tc = kb / P.cpb;
+              kcoord = P.tap_list[tc] * P.cpb + (kb - tc * P.cpb);
+            }
+            tma_load_2d(b_addr(s), &tmap_b, full_bar(s), kcoord * BK, n0);
           } else {
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i)
@@ -353,6 +393,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN, WGRAD ? 1 : 0, WGRAD ? 1 : 0);
       uint32_t cnt = 0, tcount = 0;
+      if constexpr (BSTAT) mbar_wait(bstat_bar, 0);
       for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++tcount) {
         int split, m_tile, n_tile, kb_begin, nk;
         decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
@@ -361,13 +402,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int it = 0; it < nk; ++it, ++cnt) {
-          const int s = cnt % C::kStages;
-          const uint32_t ph = (cnt / C::kStages) & 1;
+          const int s = static_cast<int>(cnt % nstages);
+          const uint32_t ph = (cnt / nstages) & 1;
           mbar_wait(full_bar(s), ph);
           tcgen05_fence_after();
           // K-major: 8-row atoms 1024 B apart; MN-major: 64-wide chunks 8192 B apart (LBO), 8-k atoms 1024 B (SBO)
           const uint64_t adesc = make_smem_desc(a_addr(s), WGRAD ? 8192u : 16u, 1024u);
-          const uint64_t bdesc = make_smem_desc(b_addr(s), WGRAD ? 8192u : 16u, 1024u);
+          const uint64_t bdesc =
+              make_smem_desc(BSTAT ? bstat_base + static_cast<uint32_t>(kb_begin + it) * C::kBBytes : b_addr(s),
+                             WGRAD ? 8192u : 16u, 1024u);
           constexpr uint32_t kadv = WGRAD ? (2048u >> 4) : (32u >> 4);   // one UMMA_K (=16) step, in 16-byte units
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
@@ -394,7 +437,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
       const int n0 = n_tile * BN;
       if constexpr (!WGRAD) {
         const long long p = static_cast<long long>(m_tile) * BM + row;
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(P.out) + p * P.ldc + n0;
+        long long orow = p;
+        if (P.cls_on && p < P.pixels) {           // class pixel -> row of the full image
+          const uint32_t pk = pack_pixel(p, P);
+          const int n = (pk >> 18) & 0x1FFF, yy = (pk >> 9) & 0x1FF, xx = pk & 0x1FF;
+          orow = (static_cast<long long>(n) * P.full_h + 2 * yy + P.cls_py) * P.full_w + 2 * xx + P.cls_px;
+        }
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(P.out) + orow * P.ldc + n0;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t v[32];
@@ -413,26 +462,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
           }
         }
       } else {
+        // partials are stored TRANSPOSED, [split][Cout][K_total]: the 32 lanes of a warp hold 32 consecutive k rows,
+        // so each scalar store below is one coalesced 128-byte line, and the reduce kernel reads/writes along k
         const int krow = m_tile * BM + row;            // row of the [K_total, Cout] result
         const int ktot = P.total_chunks * 64;
-        float* out = reinterpret_cast<float*>(P.out) + (static_cast<size_t>(split) * ktot + krow) * P.ldc + n0;
+        float* out = reinterpret_cast<float*>(P.out) + (static_cast<size_t>(split) * P.ldc + n0) * ktot + krow;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
           if (krow < ktot) {
-            float4* o = reinterpret_cast<float4*>(out + c * 32);
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              float4 tt;
-              if (nk > 0)
-                tt = make_float4(__uint_as_float(v[4 * jj]), __uint_as_float(v[4 * jj + 1]),
-                                 __uint_as_float(v[4 * jj + 2]), __uint_as_float(v[4 * jj + 3]));
-              else
-                tt = make_float4(0.f, 0.f, 0.f, 0.f);
-              o[jj] = tt;
-            }
+            for (int jj = 0; jj < 32; ++jj)
+              out[static_cast<size_t>(c * 32 + jj) * ktot] = nk > 0 ? __uint_as_float(v[jj]) : 0.f;
           }
         }
       }
@@ -491,22 +534,43 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t
   return DIRB200_OK;
 }
 
-template <int BN, bool WGRAD, bool STEM>
-static int launch_igemm(const CUtensorMap& tm, const IgemmParams& P, int m_tiles, int splits, cudaStream_t st) {
+template <int BN, bool WGRAD, bool STEM, bool BSTAT>
+static int launch_igemm_impl(const CUtensorMap& tm, const IgemmParams& Q, cudaStream_t st) {
   using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
-    DIRB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, WGRAD, STEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DIRB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, WGRAD, STEM, BSTAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    C::kSmemBytes));
     configured = true;
   }
+  const int grid = Q.num_tiles < num_sms() ? Q.num_tiles : num_sms();
+  igemm_kernel<BN, WGRAD, STEM, BSTAT><<<grid, kThreads, C::kSmemBytes, st>>>(tm, Q);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+template <int BN, bool WGRAD, bool STEM>
+static int launch_igemm(const CUtensorMap& tm, const IgemmParams& P, int m_tiles, int splits, cudaStream_t st) {
+  using C = Cfg<BN>;
   IgemmParams Q = P;
   Q.m_tiles = m_tiles;
   Q.num_tiles = m_tiles * P.n_tiles * splits;
-  const int grid = Q.num_tiles < num_sms() ? Q.num_tiles : num_sms();
-  igemm_kernel<BN, WGRAD, STEM><<<grid, kThreads, C::kSmemBytes, st>>>(tm, Q);
-  DIRB_LAUNCHED();
-  return DIRB200_OK;
+  if constexpr (!WGRAD) {
+    // B stationary when one N tile covers the layer, the weights fit beside the A ring and there are enough
+    // tiles per CTA to amortise the one-off load
+    const int bbytes = P.num_kblocks * C::kBBytes;
+    int ns = (C::kBarOffset - bbytes) / C::kABytes;
+    if (ns > C::kStages) ns = C::kStages;
+    static const bool bstat_enabled = [] {
+      const char* e = getenv("DIRB200_BSTAT");
+      return e != nullptr && e[0] == '1';     // off by default: measured 3 % slower on ResNet-50 (L2 is not the limiter there)
+    }();
+    if (bstat_enabled && P.n_tiles == 1 && ns >= 4 && Q.num_tiles >= 4 * num_sms()) {
+      Q.nstages = ns;
+      return launch_igemm_impl<BN, false, STEM, true>(tm, Q, st);
+    }
+  }
+  return launch_igemm_impl<BN, WGRAD, STEM, false>(tm, Q, st);
 }
 
 // GEMM-N tile width: 256 halves the A-operand traffic per FLOP (the conv kernels are bound by L2->SM operand
@@ -543,6 +607,9 @@ int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y,
   P.cpb = stem ? 1 : s.cin / 64;
   P.pixels = static_cast<long long>(s.n) * s.ho * s.wo;
   P.num_kblocks = ktot / 64;
+  P.ntaps_c = s.kh * s.kw;
+  DIRB_CHECK_ARG(stem || P.ntaps_c <= 9, "conv_fprop: at most 9 filter taps (got %dx%d)", s.kh, s.kw);
+  for (int i = 0; i < 9; ++i) P.tap_list[i] = i;
   P.ldc = s.cout; P.out = y;
   const int m_tiles = static_cast<int>((P.pixels + BM - 1) / BM);
   const int bn = pick_bn(s.cout, m_tiles);
@@ -558,20 +625,56 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
                cudaStream_t st) {
   if (int rc = check_shape(s, false, "conv_dgrad")) return rc;
   DIRB_CHECK_ARG(s.stride == 1 || s.stride == 2, "conv_dgrad: stride must be 1 or 2 (got %d)", s.stride);
+  DIRB_CHECK_ARG(s.kh * s.kw <= 9, "conv_dgrad: at most 9 filter taps (got %dx%d)", s.kh, s.kw);
   const int ktot = s.kh * s.kw * s.cout;
   IgemmParams P{};
   P.src = dy; P.n = s.n; P.hs = s.ho; P.ws = s.wo; P.cs = s.cout; P.hm = s.h; P.wm = s.w;
   P.kh = s.kh; P.kw = s.kw; P.stride = s.stride; P.pad = s.pad; P.transposed = 1;
   P.cpb = s.cout / 64;
-  P.pixels = static_cast<long long>(s.n) * s.h * s.w;
-  P.num_kblocks = ktot / 64;
   P.ldc = s.cin; P.out = dx;
-  const int m_tiles = static_cast<int>((P.pixels + BM - 1) / BM);
-  const int bn = pick_bn(s.cin, m_tiles);
-  P.n_tiles = s.cin / bn;
   CUtensorMap tm;
-  if (int rc = make_tmap_bf16_2d(&tm, wt, ktot, s.cin, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
-  return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st);
+  if (s.stride == 1) {
+    P.pixels = static_cast<long long>(s.n) * s.h * s.w;
+    P.ntaps_c = s.kh * s.kw;
+    for (int i = 0; i < 9; ++i) P.tap_list[i] = i;
+    P.num_kblocks = ktot / 64;
+    const int m_tiles = static_cast<int>((P.pixels + BM - 1) / BM);
+    const int bn = pick_bn(s.cin, m_tiles);
+    P.n_tiles = s.cin / bn;
+    if (int rc = make_tmap_bf16_2d(&tm, wt, ktot, s.cin, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
+    return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st);
+  }
+  // stride 2: one launch per output-pixel parity class; a class without any tap receives no gradient (zeros)
+  bool need_zero = false;
+  for (int cls = 0; cls < 4; ++cls) {
+    const int py = cls >> 1, px = cls & 1;
+    int nt = 0;
+    for (int r = 0; r < s.kh; ++r)
+      for (int q = 0; q < s.kw; ++q)
+        if (((py + s.pad - r) & 1) == 0 && ((px + s.pad - q) & 1) == 0) ++nt;
+    if (nt == 0) need_zero = true;
+  }
+  if (need_zero)
+    DIRB_CUDA(cudaMemsetAsync(dx, 0, static_cast<size_t>(s.n) * s.h * s.w * s.cin * sizeof(__nv_bfloat16), st));
+  for (int cls = 0; cls < 4; ++cls) {
+    IgemmParams Q = P;
+    Q.cls_on = 1; Q.cls_py = cls >> 1; Q.cls_px = cls & 1; Q.full_h = s.h; Q.full_w = s.w;
+    Q.hm = (s.h - Q.cls_py + 1) / 2;
+    Q.wm = (s.w - Q.cls_px + 1) / 2;
+    Q.ntaps_c = 0;
+    for (int r = 0; r < s.kh; ++r)
+      for (int q = 0; q < s.kw; ++q)
+        if (((Q.cls_py + s.pad - r) & 1) == 0 && ((Q.cls_px + s.pad - q) & 1) == 0) Q.tap_list[Q.ntaps_c++] = r * s.kw + q;
+    if (Q.ntaps_c == 0 || Q.hm <= 0 || Q.wm <= 0) continue;
+    Q.pixels = static_cast<long long>(s.n) * Q.hm * Q.wm;
+    Q.num_kblocks = Q.ntaps_c * Q.cpb;
+    const int m_tiles = static_cast<int>((Q.pixels + BM - 1) / BM);
+    const int bn = pick_bn(s.cin, m_tiles);
+    Q.n_tiles = s.cin / bn;
+    if (int rc = make_tmap_bf16_2d(&tm, wt, ktot, s.cin, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
+    if (int rc = DISPATCH_BN(bn, false, false, tm, Q, m_tiles, 1, st)) return rc;
+  }
+  return DIRB200_OK;
 }
 
 static int wgrad_bn(const ConvShape& s) { return s.cout % 256 == 0 ? 256 : (s.cout % 128 == 0 ? 128 : 64); }
@@ -604,6 +707,8 @@ int conv_wgrad_partials(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
   P.pixels = static_cast<long long>(s.n) * s.ho * s.wo;
   P.num_kblocks = static_cast<int>((P.pixels + 63) / 64);
   P.total_chunks = s.kh * s.kw * s.cin / 64;
+  P.ntaps_c = s.kh * s.kw;
+  for (int i = 0; i < 9; ++i) P.tap_list[i] = i;
   const int splits = conv_wgrad_splits(s);
   P.kblocks_per_split = (P.num_kblocks + splits - 1) / splits;
   P.ldc = s.cout; P.out = partial;

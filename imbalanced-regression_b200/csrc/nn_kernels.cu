@@ -352,10 +352,12 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, i
   }
 }
 
-// dx[h,w] = sum over the (<= 4) windows containing (h,w) whose argmax is this position of (g1 [+ g2])
-__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
-                                   const uint8_t* __restrict__ idx, int n, int h, int w, int c,
-                                   __nv_bfloat16* __restrict__ dx) {
+// dx[h,w] = sum over the (<= 4) windows containing (h,w) whose argmax is this position of (g1 [+ g2]).
+// All candidate loads are issued before any is consumed (the dependent-load chain made the first version 6x slower
+// than its DRAM traffic).
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
+                   const uint8_t* __restrict__ idx, int n, int h, int w, int c, __nv_bfloat16* __restrict__ dx) {
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1, cg = c / 8;
   const int64_t total = (int64_t)n * h * w * cg;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -364,27 +366,52 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const _
     const int xi = (int)(t % w); t /= w;
     const int yi = (int)(t % h);
     const int b = (int)(t / h);
-    V8 acc{};
-    for (int yo = max(0, yi / 2); yo <= min(ho - 1, (yi + 1) / 2); ++yo) {
-      const int r = yi - (2 * yo - 1);
-      if (r < 0 || r > 2) continue;
-      for (int xo = max(0, xi / 2); xo <= min(wo - 1, (xi + 1) / 2); ++xo) {
-        const int s = xi - (2 * xo - 1);
-        if (s < 0 || s > 2) continue;
-        const int64_t off = (((int64_t)b * ho + yo) * wo + xo) * c + g * 8;
-        V8 gv = load8(g1 + off);
-        if (g2) {
-          const V8 t2 = load8(g2 + off);
+    // windows (yo, xo) with 2*yo - 1 <= yi <= 2*yo + 1: yo in {yi/2, (yi+1)/2}
+    int64_t off[4];
+    int pos[4];
+    int cnt = 0;
+    const int y0 = yi / 2, y1 = (yi + 1) / 2, x0 = xi / 2, x1 = (xi + 1) / 2;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) gv.v[j] += t2.v[j];
-        }
-        const uint2 iv = *reinterpret_cast<const uint2*>(idx + off);
-        const uint8_t* ib = reinterpret_cast<const uint8_t*>(&iv);
+    for (int a = 0; a < 2; ++a) {
+      const int yo = a ? y1 : y0;
+      if ((a && y1 == y0) || yo >= ho) continue;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (ib[j] == r * 3 + s) acc.v[j] += gv.v[j];
+      for (int bb = 0; bb < 2; ++bb) {
+        const int xo = bb ? x1 : x0;
+        if ((bb && x1 == x0) || xo >= wo) continue;
+        off[cnt] = (((int64_t)b * ho + yo) * wo + xo) * c + g * 8;
+        pos[cnt] = (yi - (2 * yo - 1)) * 3 + (xi - (2 * xo - 1));
+        ++cnt;
       }
     }
+    uint4 gv[4], g2v[4];
+    uint2 iv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < cnt) {
+        gv[k] = *reinterpret_cast<const uint4*>(g1 + off[k]);
+        if (g2) g2v[k] = *reinterpret_cast<const uint4*>(g2 + off[k]);
+        iv[k] = *reinterpret_cast<const uint2*>(idx + off[k]);
+      }
+    V8 acc{};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < cnt) {
+        const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&gv[k]);
+        const __nv_bfloat162* hg2 = reinterpret_cast<const __nv_bfloat162*>(&g2v[k]);
+        const uint8_t* ib = reinterpret_cast<const uint8_t*>(&iv[k]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __bfloat1622float2(hg[j]);
+          if (g2) {
+            const float2 f2 = __bfloat1622float2(hg2[j]);
+            f.x += f2.x;
+            f.y += f2.y;
+          }
+          if (ib[2 * j] == pos[k]) acc.v[2 * j] += f.x;
+          if (ib[2 * j + 1] == pos[k]) acc.v[2 * j + 1] += f.y;
+        }
+      }
     store8(dx + i * 8, acc);
   }
 }
