@@ -53,14 +53,20 @@ struct IgemmParams {
   void* out;                 // bf16 [pixels][ldc]   or   fp32 [splits][total_chunks*64][ldc]
 };
 
-template <int BN>
+template <int BN, bool STAGED_EPI>
 struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);   // 192 KB ring, one persistent CTA per SM
+  // smem: operand ring + (fprop/dgrad) a per-epilogue-warp staging tile so output rows leave as whole coalesced
+  // lines; one persistent CTA per SM
+  static constexpr int kStages = STAGED_EPI ? ((BN == 256) ? 3 : ((BN == 128) ? 5 : 8))
+                                            : ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8));
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kSmemBytes = kBarOffset + (2 * kStages + 6) * 8 + 1024;
+  static constexpr int kStageRowBytes = BN * 2 + 16;            // +16 B: conflict-free 16-byte column writes
+  static constexpr int kEpiWarpBytes = 32 * kStageRowBytes;
+  static constexpr int kEpiOffset = kBarOffset + 256;           // after the mbarriers ((2*kStages + 6) * 8 <= 176 B)
+  static constexpr int kSmemBytes = kEpiOffset + (STAGED_EPI ? 4 * kEpiWarpBytes : 0) + 1024;
   // B-stationary layout: nstages (<= kStages) A slots, then the whole B matrix; barriers stay at kBarOffset
   static constexpr int kTmemCols = 2 * BN;  // two accumulators (epilogue of tile i overlaps the MMAs of tile i+1)
 };
@@ -137,7 +143,7 @@ __device__ __forceinline__ const __nv_bfloat16* tap_source(const IgemmParams& P,
 template <int BN, bool WGRAD, bool STEM, bool BSTAT = false>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, !WGRAD>;
   static_assert(!(BSTAT && WGRAD), "B-stationary mode is for fprop/dgrad");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -436,31 +442,52 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
       const int n0 = n_tile * BN;
       if constexpr (!WGRAD) {
-        const long long p = static_cast<long long>(m_tile) * BM + row;
-        long long orow = p;
-        if (P.cls_on && p < P.pixels) {           // class pixel -> row of the full image
-          const uint32_t pk = pack_pixel(p, P);
-          const int n = (pk >> 18) & 0x1FFF, yy = (pk >> 9) & 0x1FF, xx = pk & 0x1FF;
-          orow = (static_cast<long long>(n) * P.full_h + 2 * yy + P.cls_py) * P.full_w + 2 * xx + P.cls_px;
-        }
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(P.out) + orow * P.ldc + n0;
+        // TMEM -> registers -> bf16 -> this warp's smem staging tile (32 rows x BN), then whole rows go out as
+        // coalesced 16-byte-per-lane stores (BN*2 contiguous bytes per row)
+        const uint32_t stage_base = smem_base + C::kEpiOffset + quarter * C::kEpiWarpBytes;
+        const uint32_t my_row = stage_base + lane * C::kStageRowBytes;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
-          if (p < P.pixels && nk > 0) {
-            uint32_t pk[16];
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * jj]), __uint_as_float(v[2 * jj + 1]));
-              pk[jj] = *reinterpret_cast<uint32_t*>(&h);
+          for (int jj = 0; jj < 4; ++jj) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[8 * jj + 2 * e]), __uint_as_float(v[8 * jj + 2 * e + 1]));
+              pk[e] = *reinterpret_cast<uint32_t*>(&h);
             }
-            uint4* o = reinterpret_cast<uint4*>(out + c * 32);
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) o[jj] = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + c * 64 + jj * 16), "r"(pk[0]),
+                         "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                         : "memory");
           }
         }
+        __syncwarp();
+        constexpr int kLanesPerRow = BN * 2 / 16;               // 32 / 16 / 8
+        constexpr int kRowsPerIter = 32 / kLanesPerRow;         // 1 / 2 / 4
+        const int sub = lane / kLanesPerRow, col16 = lane % kLanesPerRow;
+        const long long p0 = static_cast<long long>(m_tile) * BM + quarter * 32;
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += kRowsPerIter) {
+          const int rr = r0 + sub;
+          const long long p = p0 + rr;
+          if (p < P.pixels && nk > 0) {
+            long long orow = p;
+            if (P.cls_on) {                                     // class pixel -> row of the full image
+              const uint32_t pk = pack_pixel(p, P);
+              const int n = (pk >> 18) & 0x1FFF, yy = (pk >> 9) & 0x1FF, xx = pk & 0x1FF;
+              orow = (static_cast<long long>(n) * P.full_h + 2 * yy + P.cls_py) * P.full_w + 2 * xx + P.cls_px;
+            }
+            uint4 val;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                         : "r"(stage_base + rr * C::kStageRowBytes + col16 * 16));
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + orow * P.ldc + n0 + col16 * 8) = val;
+          }
+        }
+        __syncwarp();                                           // staging tile is reused by the next tile
       } else {
         // partials are stored TRANSPOSED, [split][Cout][K_total]: the 32 lanes of a warp hold 32 consecutive k rows,
         // so each scalar store below is one coalesced 128-byte line, and the reduce kernel reads/writes along k
@@ -536,7 +563,7 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t
 
 template <int BN, bool WGRAD, bool STEM, bool BSTAT>
 static int launch_igemm_impl(const CUtensorMap& tm, const IgemmParams& Q, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, !WGRAD>;
   static bool configured = false;
   if (!configured) {
     DIRB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, WGRAD, STEM, BSTAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -551,7 +578,7 @@ static int launch_igemm_impl(const CUtensorMap& tm, const IgemmParams& Q, cudaSt
 
 template <int BN, bool WGRAD, bool STEM>
 static int launch_igemm(const CUtensorMap& tm, const IgemmParams& P, int m_tiles, int splits, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, !WGRAD>;
   IgemmParams Q = P;
   Q.m_tiles = m_tiles;
   Q.num_tiles = m_tiles * P.n_tiles * splits;

@@ -37,6 +37,10 @@ __device__ __forceinline__ V8 loadf8(const float* p) {
   return V8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
 }
 
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+
 // Column (per-channel) reduction over the rows of [P][C]: thread owns channel group cg = tid % (C/8) and walks
 // rows with K partial sums per channel; the CTA combines its row-lanes in smem and writes ONE partial vector
 // partial[blockIdx.x][k][c] (fp32, no atomics -> deterministic); the tiny per-channel finalize kernels add the
@@ -157,33 +161,56 @@ __global__ void bn_eval_coeffs_kernel(int c, const float* __restrict__ gamma, co
 }
 
 // out = [relu]( y*scale + shift  [+ res]  [+ res_y*res_scale + res_shift] )
+// Thread = (channel group of 8, row lane): the per-channel coefficients are loaded once into registers and the
+// thread walks rows (same mapping as the column reductions), so the streaming loop is pure 16-byte loads + FMAs.
+__device__ __forceinline__ uint32_t f2_to_bf2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                 const __nv_bfloat16* __restrict__ res, const __nv_bfloat16* __restrict__ res_y,
-                const float* __restrict__ res_scale, const float* __restrict__ res_shift, int relu, int64_t total8,
+                const float* __restrict__ res_scale, const float* __restrict__ res_shift, int relu, int64_t rows,
                 int c, __nv_bfloat16* __restrict__ out) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)((i * 8) % c);
-    V8 x = load8(y + i * 8);
-    const V8 sc = loadf8(scale + c8), sh = loadf8(shift + c8);
+  const int cgroups = c / 8;
+  const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
+  const V8 sc = loadf8(scale + cg * 8), sh = loadf8(shift + cg * 8);
+  V8 rs{}, rh{};
+  if (res_y) {
+    rs = loadf8(res_scale + cg * 8);
+    rh = loadf8(res_shift + cg * 8);
+  }
+  const int64_t stride = (int64_t)gridDim.x * lanes;
+  for (int64_t r = blockIdx.x * (int64_t)lanes + lane; r < rows; r += stride) {
+    const int64_t off = r * c + cg * 8;
+    const uint4 Y = *reinterpret_cast<const uint4*>(y + off);
+    uint4 R = make_uint4(0, 0, 0, 0), RY = make_uint4(0, 0, 0, 0);
+    if (res) R = *reinterpret_cast<const uint4*>(res + off);
+    if (res_y) RY = *reinterpret_cast<const uint4*>(res_y + off);
+    const uint32_t yw[4] = {Y.x, Y.y, Y.z, Y.w}, rw[4] = {R.x, R.y, R.z, R.w}, ryw[4] = {RY.x, RY.y, RY.z, RY.w};
+    uint32_t ow[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x.v[j] = fmaf(x.v[j], sc.v[j], sh.v[j]);
-    if (res) {
-      const V8 r = load8(res + i * 8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x.v[j] += r.v[j];
+    for (int w = 0; w < 4; ++w) {
+      const float2 yv = bf2_to_f2(yw[w]);
+      float a = fmaf(yv.x, sc.v[2 * w], sh.v[2 * w]), b = fmaf(yv.y, sc.v[2 * w + 1], sh.v[2 * w + 1]);
+      if (res) {
+        const float2 t = bf2_to_f2(rw[w]);
+        a += t.x;
+        b += t.y;
+      }
+      if (res_y) {
+        const float2 t = bf2_to_f2(ryw[w]);
+        a += fmaf(t.x, rs.v[2 * w], rh.v[2 * w]);
+        b += fmaf(t.y, rs.v[2 * w + 1], rh.v[2 * w + 1]);
+      }
+      if (relu) {
+        a = fmaxf(a, 0.f);
+        b = fmaxf(b, 0.f);
+      }
+      ow[w] = f2_to_bf2(a, b);
     }
-    if (res_y) {
-      const V8 r = load8(res_y + i * 8);
-      const V8 rs = loadf8(res_scale + c8), rh = loadf8(res_shift + c8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x.v[j] += fmaf(r.v[j], rs.v[j], rh.v[j]);
-    }
-    if (relu) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x.v[j] = fmaxf(x.v[j], 0.f);
-    }
-    store8(out + i * 8, x);
+    *reinterpret_cast<uint4*>(out + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
 }
 
@@ -192,10 +219,6 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
 // dbeta = S0 and dgamma = invstd * (S1 - mean*S0) are formed in fp64 by bn_bwd_coeffs_kernel.  Keeping mean/invstd
 // out of the streaming loop keeps the kernel within 64 registers (no local-memory spills: the first version was
 // L1-bound on spill traffic, ncu profiles/).
-__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) {
-  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
-}
-
 __global__ void __launch_bounds__(256, 4)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                      const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ y,
@@ -273,44 +296,59 @@ __global__ void bn_bwd_coeffs_kernel(const float* __restrict__ partial, int nblo
 }
 
 // dz = (g1 [+ g2]) * (act > 0);  dy = A*dz + B*y + C  (and the same for the second BN);  optionally writes dz.
+// Same (channel group, row lane) mapping as bn_apply: coefficients live in registers.
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                     const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ y,
                     const float* __restrict__ coef, const __nv_bfloat16* __restrict__ y2,
                     const float* __restrict__ coef2, int64_t rows, int c, __nv_bfloat16* __restrict__ dy,
                     __nv_bfloat16* __restrict__ dy2, __nv_bfloat16* __restrict__ dz_out) {
-  const int64_t total8 = rows * c / 8;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)((i * 8) % c);
-    V8 g = load8(g1 + i * 8);
-    const V8 x = load8(y + i * 8);
-    V8 gg{}, aa{}, xx{};
-    if (g2) gg = load8(g2 + i * 8);
-    if (act) aa = load8(act + i * 8);
-    if (y2) xx = load8(y2 + i * 8);
-    if (g2) {
+  const int cgroups = c / 8;
+  const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
+  const V8 A = loadf8(coef + cg * 8), B = loadf8(coef + c + cg * 8), C = loadf8(coef + 2 * c + cg * 8);
+  V8 A2{}, B2{}, C2{};
+  if (y2) {
+    A2 = loadf8(coef2 + cg * 8);
+    B2 = loadf8(coef2 + c + cg * 8);
+    C2 = loadf8(coef2 + 2 * c + cg * 8);
+  }
+  const int64_t stride = (int64_t)gridDim.x * lanes;
+  for (int64_t r = blockIdx.x * (int64_t)lanes + lane; r < rows; r += stride) {
+    const int64_t off = r * c + cg * 8;
+    const uint4 G = *reinterpret_cast<const uint4*>(g1 + off);
+    const uint4 Y = *reinterpret_cast<const uint4*>(y + off);
+    uint4 G2 = make_uint4(0, 0, 0, 0), AC = make_uint4(0, 0, 0, 0), Y2 = make_uint4(0, 0, 0, 0);
+    if (g2) G2 = *reinterpret_cast<const uint4*>(g2 + off);
+    if (act) AC = *reinterpret_cast<const uint4*>(act + off);
+    if (y2) Y2 = *reinterpret_cast<const uint4*>(y2 + off);
+    const uint32_t gw[4] = {G.x, G.y, G.z, G.w}, g2w[4] = {G2.x, G2.y, G2.z, G2.w}, aw[4] = {AC.x, AC.y, AC.z, AC.w};
+    const uint32_t yw[4] = {Y.x, Y.y, Y.z, Y.w}, y2w[4] = {Y2.x, Y2.y, Y2.z, Y2.w};
+    uint32_t o1[4], o2[4], oz[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g.v[j] += gg.v[j];
+    for (int w = 0; w < 4; ++w) {
+      float2 g = bf2_to_f2(gw[w]);
+      if (g2) {
+        const float2 t = bf2_to_f2(g2w[w]);
+        g.x += t.x;
+        g.y += t.y;
+      }
+      if (act) {
+        if ((aw[w] & 0x00007fffu) == 0u) g.x = 0.f;
+        if ((aw[w] & 0x7fff0000u) == 0u) g.y = 0.f;
+      }
+      if (dz_out) oz[w] = f2_to_bf2(g.x, g.y);
+      const float2 yv = bf2_to_f2(yw[w]);
+      o1[w] = f2_to_bf2(fmaf(A.v[2 * w], g.x, fmaf(B.v[2 * w], yv.x, C.v[2 * w])),
+                        fmaf(A.v[2 * w + 1], g.y, fmaf(B.v[2 * w + 1], yv.y, C.v[2 * w + 1])));
+      if (y2) {
+        const float2 y2v = bf2_to_f2(y2w[w]);
+        o2[w] = f2_to_bf2(fmaf(A2.v[2 * w], g.x, fmaf(B2.v[2 * w], y2v.x, C2.v[2 * w])),
+                          fmaf(A2.v[2 * w + 1], g.y, fmaf(B2.v[2 * w + 1], y2v.y, C2.v[2 * w + 1])));
+      }
     }
-    if (act) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g.v[j] = aa.v[j] > 0.f ? g.v[j] : 0.f;
-    }
-    if (dz_out) store8(dz_out + i * 8, g);
-    {
-      const V8 A = loadf8(coef + c8), B = loadf8(coef + c + c8), C = loadf8(coef + 2 * c + c8);
-      V8 o;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o.v[j] = fmaf(A.v[j], g.v[j], fmaf(B.v[j], x.v[j], C.v[j]));
-      store8(dy + i * 8, o);
-    }
-    if (y2) {
-      const V8 A = loadf8(coef2 + c8), B = loadf8(coef2 + c + c8), C = loadf8(coef2 + 2 * c + c8);
-      V8 o;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o.v[j] = fmaf(A.v[j], g.v[j], fmaf(B.v[j], xx.v[j], C.v[j]));
-      store8(dy2 + i * 8, o);
-    }
+    *reinterpret_cast<uint4*>(dy + off) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+    if (y2) *reinterpret_cast<uint4*>(dy2 + off) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+    if (dz_out) *reinterpret_cast<uint4*>(dz_out + off) = make_uint4(oz[0], oz[1], oz[2], oz[3]);
   }
 }
 
@@ -549,6 +587,13 @@ static inline int grid1d(int64_t n, int block = 256, int per_sm = 8) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+// grid of the row-walking elementwise kernels: ~4 rows per thread, at most 8 CTAs per SM
+static inline int stream_grid(int64_t rows, int lanes) {
+  int64_t g = (rows + (int64_t)lanes * 4 - 1) / ((int64_t)lanes * 4);
+  const int64_t cap = 8 * (int64_t)num_sms();
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
 int bn_partial_floats(int max_c) { return kReduceCtasPerSm * num_sms() * 3 * max_c; }
 
 static inline int reduce_grid(int64_t rows, int lanes) {
@@ -587,9 +632,10 @@ int bn_eval_coeffs(int c, const float* gamma, const float* beta, float eps, cons
 int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, const __nv_bfloat16* res,
              const __nv_bfloat16* res_y, const float* res_scale, const float* res_shift, bool relu, int64_t rows, int c,
              __nv_bfloat16* out, cudaStream_t st) {
-  const int64_t total8 = rows * c / 8;
-  bn_apply_kernel<<<grid1d(total8), 256, 0, st>>>(y, scale, shift, res, res_y, res_scale, res_shift, relu ? 1 : 0,
-                                                  total8, c, out);
+  const int cgroups = c / 8;
+  DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_apply: unsupported channel count %d", c);
+  bn_apply_kernel<<<stream_grid(rows, 256 / cgroups), 256, 0, st>>>(y, scale, shift, res, res_y, res_scale, res_shift,
+                                                                    relu ? 1 : 0, rows, c, out);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
@@ -619,7 +665,10 @@ int bn_bwd_coeffs(const float* partial, int nblocks, int k, int gslot, int64_t r
 int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* act, const __nv_bfloat16* y,
                  const float* coef, const __nv_bfloat16* y2, const float* coef2, int64_t rows, int c,
                  __nv_bfloat16* dy, __nv_bfloat16* dy2, __nv_bfloat16* dz_out, cudaStream_t st) {
-  bn_bwd_apply_kernel<<<grid1d(rows * c / 8), 256, 0, st>>>(g1, g2, act, y, coef, y2, coef2, rows, c, dy, dy2, dz_out);
+  const int cgroups = c / 8;
+  DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_bwd_apply: unsupported channel count %d", c);
+  bn_bwd_apply_kernel<<<stream_grid(rows, 256 / cgroups), 256, 0, st>>>(g1, g2, act, y, coef, y2, coef2, rows, c, dy,
+                                                                        dy2, dz_out);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
