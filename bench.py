@@ -90,8 +90,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle.train_ref import RefTrainer
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    torch.set_num_threads(cpu_threads())
     bs = args.cpu_batch
     g = torch.Generator().manual_seed(0)
     tables = (torch.randn(101, 2048, generator=g) * .1 + .5, torch.rand(101, 2048, generator=g) + .5,
@@ -119,11 +118,16 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
-def cpu_baseline_sample(seconds_budget=25.0):
+def cpu_threads():
+    """Host threads for the CPU arm: all cores up to 32 -- beyond that torch's CPU conv/BN kernels on a small batch
+    slow down badly (measured on the 128-thread B200 host: 0.05-0.5 img/s with 128 threads)."""
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
+def cpu_baseline_sample(seconds_budget=20.0):
     from oracle.train_ref import RefTrainer
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    bs = 8
+    torch.set_num_threads(cpu_threads())
+    bs = 4
     g = torch.Generator().manual_seed(0)
     tables = (torch.randn(101, 2048, generator=g) * .1 + .5, torch.rand(101, 2048, generator=g) + .5,
               torch.randn(101, 2048, generator=g) * .1 + .5, torch.rand(101, 2048, generator=g) + .5)
@@ -133,7 +137,7 @@ def cpu_baseline_sample(seconds_budget=25.0):
     w = torch.ones(bs, 1)
     tr.step(x, t, w)
     n, t0 = 0, time.perf_counter()
-    while n < 3 or (time.perf_counter() - t0 < seconds_budget and n < 12):
+    while n < 2 or (time.perf_counter() - t0 < seconds_budget and n < 12):
         tr.step(x, t, w)
         n += 1
     dt = time.perf_counter() - t0
@@ -368,10 +372,18 @@ def run_ours(args):
     f, d, wg = conv_flops_per_image()
     conv_ms = prof["conv_fprop"][0] + prof["conv_dgrad"][0] + prof["conv_wgrad"][0]
     conv_flops = (f + d + wg) * args.batch
+    # DRAM traffic of the same kernels from the committed ncu launch list (profiles/r1_launches.json: sum of
+    # dram__bytes_read + dram__bytes_write over the conv launches of one step), else null
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_launches.json")
+    if os.path.exists(tpath) and args.batch == 256:
+        traffic = json.load(open(tpath)).get("conv_dram_gb")
+    nlaunch = prof['conv_fprop'][1] + prof['conv_dgrad'][1] + prof['conv_wgrad'][1]
     roofline = {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv: fprop+dgrad+wgrad, "
-                f"{prof['conv_fprop'][1] + prof['conv_dgrad'][1] + prof['conv_wgrad'][1]} launches/step)",
+                f"{nlaunch} launch groups/step; achieved = their summed algorithmic FLOPs / summed CUDA-event time)",
                 "achieved": conv_flops / (conv_ms / 1e3) / 1e12, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": conv_flops / (conv_ms / 1e3) / 1e12 / peaks["bf16_sustained"], "traffic": None,
+                "frac": conv_flops / (conv_ms / 1e3) / 1e12 / peaks["bf16_sustained"], "traffic": traffic,
+                "traffic_unit": "GB of DRAM read+write per step over these launches (ncu)",
                 "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)",
                 "algorithmic_gflop_per_step": conv_flops / 1e9, "kernel_ms_per_step": conv_ms}
     breakdown = {k: {"ms_per_step": round(ms, 4), "launch_groups": cnt} for k, (ms, cnt) in prof.items()}
@@ -409,7 +421,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--num-batches", dest="num_batches", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-batch", dest="cpu_batch", type=int, default=8)
+    ap.add_argument("--cpu-batch", dest="cpu_batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
