@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdirb200.so")
 
-BIN_AGE = 0
+BIN_AGE, BIN_DEPTH10, BIN_EDGES5 = 0, 1, 2
 LOSS_KINDS = {"mse": 0, "l1": 1, "focal_mse": 2, "focal_l1": 3, "huber": 4}
 ACTIVATE = {"sigmoid": 0, "tanh": 1}
 REWEIGHT = {"sqrt_inv": 1, "inverse": 2}
@@ -44,7 +44,8 @@ _SIGS = {
     "dirb200_fds_smooth_tables": (c_int, [P, c_int, c_int, P, c_int, P, P]),
     "dirb200_fds_calibrate_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, P,
                                           c_float, c_float, P, P, P]),
-    "dirb200_fds_calibrate_bwd": (c_int, [P, P, c_int64, c_int, P, P, c_float, c_float, P, P]),
+    "dirb200_fds_calibrate_bwd": (c_int, [c_int, P, P, c_int64, c_int, P, P, c_float, c_float, P, P]),
+    "dirb200_fds_fill_empty": (c_int, [P, c_int, c_int, P, P, P]),
     "dirb200_loss_workspace_bytes": (c_size_t, [c_int64]),
     "dirb200_loss_fwd_bwd": (c_int, [c_int, P, P, P, c_int64, c_float, c_float, c_int, c_float, P, P, P,
                                      c_size_t, P]),

@@ -34,7 +34,7 @@ class _CalibrateFn(torch.autograd.Function):
     (x - m1) * sqrt(clamp(v2 / v1)) + m2; backward scales the gradient."""
 
     @staticmethod
-    def forward(ctx, x, labels, m1, v1, m2, v2, bucket_num, bucket_start, clip_min, clip_max):
+    def forward(ctx, x, labels, m1, v1, m2, v2, bucket_num, bucket_start, clip_min, clip_max, bin_rule=0):
         _lib.require_cuda(x, labels, m1, v1, m2, v2)
         assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
         b, d = x.shape
@@ -43,11 +43,12 @@ class _CalibrateFn(torch.autograd.Function):
         rowbin = torch.empty(b, dtype=torch.int32, device=x.device)
         scratch = torch.empty(2, dtype=torch.int32, device=x.device) if b > 2048 else None
         _lib.call("dirb200_fds_calibrate_fwd", _lib.ptr(x), _lib.ptr(labels), b, d, bucket_num, bucket_start,
-                  _lib.BIN_AGE, _lib.ptr(m1), _lib.ptr(v1), _lib.ptr(m2), _lib.ptr(v2), clip_min, clip_max,
+                  bin_rule, _lib.ptr(m1), _lib.ptr(v1), _lib.ptr(m2), _lib.ptr(v2), clip_min, clip_max,
                   _lib.ptr(rowbin), _lib.ptr(scratch), _lib.stream_ptr())
         ctx.mark_dirty(x)
         ctx.save_for_backward(rowbin, v1, v2)
         ctx.clip = (clip_min, clip_max)
+        ctx.bin_rule = bin_rule
         return x
 
     @staticmethod
@@ -56,14 +57,16 @@ class _CalibrateFn(torch.autograd.Function):
         g = g.contiguous()
         out = torch.empty_like(g)
         b, d = g.shape
-        _lib.call("dirb200_fds_calibrate_bwd", _lib.ptr(g), _lib.ptr(rowbin), b, d, _lib.ptr(v1), _lib.ptr(v2),
-                  ctx.clip[0], ctx.clip[1], _lib.ptr(out), _lib.stream_ptr())
-        return (out,) + (None,) * 9
+        _lib.call("dirb200_fds_calibrate_bwd", ctx.bin_rule, _lib.ptr(g), _lib.ptr(rowbin), b, d, _lib.ptr(v1),
+                  _lib.ptr(v2), ctx.clip[0], ctx.clip[1], _lib.ptr(out), _lib.stream_ptr())
+        return (out,) + (None,) * 10
 
 
 class FDS(nn.Module):
 
     clip = (0.1, 10.0)      # calibrate_mean_var defaults, agedb-dir/utils.py:97
+    bin_rule = _lib.BIN_AGE  # label -> bucket rule (see include/dirb200.h); variants in fds_variants.py
+    fill_empty = False      # sts-b-dir/fds.py:112-125
 
     def __init__(self, feature_dim, bucket_num=100, bucket_start=3, start_update=0, start_smooth=1,
                  kernel='gaussian', ks=5, sigma=2, momentum=0.9):
@@ -166,7 +169,7 @@ class FDS(nn.Module):
         lab = all_labels.reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
         flags = torch.zeros(2, dtype=torch.int32, device=dev)
         _lib.call("dirb200_fds_label_flags", _lib.ptr(lab), lab.numel(), self.bucket_num, self.bucket_start,
-                  _lib.BIN_AGE, _lib.ptr(flags), _lib.stream_ptr())
+                  self.bin_rule, _lib.ptr(flags), _lib.stream_ptr())
         dist = self._dist()
         if dist is not None:
             dist.all_reduce(flags, op=dist.ReduceOp.MAX)
@@ -186,7 +189,7 @@ class FDS(nn.Module):
         lab = labels.reshape(-1).to(device=features.device, dtype=torch.float32).contiguous()
         bins = torch.empty(n, dtype=torch.int32, device=features.device)
         st = _lib.stream_ptr()
-        _lib.call("dirb200_fds_bin_rows", _lib.ptr(lab), n, self.bucket_num, self.bucket_start, _lib.BIN_AGE,
+        _lib.call("dirb200_fds_bin_rows", _lib.ptr(lab), n, self.bucket_num, self.bucket_start, self.bin_rule,
                   _lib.ptr(acc["flags"]), _lib.ptr(bins), st)
         need = _lib.raw("dirb200_fds_accumulate_workspace_bytes")(n, nb)
         if acc["ws"] is None or acc["ws"].numel() < need:
@@ -213,6 +216,9 @@ class FDS(nn.Module):
                   nb, d, _lib.ptr(self.running_mean), _lib.ptr(self.running_var),
                   _lib.ptr(self.num_samples_tracked), -1.0 if self.momentum is None else float(self.momentum),
                   int(epoch == self.start_update), _lib.stream_ptr())
+        if self.fill_empty:
+            _lib.call("dirb200_fds_fill_empty", _lib.ptr(acc["counts"]), nb, d, _lib.ptr(self.running_mean),
+                      _lib.ptr(self.running_var), _lib.stream_ptr())
         print(f"Updated running statistics with Epoch [{epoch}] features!")
 
     # ------------------------------------------------------------ reference API
@@ -230,4 +236,4 @@ class FDS(nn.Module):
             return features
         return _CalibrateFn.apply(features, labels, self.running_mean_last_epoch, self.running_var_last_epoch,
                                   self.smoothed_mean_last_epoch, self.smoothed_var_last_epoch,
-                                  self.bucket_num, self.bucket_start, self.clip[0], self.clip[1])
+                                  self.bucket_num, self.bucket_start, self.clip[0], self.clip[1], self.bin_rule)

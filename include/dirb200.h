@@ -35,7 +35,11 @@ extern "C" {
 #define DIRB200_ERR_WORKSPACE (-3)
 
 /* bin rules (row label -> FDS table row) */
-#define DIRB200_BIN_AGE 0 /* agedb-dir/fds.py:91-99 : int(label - bucket_start), edge folding */
+#define DIRB200_BIN_AGE 0     /* agedb-dir/fds.py:91-99 : int(label - bucket_start), edge folding */
+#define DIRB200_BIN_DEPTH10 1 /* nyud2-dir/models/fds.py:51-53 : clamp(int(label*10), bucket_start, bucket_num-1) */
+#define DIRB200_BIN_EDGES5 2  /* sts-b-dir/fds.py:51-57 : np.histogram edges over [0,5], bucket_num bins */
+/* the rule also selects calibrate_mean_var's channel mask: v1 != 0 (age, agedb-dir/utils.py:100) or
+ * v1 > 0 && v2 >= 0 (nyud2-dir/util.py:154, sts-b-dir/util.py:66) */
 
 /* loss kinds (agedb-dir/loss.py) */
 #define DIRB200_LOSS_MSE 0       /* loss.py:5-10  */
@@ -107,8 +111,13 @@ int dirb200_fds_calibrate_fwd(float* x, const float* labels, int64_t b, int d, i
                               int32_t* rowbin_out, int32_t* flags_scratch /* int32[2]; may be NULL when b <= 2048 */,
                               void* stream);
 
+/* STS-B variant (sts-b-dir/fds.py:112-125): buckets with counts[b] == 0 in this update take their neighbours'
+ * running statistics (copy at the two ends, mean of both neighbours inside), in increasing bucket order. */
+int dirb200_fds_fill_empty(const int64_t* counts, int nb, int d, float* running_mean, float* running_var,
+                           void* stream);
+
 /* grad_in[b,d] = grad_out[b,d] * d(calibrate)/dx (may alias). */
-int dirb200_fds_calibrate_bwd(const float* grad_out, const int32_t* rowbin, int64_t b, int d,
+int dirb200_fds_calibrate_bwd(int bin_rule, const float* grad_out, const int32_t* rowbin, int64_t b, int d,
                               const float* v1, const float* v2, float clip_min, float clip_max,
                               float* grad_in, void* stream);
 

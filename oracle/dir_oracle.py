@@ -363,3 +363,116 @@ def weighted_loss(kind, inputs, targets, weights=None, activate="sigmoid", beta=
         w = np.broadcast_to(np.asarray(weights, dtype=np.float64), d.shape)
         l, g = l * w, g * w
     return np.float32(l.mean()), (g / n).astype(np.float32)
+
+
+# --------------------------------------------------------------------------
+# FDS variants of nyud2-dir / sts-b-dir
+# --------------------------------------------------------------------------
+def bin_index_depth10(labels, bucket_num, bucket_start):
+    """clamp(int(float32(label) * float32(10)), bucket_start, bucket_num - 1) - bucket_start
+    (nyud2-dir/models/fds.py:51-53)."""
+    lab = np.asarray(labels, dtype=np.float32).reshape(-1)
+    b = (lab * np.float32(10)).astype(np.int64)
+    return (np.clip(b, bucket_start, bucket_num - 1) - bucket_start).astype(np.int32)
+
+
+def bin_index_edges5(labels, bucket_num, bucket_start):
+    """np.histogram-style buckets over [0, 5] (sts-b-dir/fds.py:51-57): the first float32 edge greater than the
+    label, minus one; label == 5 -> last bucket; clamped below by bucket_start."""
+    lab = np.asarray(labels, dtype=np.float32).reshape(-1)
+    edges = np.linspace(0.0, 5.0, bucket_num + 1).astype(np.float32)
+    out = np.empty(lab.shape, dtype=np.int32)
+    for i, v in enumerate(lab):
+        if v == np.float32(5.0):
+            out[i] = bucket_num - 1
+        else:
+            out[i] = max(int(np.nonzero(edges > v)[0][0]) - 1, bucket_start)
+    return out - bucket_start
+
+
+def calibrate_mean_var_v2(matrix, m1, v1, m2, v2, clip_min, clip_max):
+    """nyud2-dir/util.py:151-162 == sts-b-dir/util.py:63-73, AS IT BEHAVES on PyTorch >= 1.2: the mask
+    `((v1 > 0.) + (v2 >= 0.)) == 2` adds two bool tensors (a logical OR) and compares with 2, which is never
+    true -- so if any channel has v1 <= 0 or v2 < 0 the matrix comes back unchanged; otherwise all channels are
+    calibrated.  (The fixtures were produced by running the reference, so they pin exactly this.)"""
+    x = np.asarray(matrix, dtype=np.float32)
+    m1, v1, m2, v2 = (np.asarray(a, dtype=np.float32) for a in (m1, v1, m2, v2))
+    if np.sum(v1, dtype=np.float32) < 1e-10:
+        return x
+    if (v1 <= 0).any() or (v2 < 0).any():
+        return x
+    fac = np.clip(v2 / v1, np.float32(clip_min), np.float32(clip_max))
+    return (x - m1) * np.sqrt(fac) + m2
+
+
+class FDSVariantState(FDSState):
+    """FDSState with another bucket rule.  variant 'nyud2': rows = pixels of [B,C,H,W] maps, clip (0.2, 5),
+    no alias of the last-epoch tables (device hops); variant 'stsb': edge buckets, clip (0.5, 2), empty buckets
+    filled from their neighbours after every update (sts-b-dir/fds.py:112-125), alias kept."""
+
+    def __init__(self, variant, feature_dim, bucket_num, bucket_start, **kw):
+        super().__init__(feature_dim, bucket_num, bucket_start, **kw)
+        self.variant = variant
+        self.clip = (0.2, 5.0) if variant == "nyud2" else (0.5, 2.0)
+        self.bin_fn = bin_index_depth10 if variant == "nyud2" else bin_index_edges5
+
+    def update_last_epoch_stats(self, epoch):
+        was = self.epoch
+        super().update_last_epoch_stats(epoch)
+        if self.variant == "nyud2" and self.epoch != was:
+            self.running_mean_last_epoch = self.running_mean.copy()
+            self.running_var_last_epoch = self.running_var.copy()
+
+    def _rows(self, features, labels):
+        f = np.asarray(features, dtype=np.float32)
+        if f.ndim == 4:
+            f = f.transpose(0, 2, 3, 1).reshape(-1, f.shape[1])
+        return f, np.asarray(labels, dtype=np.float32).reshape(-1)
+
+    def update_running_stats(self, features, labels, epoch):
+        if epoch < self.epoch:
+            return
+        f, lab = self._rows(features, labels)
+        bins = self.bin_fn(lab, self.bucket_num, self.bucket_start)
+        nb = self.bucket_num - self.bucket_start
+        seen = np.zeros(nb, dtype=bool)
+        for b in np.unique(bins):
+            rows = f[bins == b].astype(np.float64)
+            n = rows.shape[0]
+            seen[b] = True
+            self.num_samples_tracked[b] += np.float32(n)
+            factor = self.momentum if self.momentum is not None else (1 - n / float(self.num_samples_tracked[b]))
+            factor = 0 if epoch == self.start_update else factor
+            a, fm = np.float32(1 - factor), np.float32(factor)
+            mean = rows.mean(0).astype(np.float32)
+            var = (rows.var(0, ddof=1) if n > 1 else np.zeros(rows.shape[1])).astype(np.float32)
+            self.running_mean[b] = a * mean + fm * self.running_mean[b]
+            self.running_var[b] = a * var + fm * self.running_var[b]
+        if self.variant == "stsb":
+            for b in range(nb):
+                if seen[b]:
+                    continue
+                for t in (self.running_mean, self.running_var):
+                    if b == 0:
+                        t[0] = t[1]
+                    elif b == nb - 1:
+                        t[b] = t[b - 1]
+                    else:
+                        t[b] = (t[b - 1] + t[b + 1]) / np.float32(2.0)
+
+    def smooth(self, features, labels, epoch):
+        if epoch < self.start_smooth:
+            return np.asarray(features, dtype=np.float32)
+        shape = np.asarray(features).shape
+        f, lab = self._rows(features, labels)
+        bins = self.bin_fn(lab, self.bucket_num, self.bucket_start)
+        x = f.copy()
+        for b in np.unique(bins):
+            rows = bins == b
+            x[rows] = calibrate_mean_var_v2(x[rows], self.running_mean_last_epoch[b], self.running_var_last_epoch[b],
+                                            self.smoothed_mean_last_epoch[b], self.smoothed_var_last_epoch[b],
+                                            *self.clip)
+        if len(shape) == 4:
+            bsz, c, h, w = shape
+            return x.reshape(bsz, h, w, c).transpose(0, 3, 1, 2)
+        return x

@@ -213,3 +213,61 @@ def test_lds_histogram_clamps_and_accumulates():
         _lib.call("dirb200_lds_histogram", _lib.ptr(lab), lab.numel(), 121, _lib.ptr(hist), _lib.stream_ptr())
     h = hist.cpu().numpy()
     assert h[0] == 4 and h[1] == 2 and h[119] == 2 and h[120] == 8 and h.sum() == 16
+
+
+# ------------------------------------------------- FDS variants (nyud2-dir, sts-b-dir)
+def test_fds_variant_nyud2_vs_reference_golden():
+    from fds_variants import FDSDepth
+    g = golden("fds_nyud2")
+    bn, bs, ks, sg, mom, C, B, H, W = g["cfg"]
+    m = FDSDepth(int(C), int(bn), int(bs), 0, 1, "gaussian", int(ks), int(sg), float(mom)).to(DEV)
+    for ep in range(4):
+        sm = m.smooth(T(g[f"e{ep}_bx"]), T(g[f"e{ep}_bd"]), ep)
+        assert_close(sm.cpu().numpy(), g[f"e{ep}_smooth"], rtol=1e-5, atol=1e-5, what=f"smooth e{ep}")
+        m.update_last_epoch_stats(ep)
+        m.update_running_stats(T(g[f"e{ep}_feats"]), T(g[f"e{ep}_depth"]), ep)
+        sd = m.state_dict()
+        for k in ("running_mean", "running_var", "running_mean_last_epoch", "running_var_last_epoch",
+                  "smoothed_mean_last_epoch", "smoothed_var_last_epoch", "num_samples_tracked", "epoch"):
+            assert_close(sd[k].cpu().numpy(), g[f"e{ep}_{k}"], rtol=1e-5, atol=1e-6, what=f"{k} e{ep}")
+
+
+def test_fds_variant_stsb_vs_reference_golden():
+    import _lib
+    from fds_variants import FDSSTSB
+    g = golden("fds_stsb")
+    bn, bs, ks, sg, mom, D, N = g["cfg"]
+    # bucket index of a label sweep incl. the float32 edges: bit exact
+    sweep = T(g["sweep"])
+    bins = torch.empty(sweep.numel(), dtype=torch.int32, device=DEV)
+    flags = torch.zeros(2, dtype=torch.int32, device=DEV)
+    _lib.call("dirb200_fds_bin_rows", _lib.ptr(sweep), sweep.numel(), int(bn), int(bs), _lib.BIN_EDGES5, _lib.ptr(flags),
+              _lib.ptr(bins), _lib.stream_ptr())
+    assert np.array_equal(bins.cpu().numpy(), g["sweep_bucket"] - int(bs))
+    m = FDSSTSB(int(D), int(bn), int(bs), 0, 1, "gaussian", int(ks), int(sg), float(mom)).to(DEV)
+    for ep in range(4):
+        sm = m.smooth(T(g[f"e{ep}_bx"]), T(g[f"e{ep}_bl"]), ep)
+        assert_close(sm.cpu().numpy(), g[f"e{ep}_smooth"], rtol=1e-5, atol=1e-5, what=f"smooth e{ep}")
+        m.update_last_epoch_stats(ep)
+        m.update_running_stats(T(g[f"e{ep}_feats"]), T(g[f"e{ep}_labels"]), ep)
+        sd = m.state_dict()
+        for k in ("running_mean", "running_var", "running_mean_last_epoch", "running_var_last_epoch",
+                  "smoothed_mean_last_epoch", "smoothed_var_last_epoch", "num_samples_tracked", "epoch"):
+            assert_close(sd[k].cpu().numpy(), g[f"e{ep}_{k}"], rtol=1e-5, atol=1e-6, what=f"{k} e{ep}")
+
+
+def test_fds_depth_dense_size_vs_oracle():
+    """BASELINE config-4-like dense map (reduced: 4 x 128 x 60 x 80 = 19 200 pixel rows): bins bit-exact, stats 1e-5."""
+    import _lib
+    from fds_variants import FDSDepth
+    rng = np.random.RandomState(11)
+    B, C, H, W = 4, 128, 60, 80
+    feats = np.maximum(rng.randn(B, C, H, W).astype(np.float32) + 0.4, 0)
+    depth = (rng.rand(B, 1, H, W).astype(np.float32) * 9.3 + 0.7)
+    m = FDSDepth(C).to(DEV)
+    m.update_running_stats(T(feats), T(depth), 0)
+    ref = O.FDSVariantState("nyud2", C, 100, 7)
+    ref.update_running_stats(feats, depth, 0)
+    assert_close(m.running_mean.cpu().numpy(), ref.running_mean, rtol=1e-5, atol=1e-6)
+    assert_close(m.running_var.cpu().numpy(), ref.running_var, rtol=1e-5, atol=1e-6)
+    assert_close(m.num_samples_tracked.cpu().numpy(), ref.num_samples_tracked, rtol=0, atol=0)

@@ -150,3 +150,34 @@ def test_resnet_ref_matches_reference():
             n = key.split("/", 1)[1]
             got = p[n].grad.double().abs().sum().item()
             assert abs(got - float(g[key])) <= 3e-2 * float(g[key]) + 1e-6, (n, got, float(g[key]))  # batch-2 BN: fp32 noise flips ReLU masks
+
+
+def test_fds_variant_nyud2_matches_reference():
+    g = golden("fds_nyud2")
+    bn, bs, ks, sg, mom, C, B, H, W = g["cfg"]
+    st = O.FDSVariantState("nyud2", int(C), int(bn), int(bs), kernel="gaussian", ks=int(ks), sigma=int(sg),
+                           momentum=float(mom))
+    for ep in range(4):
+        sm = st.smooth(g[f"e{ep}_bx"], g[f"e{ep}_bd"], ep)
+        assert_close(sm, g[f"e{ep}_smooth"], rtol=1e-5, atol=1e-5, what=f"smooth e{ep}")
+        st.update_last_epoch_stats(ep)
+        st.update_running_stats(g[f"e{ep}_feats"], g[f"e{ep}_depth"], ep)
+        for k in ("running_mean", "running_var", "running_mean_last_epoch", "running_var_last_epoch",
+                  "smoothed_mean_last_epoch", "smoothed_var_last_epoch", "num_samples_tracked"):
+            assert_close(getattr(st, k), g[f"e{ep}_{k}"], rtol=1e-5, atol=1e-6, what=f"{k} e{ep}")
+
+
+def test_fds_variant_stsb_matches_reference():
+    g = golden("fds_stsb")
+    bn, bs, ks, sg, mom, D, N = g["cfg"]
+    assert np.array_equal(O.bin_index_edges5(g["sweep"], int(bn), int(bs)), g["sweep_bucket"] - int(bs))
+    st = O.FDSVariantState("stsb", int(D), int(bn), int(bs), kernel="gaussian", ks=int(ks), sigma=int(sg),
+                           momentum=float(mom))
+    for ep in range(4):
+        sm = st.smooth(g[f"e{ep}_bx"], g[f"e{ep}_bl"], ep)
+        assert_close(sm, g[f"e{ep}_smooth"], rtol=1e-5, atol=1e-5, what=f"smooth e{ep}")
+        st.update_last_epoch_stats(ep)
+        st.update_running_stats(g[f"e{ep}_feats"], g[f"e{ep}_labels"], ep)
+        for k in ("running_mean", "running_var", "running_mean_last_epoch", "running_var_last_epoch",
+                  "smoothed_mean_last_epoch", "smoothed_var_last_epoch", "num_samples_tracked"):
+            assert_close(getattr(st, k), g[f"e{ep}_{k}"], rtol=1e-5, atol=1e-6, what=f"{k} e{ep}")
