@@ -311,6 +311,7 @@ def run_ours(args):
     device = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line (no "NCCL version" banner)
         dist.init_process_group("nccl", device_id=device)
     import _lib
     peaks = measured_peaks()
