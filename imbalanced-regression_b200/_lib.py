@@ -50,6 +50,7 @@ _SIGS = {
     "dirb200_loss_fwd_bwd": (c_int, [c_int, P, P, P, c_int64, c_float, c_float, c_int, c_float, P, P, P,
                                      c_size_t, P]),
     "dirb200_lds_histogram": (c_int, [P, c_int64, c_int, P, P]),
+    "dirb200_lds_table_lookup": (c_int, [P, c_int64, c_float, c_int, P, P, P]),
     "dirb200_lds_weights": (c_int, [P, c_int64, c_int, c_int, P, c_int, P, P, P, P]),
 }
 

@@ -181,6 +181,16 @@ __global__ void lds_gather_kernel(const float* __restrict__ labels, int64_t n, i
   }
 }
 
+// out[i] = table[min(int(values[i] * mult), max_bin)]   (per-pixel LDS weight lookup, nyud2-dir/loaddata.py:55-64)
+__global__ void lds_table_lookup_kernel(const float* __restrict__ values, int64_t n, float mult, int max_bin,
+                                        const float* __restrict__ table, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)__fmul_rn(values[i], mult);
+    b = max(0, min(max_bin, b));
+    out[i] = table[b];
+  }
+}
+
 static inline int grid_for2(int64_t n, int block, int cap) {
   int64_t g = (n + block - 1) / block;
   if (g < 1) g = 1;
@@ -229,6 +239,16 @@ int dirb200_lds_histogram(const float* labels, int64_t n, int max_target, int64_
   DIRB_CHECK_ARG(labels, "lds_histogram: null labels");
   lds_hist_kernel<<<grid_for2(n, 256, 2 * num_sms()), 256, sizeof(unsigned int) * max_target, as_stream(stream)>>>(
       labels, n, max_target, reinterpret_cast<unsigned long long*>(hist));
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+int dirb200_lds_table_lookup(const float* values, int64_t n, float mult, int max_bin, const float* table,
+                             float* weights_out, void* stream) {
+  DIRB_CHECK_ARG(n >= 0 && max_bin >= 0 && table && (n == 0 || (values && weights_out)), "lds_table_lookup: bad arguments");
+  if (n == 0) return DIRB200_OK;
+  lds_table_lookup_kernel<<<grid_for2(n, 256, 8 * num_sms()), 256, 0, as_stream(stream)>>>(values, n, mult, max_bin,
+                                                                                           table, weights_out);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }

@@ -93,3 +93,41 @@ class AgeDB(data.Dataset):
 
 class IMDBWIKI(AgeDB):
     pass
+
+
+# ------------------------------------------------------------------ dense (NYUD2) LDS weights
+def depth_bucket_weights(train_bucket_num, reweight, bucket_num=100, bucket_start=7, lds=False, lds_kernel='gaussian',
+                         lds_ks=5, lds_sigma=2):
+    """Per-bucket loss weights of nyud2-dir/loaddata.py:29-50 (host side, 100 numbers, once per run).
+    `train_bucket_num`: pixel counts per 0.1 m depth bucket (the reference hard-codes its TRAIN_BUCKET_NUM)."""
+    from scipy.ndimage import convolve1d
+    assert reweight in {'none', 'inverse', 'sqrt_inv'}
+    assert reweight != 'none' if lds else True, "Set reweight to 'sqrt_inv' or 'inverse' (default) when using LDS"
+    if reweight == 'none':
+        return None
+    counts = list(train_bucket_num)
+    if lds:
+        values = counts[bucket_start:]
+        if reweight == 'sqrt_inv':
+            values = np.sqrt(values)
+        window = get_lds_kernel_window(lds_kernel, lds_ks, lds_sigma)
+        smoothed = convolve1d(np.asarray(values), weights=window, mode='reflect')
+        per_bucket = [smoothed[0]] * bucket_start + list(smoothed)
+    else:
+        per_bucket = [counts[bucket_start]] * bucket_start + counts[bucket_start:]
+        if reweight == 'sqrt_inv':
+            per_bucket = np.sqrt(per_bucket)
+    scaling = np.sum(counts) / np.sum(np.array(counts) / np.array(per_bucket))
+    return np.asarray([np.float32(scaling / per_bucket[b]) for b in range(bucket_num)], dtype=np.float32)
+
+
+def depth_pixel_weights(depth, bucket_weights):
+    """weights[i] = bucket_weights[min(int(depth[i] * 10), 99)] for a whole depth map on the GPU (the reference maps a
+    Python lambda over every pixel on the CPU, loaddata.py:52-64)."""
+    _lib.require_cuda(depth)
+    d = depth.detach().to(torch.float32).contiguous()
+    table = torch.as_tensor(np.asarray(bucket_weights, dtype=np.float32), device=d.device)
+    out = torch.empty_like(d)
+    _lib.call("dirb200_lds_table_lookup", _lib.ptr(d), d.numel(), 10.0, table.numel() - 1, _lib.ptr(table),
+              _lib.ptr(out), _lib.stream_ptr())
+    return out

@@ -147,6 +147,11 @@ int dirb200_lds_weights(const float* labels, int64_t n, int max_target, int rewe
                         const double* window_host, int ks, const int64_t* hist,
                         double* scratch, float* weights_out, void* stream);
 
+/* Dense per-element weight lookup of nyud2-dir/loaddata.py:52-64: weights_out[i] = table[min(int(values[i] * mult),
+ * max_bin)] (mult = 10, max_bin = 99 for depth maps; table = the bucket weights, device pointer). */
+int dirb200_lds_table_lookup(const float* values, int64_t n, float mult, int max_bin, const float* table,
+                             float* weights_out, void* stream);
+
 /* ------------------------------------------------- convolution stack ---- */
 /* Activations are NHWC bf16; weights arrive in the reference's fp32
  * [Cout][Cin][KH][KW] layout (agedb-dir/resnet.py:46-51,79,112-118, i.e. the

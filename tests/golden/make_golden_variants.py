@@ -95,6 +95,38 @@ def stsb():
     np.savez_compressed(os.path.join(HERE, "fds_stsb.npz"), **out)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and sys.argv[1] in ("nyud2", "stsb"):
     {"nyud2": nyud2, "stsb": stsb}[sys.argv[1]]()
     print("ok", sys.argv[1])
+
+
+def nyud2_lds():
+    """nyud2-dir/loaddata.py bucket weights + per-pixel lookup (run as: ... nyud2_lds)."""
+    import types
+    sys.path.insert(0, "/root/reference/nyud2-dir")
+    for name in ("nyu_transform",):                # image transforms pull in accimage/PIL extras: not needed here
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["nyu_transform"].__dict__.update({k: object for k in
+        ("Scale", "RandomHorizontalFlip", "Rotate", "CenterCrop", "ToTensor", "Lighting", "ColorJitter", "Normalize")})
+    # loaddata.py gets numpy / torch through `from nyu_transform import *`
+    sys.modules["nyu_transform"].__dict__.update({"np": np, "torch": torch})
+    ld = load("/root/reference/nyud2-dir/loaddata.py", "ref_loaddata")
+    out = {"train_bucket_num": np.asarray(ld.TRAIN_BUCKET_NUM, dtype=np.float64)}
+    ds = ld.depthDataset.__new__(ld.depthDataset)
+    rng = np.random.RandomState(3)
+    depth = torch.from_numpy((rng.rand(2, 1, 12, 9) * 10.5).astype(np.float32))
+    out["depth"] = depth.numpy()
+    for rw in ("inverse", "sqrt_inv"):
+        for lds_on in (0, 1):
+            args = types.SimpleNamespace(reweight=rw, lds=bool(lds_on), lds_kernel="gaussian", lds_ks=5, lds_sigma=2,
+                                         bucket_num=100, bucket_start=7)
+            bw = ds._get_bucket_weights(args)
+            ds.bucket_weights = bw
+            out[f"bw_{rw}_{lds_on}"] = np.asarray(bw, dtype=np.float32)
+            out[f"w_{rw}_{lds_on}"] = ds._get_weights(depth).numpy()
+    np.savez_compressed(os.path.join(HERE, "lds_nyud2.npz"), **out)
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "nyud2_lds":
+    nyud2_lds()
+    print("ok nyud2_lds")

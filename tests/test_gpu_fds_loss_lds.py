@@ -271,3 +271,22 @@ def test_fds_depth_dense_size_vs_oracle():
     assert_close(m.running_mean.cpu().numpy(), ref.running_mean, rtol=1e-5, atol=1e-6)
     assert_close(m.running_var.cpu().numpy(), ref.running_var, rtol=1e-5, atol=1e-6)
     assert_close(m.num_samples_tracked.cpu().numpy(), ref.num_samples_tracked, rtol=0, atol=0)
+
+
+def test_nyud2_pixel_weights_and_dense_loss_vs_reference():
+    """Per-pixel LDS weights (table lookup, bit exact) and the dense weighted MSE of nyud2-dir/train.py:200."""
+    import datasets
+    import loss as L
+    g = golden("lds_nyud2")
+    depth = T(g["depth"])
+    for rw in ("inverse", "sqrt_inv"):
+        for lds_on in (0, 1):
+            w = datasets.depth_pixel_weights(depth, g[f"bw_{rw}_{lds_on}"])
+            assert np.array_equal(w.cpu().numpy(), g[f"w_{rw}_{lds_on}"]), (rw, lds_on)
+    pred = (depth + torch.randn_like(depth) * 0.3).requires_grad_(True)
+    w = datasets.depth_pixel_weights(depth, g["bw_inverse_1"])
+    l = L.weighted_mse_loss(pred, depth, w)
+    l.backward()
+    ref = (((pred.detach() - depth) ** 2) * w).mean()
+    assert_close(l.item(), ref.item(), rtol=1e-5)
+    assert_close(pred.grad.cpu().numpy(), (2 * (pred.detach() - depth) * w / depth.numel()).cpu().numpy(), rtol=1e-5, atol=1e-9)

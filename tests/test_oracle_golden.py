@@ -181,3 +181,13 @@ def test_fds_variant_stsb_matches_reference():
         for k in ("running_mean", "running_var", "running_mean_last_epoch", "running_var_last_epoch",
                   "smoothed_mean_last_epoch", "smoothed_var_last_epoch", "num_samples_tracked"):
             assert_close(getattr(st, k), g[f"e{ep}_{k}"], rtol=1e-5, atol=1e-6, what=f"{k} e{ep}")
+
+
+def test_nyud2_bucket_weights_host_matches_reference():
+    """datasets.depth_bucket_weights (host code of the product, numpy/scipy like the reference) vs loaddata.py."""
+    import datasets
+    g = golden("lds_nyud2")
+    for rw in ("inverse", "sqrt_inv"):
+        for lds_on in (0, 1):
+            bw = datasets.depth_bucket_weights([int(v) for v in g["train_bucket_num"]], rw, lds=bool(lds_on))
+            assert_close(bw, g[f"bw_{rw}_{lds_on}"], rtol=1e-6, atol=0, what=f"{rw} {lds_on}")
