@@ -40,6 +40,8 @@ _SIGS = {
     "dirb200_fds_bin_rows": (c_int, [P, c_int64, c_int, c_int, c_int, P, P, P]),
     "dirb200_fds_accumulate_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "dirb200_fds_accumulate": (c_int, [P, P, c_int64, c_int, c_int, P, P, P, P, c_size_t, P]),
+    "dirb200_fds_set_profiling": (c_int, [c_int]),
+    "dirb200_fds_last_accumulate_kernel_ms": (c_int, [P]),
     "dirb200_fds_finalize": (c_int, [P, P, P, c_int, c_int, P, P, P, c_double, c_int, P]),
     "dirb200_fds_smooth_tables": (c_int, [P, c_int, c_int, P, c_int, P, P]),
     "dirb200_fds_calibrate_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, P,

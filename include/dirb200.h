@@ -87,6 +87,13 @@ int dirb200_fds_accumulate(const float* features, const int32_t* bins, int64_t n
                            double* sums, double* sumsq, int64_t* counts,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* Measurement aid (bench.py's `roofline` line; no reference counterpart): when enabled, dirb200_fds_accumulate
+ * records CUDA events on the caller's stream around its fds_accumulate_kernel launch alone (the counting sort
+ * that precedes it is excluded); dirb200_fds_last_accumulate_kernel_ms synchronises on them and returns the
+ * kernel's duration of the most recent call. */
+int dirb200_fds_set_profiling(int enabled);
+int dirb200_fds_last_accumulate_kernel_ms(float* ms_out);
+
 /* mean/var (unbiased; 0 when n==1) from the accumulators, then the running
  * EMA update of every bin with count>0, agedb-dir/fds.py:100-111.
  * momentum < 0 selects the `momentum is None` rule (factor = 1 - n/tracked);
