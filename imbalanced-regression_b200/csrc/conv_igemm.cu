@@ -53,17 +53,23 @@ struct IgemmParams {
   void* out;                 // bf16 [pixels][ldc]   or   fp32 [splits][total_chunks*64][ldc]
 };
 
-template <int BN, bool STAGED_EPI>
+// CTA2: the tile is computed by a CTA pair (cta_group::2, UMMA M = 256): this CTA owns 128 of the 256 rows and stages
+// only HALF of the B tile (BN/2 rows) -- 1/3 less L2->smem operand traffic per FLOP at BN = 256.
+template <int BN, bool STAGED_EPI, bool CTA2 = false>
 struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBRows = CTA2 ? BN / 2 : BN;      // B rows staged by this CTA
+  static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // smem: operand ring + (fprop/dgrad) a per-epilogue-warp staging tile so output rows leave as whole coalesced
-  // lines; one persistent CTA per SM
-  static constexpr int kStages = STAGED_EPI ? ((BN == 256) ? 3 : ((BN == 128) ? 5 : 8))
-                                            : ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8));
+  // smem: operand ring + (fprop/dgrad) a per-epilogue-warp staging tile of 32 rows x kEpiCols columns, so output
+  // rows leave as whole 128-byte lines (the tile's BN columns are drained in BN / kEpiCols passes; the narrow
+  // staging buffer buys one to two more ring stages than a full-width one); one persistent CTA per SM
+  static constexpr int kEpiCols = 64;
+  static constexpr int kStages = CTA2 ? ((BN == 256) ? 6 : 8)
+                                      : (STAGED_EPI ? ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8))
+                                                    : ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8)));
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kStageRowBytes = BN * 2 + 16;            // +16 B: conflict-free 16-byte column writes
+  static constexpr int kStageRowBytes = kEpiCols * 2 + 16;      // +16 B: conflict-free 16-byte column writes
   static constexpr int kEpiWarpBytes = 32 * kStageRowBytes;
   static constexpr int kEpiOffset = kBarOffset + 256;           // after the mbarriers ((2*kStages + 6) * 8 <= 176 B)
   static constexpr int kSmemBytes = kEpiOffset + (STAGED_EPI ? 4 * kEpiWarpBytes : 0) + 1024;
@@ -140,11 +146,26 @@ __device__ __forceinline__ const __nv_bfloat16* tap_source(const IgemmParams& P,
 // BSTAT ("B stationary"): when every tile of the launch uses the same B matrix (one N tile) and it fits in smem, the
 // whole weight matrix is loaded once per CTA and the ring carries only the gathered A rows -- removes the per-tile
 // re-fetch of the weights through L2 for the narrow layers (stem, 64/128-channel convs).
-template <int BN, bool WGRAD, bool STEM, bool BSTAT = false>
+//
+// CTA2 (fprop/dgrad, BN >= 128): launched as (2,1,1) clusters; the pair owns a 256 x BN tile.  Per k-block each CTA
+// gathers its own 128 A rows and TMA-loads its half of B; the leader's full barrier collects its own 128 gather
+// arrivals, the transaction bytes of BOTH B halves and one arrival relayed by the peer's (otherwise idle) MMA warp
+// when the peer's gather has landed; the leader issues tcgen05.mma.cta_group::2 and its commits arrive on the
+// empty / accumulator-full barriers of both CTAs (multicast); the peer's epilogue warps hand the accumulator back by
+// arriving on the leader's barrier.
+//
+// ATMA (1x1 / stride-1 convolutions): the "gathered" operand is a plain [pixels][channels] matrix, so the TMA warp
+// loads the A tiles as well (tmap_a; K-major 64 x 128 boxes for fprop/dgrad, two 64 x 64 MN-major boxes for wgrad)
+// and warps 0-3 stay idle.  Measured motivation: the cp.async gather sustains only ~16 KB per 0.6 us per SM
+// whatever the tile shape or ring depth, which bounds every GEMM fed by it at ~0.6 us per k-block.
+template <int BN, bool WGRAD, bool STEM, bool BSTAT = false, bool CTA2 = false, bool ATMA = false>
 __global__ void __launch_bounds__(kThreads, 1)
-igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
-  using C = Cfg<BN, !WGRAD>;
+igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_a,
+             const IgemmParams P) {
+  using C = Cfg<BN, !WGRAD, CTA2>;
   static_assert(!(BSTAT && WGRAD), "B-stationary mode is for fprop/dgrad");
+  static_assert(!CTA2 || (!WGRAD && !STEM && !BSTAT && BN >= 128), "CTA pairs: fprop/dgrad with BN >= 128 only");
+  static_assert(!ATMA || (!STEM && !BSTAT && !CTA2), "TMA-fed A operand: plain 1x1 stride-1 GEMMs, one CTA");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + C::kBarOffset;
@@ -161,6 +182,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
   const uint32_t tmem_holder = bar_base + 8u * (2 * C::kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CTA pair: both CTAs of a cluster walk the same sequence of pair tiles (P.m_tiles counts 256-row pair tiles)
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const int tile_start = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_stride = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   // tile id -> (split, m_tile, n_tile); consecutive ids share the A rows (n fastest) for L2 reuse
   auto decode_tile = [&](int t, int& split, int& m_tile, int& n_tile, int& kb_begin, int& nk) {
@@ -169,6 +194,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
     const int rem = t - split * per_split;
     m_tile = rem / P.n_tiles;
     n_tile = rem - m_tile * P.n_tiles;
+    if constexpr (CTA2) m_tile = 2 * m_tile + static_cast<int>(rank);   // this CTA's 128-row half
     kb_begin = 0;
     int kb_end = P.num_kblocks;
     if constexpr (WGRAD) {
@@ -181,179 +207,187 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < C::kStages; ++s) {
-        mbar_init(full_bar(s), kProducerThreads + (BSTAT ? 0 : 1));
+        // gather threads + the TMA thread's expect_tx arrival; pair leader: + the peer's relayed arrival;
+        // pair peer: gather threads only (its B bytes are counted on the leader's barrier)
+        mbar_init(full_bar(s), ATMA ? 1
+                                    : (CTA2 ? (rank == 0 ? kProducerThreads + 2 : kProducerThreads)
+                                            : kProducerThreads + (BSTAT ? 0 : 1)));
         mbar_init(empty_bar(s), 1);
       }
       mbar_init(bstat_bar, 1);
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);
-        mbar_init(tempty_bar(a), 4);      // one arrival per epilogue warp
+        mbar_init(tempty_bar(a), CTA2 ? 8 : 4);      // one arrival per epilogue warp (of both CTAs of a pair)
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_holder, C::kTmemCols);
+    if constexpr (CTA2) tmem_alloc_cta2(tmem_holder, C::kTmemCols);
+    else tmem_alloc(tmem_holder, C::kTmemCols);
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();      // the peer's barriers must be initialised before anything arrives on them
+  else __syncthreads();
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_holder));
 
   if (warp < 4) {
-    // ============================ A producer (4 warps) ============================
-    // Address generation is hoisted out of the k-loop: per tile each thread precomputes, for its 8 rows, the
-    // element offset of the filter-tap origin and a bit mask of the taps that fall inside the image; per k-block
-    // only a (warp-uniform) tap offset is added.  wgrad rows change every k-block, so there each lane resolves ONE
-    // pixel and the quarter-warps fetch it with shuffles.
-    const int j = lane & 7;          // 16-byte column served by this thread
-    const int q = lane >> 3;         // row within a group of 4
-    const int ntaps = STEM ? P.kh : P.kh * P.kw;
-    uint32_t cnt = 0;                // k-blocks produced so far (ring position)
-    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
-      int split, m_tile, n_tile, kb_begin, nk;
-      decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
-      long long off8[8];             // fprop/dgrad: origin offsets (elements) of the 8 rows this thread serves
-      uint32_t mask8[8];             //              valid-tap bit masks
-      int chunk_r = 0, chunk_s = 0, chunk_c0 = 0;
-      bool chunk_ok = true;
-      uint32_t tile_off = 0;
-      if constexpr (!WGRAD) {
-        // lane l resolves row l of this warp's 32 rows (one pixel decode per lane, not per served row) ...
-        const RowPre rp = row_pre(P, pack_pixel(static_cast<long long>(m_tile) * BM + warp * 32 + lane, P));
-        const bool rvalid = rp.yb > -(1 << 27);
-        int oy = rp.yb, ox = rp.xb;
-        if (P.transposed && P.stride == 2) { oy >>= 1; ox >>= 1; }
-        const long long my_off = (static_cast<long long>(rp.nb + oy) * P.ws + ox) * P.cs;
-        // per-axis tap validity (bit r of vy: filter row r lands inside the image; likewise vx for columns)
-        uint32_t vy = 0, vx = 0;
-        if (rvalid) {
-          const int nky = P.kh, nkx = STEM ? 4 : P.kw;
-          for (int r = 0; r < nky; ++r) {
-            int h = P.transposed ? rp.yb - r : rp.yb + r;
-            bool ok = true;
-            if (P.transposed && P.stride == 2) { ok = (h & 1) == 0; h >>= 1; }
-            vy |= (ok && static_cast<unsigned>(h) < static_cast<unsigned>(P.hs) ? 1u : 0u) << r;
-          }
-          for (int c = 0; c < nkx; ++c) {
-            int w = P.transposed ? rp.xb - c : rp.xb + c;
-            bool ok = true;
-            if (P.transposed && P.stride == 2) { ok = (w & 1) == 0; w >>= 1; }
-            vx |= (ok && static_cast<unsigned>(w) < static_cast<unsigned>(P.ws) ? 1u : 0u) << c;
-          }
-        }
-        uint32_t my_mask;
-        if constexpr (STEM) {
-          my_mask = vy | (vx << 8);                     // taps r' in bits 0-3, column validity per s' in bits 8-11
-        } else {
-          my_mask = 0;
-          for (int r = 0; r < P.kh; ++r)
-            if ((vy >> r) & 1u) my_mask |= vx << (r * P.kw);
-        }
-        // ... and every thread fetches the 8 rows it serves
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = 4 * i + q;
-          const long long o = __shfl_sync(0xffffffffu, my_off, row);
-          const uint32_t m = __shfl_sync(0xffffffffu, my_mask, row);
-          if constexpr (STEM) {
-            off8[i] = o + (j >> 1) * P.cs + (j & 1) * 8;
-            mask8[i] = ((m >> (8 + (j >> 1))) & 1u) ? (m & 0xFu) : 0u;
-          } else {
-            off8[i] = o + j * 8;
-            mask8[i] = m;
-          }
-        }
-        tile_off = warp * 32 * 128;
-      } else {
-        // warp = (chunk, half): 64 gathered channels x 32 of the 64 pixel rows of the k-block
-        const int chunk = warp >> 1;
-        const int gchunk = m_tile * 2 + chunk;           // 64-row chunk of the [K_total, Cout] result
-        chunk_ok = gchunk < P.total_chunks;
-        if constexpr (STEM) {
-          chunk_r = gchunk;                              // filter row r'
-        } else {
-          const int tap = gchunk / P.cpb;
-          chunk_c0 = (gchunk - tap * P.cpb) * 64;
-          chunk_r = tap / P.kw;
-          chunk_s = tap - chunk_r * P.kw;
-        }
-        tile_off = chunk * 8192 + (warp & 1) * 32 * 128;
-      }
-      for (int it = 0; it < nk; ++it, ++cnt) {
-        const int s = static_cast<int>(cnt % nstages);
-        const uint32_t ph = (cnt / nstages) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const int kb = kb_begin + it;
-        const uint32_t dst_base = a_addr(s) + tile_off;
+    if constexpr (!ATMA) {
+      // ============================ A producer (4 warps) ============================
+      // Address generation is hoisted out of the k-loop: per tile each thread precomputes, for its 8 rows, the
+      // element offset of the filter-tap origin and a bit mask of the taps that fall inside the image; per k-block
+      // only a (warp-uniform) tap offset is added.  wgrad rows change every k-block, so there each lane resolves ONE
+      // pixel and the quarter-warps fetch it with shuffles.
+      const int j = lane & 7;          // 16-byte column served by this thread
+      const int q = lane >> 3;         // row within a group of 4
+      const int ntaps = STEM ? P.kh : P.kh * P.kw;
+      uint32_t cnt = 0;                // k-blocks produced so far (ring position)
+      for (int t = tile_start; t < P.num_tiles; t += tile_stride) {
+        int split, m_tile, n_tile, kb_begin, nk;
+        decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
+        long long off8[8];             // fprop/dgrad: origin offsets (elements) of the 8 rows this thread serves
+        uint32_t mask8[8];             //              valid-tap bit masks
+        int chunk_r = 0, chunk_s = 0, chunk_c0 = 0;
+        bool chunk_ok = true;
+        uint32_t tile_off = 0;
         if constexpr (!WGRAD) {
-          // warp-uniform tap offset
-          int tp;
-          long long toff;
-          if constexpr (STEM) {
-            tp = kb;
-            toff = static_cast<long long>(kb) * P.ws * P.cs;
-          } else {
-            const int tc = kb / P.cpb;
-            tp = P.tap_list[tc];
-            const int c0 = (kb - tc * P.cpb) * 64;
-            int r = tp / P.kw, sx = tp - r * P.kw;
-            if (P.transposed) {
-              if (P.stride == 2) { r >>= 1; sx >>= 1; }
-              toff = c0 - static_cast<long long>(r * P.ws + sx) * P.cs;
-            } else {
-              toff = c0 + static_cast<long long>(r * P.ws + sx) * P.cs;
+          // lane l resolves row l of this warp's 32 rows (one pixel decode per lane, not per served row) ...
+          const RowPre rp = row_pre(P, pack_pixel(static_cast<long long>(m_tile) * BM + warp * 32 + lane, P));
+          const bool rvalid = rp.yb > -(1 << 27);
+          int oy = rp.yb, ox = rp.xb;
+          if (P.transposed && P.stride == 2) { oy >>= 1; ox >>= 1; }
+          const long long my_off = (static_cast<long long>(rp.nb + oy) * P.ws + ox) * P.cs;
+          // per-axis tap validity (bit r of vy: filter row r lands inside the image; likewise vx for columns)
+          uint32_t vy = 0, vx = 0;
+          if (rvalid) {
+            const int nky = P.kh, nkx = STEM ? 4 : P.kw;
+            for (int r = 0; r < nky; ++r) {
+              int h = P.transposed ? rp.yb - r : rp.yb + r;
+              bool ok = true;
+              if (P.transposed && P.stride == 2) { ok = (h & 1) == 0; h >>= 1; }
+              vy |= (ok && static_cast<unsigned>(h) < static_cast<unsigned>(P.hs) ? 1u : 0u) << r;
+            }
+            for (int c = 0; c < nkx; ++c) {
+              int w = P.transposed ? rp.xb - c : rp.xb + c;
+              bool ok = true;
+              if (P.transposed && P.stride == 2) { ok = (w & 1) == 0; w >>= 1; }
+              vx |= (ok && static_cast<unsigned>(w) < static_cast<unsigned>(P.ws) ? 1u : 0u) << c;
             }
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = 4 * i + q;                   // row within this warp's 32 rows
-            const bool ok = (mask8[i] >> tp) & 1u;
-            const __nv_bfloat16* src = ok ? P.src + (off8[i] + toff) : P.src;
-            cp_async16(dst_base + row * 128 + ((j ^ (row & 7)) << 4), src, ok ? 16u : 0u);
-          }
-        } else {
-          // each lane resolves one of the warp's 32 pixels for this thread's fixed tap ...
-          const uint32_t mypk = chunk_ok ? pack_pixel(static_cast<long long>(kb) * 64 + (warp & 1) * 32 + lane, P) : 0u;
-          const RowPre rp = row_pre(P, mypk);
-          bool myok;
-          const __nv_bfloat16* myptr = tap_source(P, rp, chunk_r, STEM ? 0 : chunk_s, STEM ? 0 : chunk_c0, myok);
-          const unsigned long long myaddr = reinterpret_cast<unsigned long long>(myptr);
-          uint32_t okbits;                               // stem: validity per tap s' (4 bits); else 1 bit
+          uint32_t my_mask;
           if constexpr (STEM) {
-            okbits = 0;
-            const bool rowok = (mypk >> 31) && static_cast<unsigned>(rp.yb + chunk_r) < static_cast<unsigned>(P.hs);
-            for (int sp = 0; sp < 4; ++sp)
-              okbits |= (rowok && static_cast<unsigned>(rp.xb + sp) < static_cast<unsigned>(P.ws) ? 1u : 0u) << sp;
+            my_mask = vy | (vx << 8);                     // taps r' in bits 0-3, column validity per s' in bits 8-11
           } else {
-            okbits = myok ? 1u : 0u;
+            my_mask = 0;
+            for (int r = 0; r < P.kh; ++r)
+              if ((vy >> r) & 1u) my_mask |= vx << (r * P.kw);
           }
-          unsigned long long rowaddr = myaddr;
-          if constexpr (STEM)   // origin of the filter row (tap s' = 0), may lie outside the image: used only when valid
-            rowaddr = reinterpret_cast<unsigned long long>(
-                P.src + ((static_cast<long long>(rp.nb + rp.yb + chunk_r) * P.ws + rp.xb) * P.cs));
+          // ... and every thread fetches the 8 rows it serves
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int row = 4 * i + q;                   // ... and the quarter-warp serving that row fetches it
-            const unsigned long long a = __shfl_sync(0xffffffffu, rowaddr, row);
-            const uint32_t okb = __shfl_sync(0xffffffffu, okbits, row);
-            bool ok;
-            const __nv_bfloat16* src;
+            const int row = 4 * i + q;
+            const long long o = __shfl_sync(0xffffffffu, my_off, row);
+            const uint32_t m = __shfl_sync(0xffffffffu, my_mask, row);
             if constexpr (STEM) {
-              ok = (okb >> (j >> 1)) & 1u;
-              src = reinterpret_cast<const __nv_bfloat16*>(a) + j * 8;    // 4 taps x 16 channels are contiguous
+              off8[i] = o + (j >> 1) * P.cs + (j & 1) * 8;
+              mask8[i] = ((m >> (8 + (j >> 1))) & 1u) ? (m & 0xFu) : 0u;
             } else {
-              ok = okb & 1u;
-              src = reinterpret_cast<const __nv_bfloat16*>(a) + j * 8;
+              off8[i] = o + j * 8;
+              mask8[i] = m;
             }
-            cp_async16(dst_base + row * 128 + ((j ^ (row & 7)) << 4), ok ? src : P.src, ok ? 16u : 0u);
           }
+          tile_off = warp * 32 * 128;
+        } else {
+          // warp = (chunk, half): 64 gathered channels x 32 of the 64 pixel rows of the k-block
+          const int chunk = warp >> 1;
+          const int gchunk = m_tile * 2 + chunk;           // 64-row chunk of the [K_total, Cout] result
+          chunk_ok = gchunk < P.total_chunks;
+          if constexpr (STEM) {
+            chunk_r = gchunk;                              // filter row r'
+          } else {
+            const int tap = gchunk / P.cpb;
+            chunk_c0 = (gchunk - tap * P.cpb) * 64;
+            chunk_r = tap / P.kw;
+            chunk_s = tap - chunk_r * P.kw;
+          }
+          tile_off = chunk * 8192 + (warp & 1) * 32 * 128;
         }
-        // the mbarrier receives this thread's arrival when all of its cp.async above have landed (no wait here:
-        // the ring depth alone bounds the loads in flight), as CUTLASS's sm100 cp.async->UMMA mainloop does
-        cp_async_mbar_arrive_noinc(full_bar(s));
+        for (int it = 0; it < nk; ++it, ++cnt) {
+          const int s = static_cast<int>(cnt % nstages);
+          const uint32_t ph = (cnt / nstages) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const int kb = kb_begin + it;
+          const uint32_t dst_base = a_addr(s) + tile_off;
+          if constexpr (!WGRAD) {
+            // warp-uniform tap offset
+            int tp;
+            long long toff;
+            if constexpr (STEM) {
+              tp = kb;
+              toff = static_cast<long long>(kb) * P.ws * P.cs;
+            } else {
+              const int tc = kb / P.cpb;
+              tp = P.tap_list[tc];
+              const int c0 = (kb - tc * P.cpb) * 64;
+              int r = tp / P.kw, sx = tp - r * P.kw;
+              if (P.transposed) {
+                if (P.stride == 2) { r >>= 1; sx >>= 1; }
+                toff = c0 - static_cast<long long>(r * P.ws + sx) * P.cs;
+              } else {
+                toff = c0 + static_cast<long long>(r * P.ws + sx) * P.cs;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = 4 * i + q;                   // row within this warp's 32 rows
+              const bool ok = (mask8[i] >> tp) & 1u;
+              const __nv_bfloat16* src = ok ? P.src + (off8[i] + toff) : P.src;
+              cp_async16(dst_base + row * 128 + ((j ^ (row & 7)) << 4), src, ok ? 16u : 0u);
+            }
+          } else {
+            // each lane resolves one of the warp's 32 pixels for this thread's fixed tap ...
+            const uint32_t mypk = chunk_ok ? pack_pixel(static_cast<long long>(kb) * 64 + (warp & 1) * 32 + lane, P) : 0u;
+            const RowPre rp = row_pre(P, mypk);
+            bool myok;
+            const __nv_bfloat16* myptr = tap_source(P, rp, chunk_r, STEM ? 0 : chunk_s, STEM ? 0 : chunk_c0, myok);
+            const unsigned long long myaddr = reinterpret_cast<unsigned long long>(myptr);
+            uint32_t okbits;                               // stem: validity per tap s' (4 bits); else 1 bit
+            if constexpr (STEM) {
+              okbits = 0;
+              const bool rowok = (mypk >> 31) && static_cast<unsigned>(rp.yb + chunk_r) < static_cast<unsigned>(P.hs);
+              for (int sp = 0; sp < 4; ++sp)
+                okbits |= (rowok && static_cast<unsigned>(rp.xb + sp) < static_cast<unsigned>(P.ws) ? 1u : 0u) << sp;
+            } else {
+              okbits = myok ? 1u : 0u;
+            }
+            unsigned long long rowaddr = myaddr;
+            if constexpr (STEM)   // origin of the filter row (tap s' = 0), may lie outside the image: used only when valid
+              rowaddr = reinterpret_cast<unsigned long long>(
+                  P.src + ((static_cast<long long>(rp.nb + rp.yb + chunk_r) * P.ws + rp.xb) * P.cs));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = 4 * i + q;                   // ... and the quarter-warp serving that row fetches it
+              const unsigned long long a = __shfl_sync(0xffffffffu, rowaddr, row);
+              const uint32_t okb = __shfl_sync(0xffffffffu, okbits, row);
+              bool ok;
+              const __nv_bfloat16* src;
+              if constexpr (STEM) {
+                ok = (okb >> (j >> 1)) & 1u;
+                src = reinterpret_cast<const __nv_bfloat16*>(a) + j * 8;    // 4 taps x 16 channels are contiguous
+              } else {
+                ok = okb & 1u;
+                src = reinterpret_cast<const __nv_bfloat16*>(a) + j * 8;
+              }
+              cp_async16(dst_base + row * 128 + ((j ^ (row & 7)) << 4), ok ? src : P.src, ok ? 16u : 0u);
+            }
+          }
+          // the mbarrier receives this thread's arrival when all of its cp.async above have landed (no wait here:
+          // the ring depth alone bounds the loads in flight), as CUTLASS's sm100 cp.async->UMMA mainloop does
+          cp_async_mbar_arrive_noinc(full_bar(s));
+        }
       }
-    }
+    }  // !ATMA: with a TMA-fed A operand these four warps have nothing to do
   } else if (warp == kTmaWarp) {
     // ============================ B producer (TMA) ============================
     if (lane == 0 && BSTAT) {
@@ -369,7 +403,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
       }
     } else if (lane == 0) {
       uint32_t cnt = 0;
-      for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
+      for (int t = tile_start; t < P.num_tiles; t += tile_stride) {
         int split, m_tile, n_tile, kb_begin, nk;
         decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
         const int n0 = n_tile * BN;
@@ -377,8 +411,30 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
           const int s = static_cast<int>(cnt % nstages);
           const uint32_t ph = (cnt / nstages) & 1;
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_arrive_expect_tx(full_bar(s), C::kBBytes);
           const int kb = kb_begin + it;
+          if constexpr (CTA2) {
+            // this CTA's half of the B tile; both halves are accounted on the leader's barrier
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * C::kBBytes);
+            const int tc = kb / P.cpb;
+            const int kcoord = P.tap_list[tc] * P.cpb + (kb - tc * P.cpb);
+            tma_load_2d_cta2(b_addr(s), &tmap_b, full_bar(s), kcoord * BK, n0 + static_cast<int>(rank) * C::kBRows);
+            continue;
+          }
+          if constexpr (ATMA) {
+            if constexpr (!WGRAD) {
+              // A tile: 128 pixel rows x 64 channels of the [pixels][channels] matrix (rows past the end: zeros)
+              mbar_arrive_expect_tx(full_bar(s), C::kBBytes + C::kABytes);
+              tma_load_2d(a_addr(s), &tmap_a, full_bar(s), kb * BK, m_tile * BM);
+            } else {
+              // A tile: 64 pixels x (up to) two 64-channel chunks, MN-major like the dY tile
+              const int nchunks = min(2, P.total_chunks - 2 * m_tile);
+              mbar_arrive_expect_tx(full_bar(s), C::kBBytes + nchunks * 8192);
+              for (int i = 0; i < nchunks; ++i)
+                tma_load_2d(a_addr(s) + i * 8192, &tmap_a, full_bar(s), (2 * m_tile + i) * 64, kb * 64);
+            }
+          } else {
+            mbar_arrive_expect_tx(full_bar(s), C::kBBytes);
+          }
           if constexpr (!WGRAD) {
             int kcoord = kb;
             if constexpr (!STEM) {
@@ -396,15 +452,29 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
     }
   } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, WGRAD ? 1 : 0, WGRAD ? 1 : 0);
+    if (CTA2 && rank != 0) {
+      // pair peer: no MMAs to issue -- relay "my gathered A rows of this stage have landed" to the leader's barrier
+      if (lane == 0) {
+        uint32_t cnt = 0;
+        for (int t = tile_start; t < P.num_tiles; t += tile_stride) {
+          int split, m_tile, n_tile, kb_begin, nk;
+          decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
+          for (int it = 0; it < nk; ++it, ++cnt) {
+            const int s = static_cast<int>(cnt % nstages);
+            mbar_wait(full_bar(s), (cnt / nstages) & 1);
+            mbar_arrive_remote(mapa_rank(full_bar(s), 0));
+          }
+        }
+      }
+    } else if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(CTA2 ? 2 * BM : BM, BN, WGRAD ? 1 : 0, WGRAD ? 1 : 0);
       uint32_t cnt = 0, tcount = 0;
       if constexpr (BSTAT) mbar_wait(bstat_bar, 0);
-      for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++tcount) {
+      for (int t = tile_start; t < P.num_tiles; t += tile_stride, ++tcount) {
         int split, m_tile, n_tile, kb_begin, nk;
         decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
         const int acc = tcount & 1;
-        mbar_wait(tempty_bar(acc), ((tcount >> 1) & 1) ^ 1u);     // epilogue has drained this accumulator
+        mbar_wait(tempty_bar(acc), ((tcount >> 1) & 1) ^ 1u);     // epilogue(s) have drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int it = 0; it < nk; ++it, ++cnt) {
@@ -419,12 +489,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
                              WGRAD ? 8192u : 16u, 1024u);
           constexpr uint32_t kadv = WGRAD ? (2048u >> 4) : (32u >> 4);   // one UMMA_K (=16) step, in 16-byte units
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(tmem_d, adesc + static_cast<uint64_t>(k * kadv), bdesc + static_cast<uint64_t>(k * kadv), idesc,
-                      (it > 0 || k > 0) ? 1u : 0u);
-          umma_commit(empty_bar(s));
+          for (int k = 0; k < BK / 16; ++k) {
+            if constexpr (CTA2)
+              umma_bf16_cta2(tmem_d, adesc + static_cast<uint64_t>(k * kadv), bdesc + static_cast<uint64_t>(k * kadv),
+                             idesc, (it > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_bf16(tmem_d, adesc + static_cast<uint64_t>(k * kadv), bdesc + static_cast<uint64_t>(k * kadv), idesc,
+                        (it > 0 || k > 0) ? 1u : 0u);
+          }
+          if constexpr (CTA2) umma_commit_cta2(empty_bar(s));     // frees the stage in both CTAs
+          else umma_commit(empty_bar(s));
         }
-        umma_commit(tfull_bar(acc));
+        if constexpr (CTA2) umma_commit_cta2(tfull_bar(acc));     // both CTAs' epilogues may drain their halves
+        else umma_commit(tfull_bar(acc));
       }
     }
     __syncwarp();
@@ -433,7 +510,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32)
     const int row = quarter * 32 + lane;
     uint32_t tcount = 0;
-    for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++tcount) {
+    for (int t = tile_start; t < P.num_tiles; t += tile_stride, ++tcount) {
       int split, m_tile, n_tile, kb_begin, nk;
       decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
       const int acc = tcount & 1;
@@ -442,52 +519,62 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
       const int n0 = n_tile * BN;
       if constexpr (!WGRAD) {
-        // TMEM -> registers -> bf16 -> this warp's smem staging tile (32 rows x BN), then whole rows go out as
-        // coalesced 16-byte-per-lane stores (BN*2 contiguous bytes per row)
+        // TMEM -> registers -> bf16 -> this warp's smem staging tile (32 rows x kEpiCols), then the rows go out as
+        // coalesced 16-byte-per-lane stores (one full 128-byte line per row and pass)
         const uint32_t stage_base = smem_base + C::kEpiOffset + quarter * C::kEpiWarpBytes;
         const uint32_t my_row = stage_base + lane * C::kStageRowBytes;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[8 * jj + 2 * e]), __uint_as_float(v[8 * jj + 2 * e + 1]));
-              pk[e] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + c * 64 + jj * 16), "r"(pk[0]),
-                         "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
-                         : "memory");
-          }
-        }
-        __syncwarp();
-        constexpr int kLanesPerRow = BN * 2 / 16;               // 32 / 16 / 8
-        constexpr int kRowsPerIter = 32 / kLanesPerRow;         // 1 / 2 / 4
+        constexpr int kLanesPerRow = C::kEpiCols * 2 / 16;      // 8 lanes x 16 B = one 128-byte line
+        constexpr int kRowsPerIter = 32 / kLanesPerRow;         // 4 rows per store iteration
+        constexpr int kIters = 32 / kRowsPerIter;               // 8
         const int sub = lane / kLanesPerRow, col16 = lane % kLanesPerRow;
         const long long p0 = static_cast<long long>(m_tile) * BM + quarter * 32;
-#pragma unroll 1
-        for (int r0 = 0; r0 < 32; r0 += kRowsPerIter) {
-          const int rr = r0 + sub;
-          const long long p = p0 + rr;
-          if (p < P.pixels && nk > 0) {
-            long long orow = p;
-            if (P.cls_on) {                                     // class pixel -> row of the full image
-              const uint32_t pk = pack_pixel(p, P);
-              const int n = (pk >> 18) & 0x1FFF, yy = (pk >> 9) & 0x1FF, xx = pk & 0x1FF;
-              orow = (static_cast<long long>(n) * P.full_h + 2 * yy + P.cls_py) * P.full_w + 2 * xx + P.cls_px;
-            }
-            uint4 val;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
-                         : "r"(stage_base + rr * C::kStageRowBytes + col16 * 16));
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + orow * P.ldc + n0 + col16 * 8) = val;
+        // output row of each of the 8 tile rows this lane stores (-1: out of range), resolved once per tile
+        long long orow8[kIters];
+#pragma unroll
+        for (int i = 0; i < kIters; ++i) {
+          const long long p = p0 + i * kRowsPerIter + sub;
+          long long orow = (p < P.pixels && nk > 0) ? p : -1;
+          if (orow >= 0 && P.cls_on) {                          // class pixel -> row of the full image
+            const uint32_t pk = pack_pixel(p, P);
+            const int n = (pk >> 18) & 0x1FFF, yy = (pk >> 9) & 0x1FF, xx = pk & 0x1FF;
+            orow = (static_cast<long long>(n) * P.full_h + 2 * yy + P.cls_py) * P.full_w + 2 * xx + P.cls_px;
           }
+          orow8[i] = orow;
         }
-        __syncwarp();                                           // staging tile is reused by the next tile
+#pragma unroll 1
+        for (int cb = 0; cb < BN / C::kEpiCols; ++cb) {
+#pragma unroll
+          for (int c = 0; c < C::kEpiCols / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + cb * C::kEpiCols + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[8 * jj + 2 * e]), __uint_as_float(v[8 * jj + 2 * e + 1]));
+                pk[e] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + c * 64 + jj * 16), "r"(pk[0]),
+                           "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                           : "memory");
+            }
+          }
+          __syncwarp();
+          __nv_bfloat16* out_cols = reinterpret_cast<__nv_bfloat16*>(P.out) + n0 + cb * C::kEpiCols + col16 * 8;
+#pragma unroll
+          for (int i = 0; i < kIters; ++i) {
+            if (orow8[i] >= 0) {
+              uint4 val;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                           : "r"(stage_base + (i * kRowsPerIter + sub) * C::kStageRowBytes + col16 * 16));
+              *reinterpret_cast<uint4*>(out_cols + orow8[i] * P.ldc) = val;
+            }
+          }
+          __syncwarp();                                         // staging tile is reused by the next pass / tile
+        }
       } else {
         // partials are stored TRANSPOSED, [split][Cout][K_total]: the 32 lanes of a warp hold 32 consecutive k rows,
         // so each scalar store below is one coalesced 128-byte line, and the reduce kernel reads/writes along k
@@ -509,15 +596,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const IgemmParams P) {
       // accumulator drained: hand it back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CTA2 && rank != 0) mbar_arrive_remote(mapa_rank(tempty_bar(acc), 0));   // the leader issues the MMAs
+        else mbar_arrive(tempty_bar(acc));
+      }
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if constexpr (CTA2) cluster_sync_all();   // neither CTA may exit (or free TMEM) while its peer still uses its smem/barriers
+  else __syncthreads();
   if (warp == kMmaWarp) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if constexpr (CTA2) tmem_dealloc_cta2(tmem_base, C::kTmemCols);
+    else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -561,27 +654,82 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t
   return DIRB200_OK;
 }
 
-template <int BN, bool WGRAD, bool STEM, bool BSTAT>
-static int launch_igemm_impl(const CUtensorMap& tm, const IgemmParams& Q, cudaStream_t st) {
+template <int BN, bool WGRAD, bool STEM, bool BSTAT, bool ATMA = false>
+static int launch_igemm_impl(const CUtensorMap& tm, const CUtensorMap& tma, const IgemmParams& Q, cudaStream_t st) {
   using C = Cfg<BN, !WGRAD>;
   static bool configured = false;
   if (!configured) {
-    DIRB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, WGRAD, STEM, BSTAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   C::kSmemBytes));
+    DIRB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, WGRAD, STEM, BSTAT, false, ATMA>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
   const int grid = Q.num_tiles < num_sms() ? Q.num_tiles : num_sms();
-  igemm_kernel<BN, WGRAD, STEM, BSTAT><<<grid, kThreads, C::kSmemBytes, st>>>(tm, Q);
+  igemm_kernel<BN, WGRAD, STEM, BSTAT, false, ATMA><<<grid, kThreads, C::kSmemBytes, st>>>(tm, tma, Q);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
 
+// CTA-pair variant: (2,1,1) clusters, one pair per two SMs; Q.m_tiles / Q.num_tiles count 256-row pair tiles.
+template <int BN>
+static int launch_igemm_cta2(const CUtensorMap& tm, const IgemmParams& Q, cudaStream_t st) {
+  using C = Cfg<BN, true, true>;
+  auto kern = igemm_kernel<BN, false, false, false, true>;
+  static bool configured = false;
+  if (!configured) {
+    DIRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(num_sms() & ~1, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // the persistent tile walk assumes every cluster of the grid is resident at once: cap the grid at the number of
+  // CTA pairs the device can actually co-schedule (a TPC with one SM fused off cannot host a pair)
+  static int max_pairs = 0;
+  if (max_pairs == 0) {
+    int mc = 0;
+    if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) != cudaSuccess || mc <= 0) {
+      (void)cudaGetLastError();
+      mc = num_sms() / 2;
+    }
+    max_pairs = mc < num_sms() / 2 ? mc : num_sms() / 2;
+    if (getenv("DIRB200_VERBOSE")) fprintf(stderr, "dirb200: igemm CTA pairs BN=%d: %d co-resident clusters\n", BN, max_pairs);
+  }
+  const int pairs = Q.num_tiles < max_pairs ? Q.num_tiles : max_pairs;
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  DIRB_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, tm, Q));
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+// DIRB200_CTA2=1 routes the fprop / dgrad GEMMs with BN >= 128 through CTA pairs (tcgen05 cta_group::2).
+static bool cta2_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DIRB200_CTA2");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
+// tma != nullptr: the A operand is a plain [pixels][channels] matrix (1x1 stride-1 conv) and is loaded by TMA too
 template <int BN, bool WGRAD, bool STEM>
-static int launch_igemm(const CUtensorMap& tm, const IgemmParams& P, int m_tiles, int splits, cudaStream_t st) {
+static int launch_igemm(const CUtensorMap& tm, const IgemmParams& P, int m_tiles, int splits, cudaStream_t st,
+                        const CUtensorMap* tma = nullptr) {
   using C = Cfg<BN, !WGRAD>;
   IgemmParams Q = P;
   Q.m_tiles = m_tiles;
   Q.num_tiles = m_tiles * P.n_tiles * splits;
+  if constexpr (!STEM) {
+    if (tma) return launch_igemm_impl<BN, WGRAD, false, false, true>(tm, *tma, Q, st);
+  }
   if constexpr (!WGRAD) {
     // B stationary when one N tile covers the layer, the weights fit beside the A ring and there are enough
     // tiles per CTA to amortise the one-off load
@@ -594,10 +742,10 @@ static int launch_igemm(const CUtensorMap& tm, const IgemmParams& P, int m_tiles
     }();
     if (bstat_enabled && P.n_tiles == 1 && ns >= 4 && Q.num_tiles >= 4 * num_sms()) {
       Q.nstages = ns;
-      return launch_igemm_impl<BN, false, STEM, true>(tm, Q, st);
+      return launch_igemm_impl<BN, false, STEM, true>(tm, tm, Q, st);
     }
   }
-  return launch_igemm_impl<BN, WGRAD, STEM, false>(tm, Q, st);
+  return launch_igemm_impl<BN, WGRAD, STEM, false>(tm, tm, Q, st);
 }
 
 // GEMM-N tile width: 256 halves the A-operand traffic per FLOP (the conv kernels are bound by L2->SM operand
@@ -623,6 +771,30 @@ static int check_shape(const ConvShape& s, bool stem, const char* who) {
   return DIRB200_OK;
 }
 
+// DIRB200_ATMA=0 keeps the cp.async gather for every layer (A/B measurements); default: 1x1 stride-1 GEMMs take the
+// A operand through TMA.
+static bool atma_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DIRB200_ATMA");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+static bool is_plain_gemm(const ConvShape& s, bool stem) {
+  return !stem && s.kh == 1 && s.kw == 1 && s.stride == 1 && s.pad == 0 && atma_enabled();
+}
+
+// CTA-pair launch of an fprop / dgrad GEMM: B = wmat [n_dim][ktot] (K-major), each CTA TMA-loads bn/2 of its rows.
+static int launch_cta2(const __nv_bfloat16* wmat, int ktot, int n_dim, int bn, const IgemmParams& P, int m_tiles,
+                       cudaStream_t st) {
+  CUtensorMap tm;
+  if (int rc = make_tmap_bf16_2d(&tm, wmat, ktot, n_dim, static_cast<uint64_t>(ktot) * 2, bn / 2)) return rc;
+  IgemmParams Q = P;
+  Q.m_tiles = (m_tiles + 1) / 2;                 // 256-row pair tiles
+  Q.num_tiles = Q.m_tiles * P.n_tiles;
+  return bn == 256 ? launch_igemm_cta2<256>(tm, Q, st) : launch_igemm_cta2<128>(tm, Q, st);
+}
+
 // Y[n,ho,wo,cout] = conv(X[n,h,w,cin], W[cout][kh][kw][cin])
 int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, const ConvShape& s, bool stem,
                cudaStream_t st) {
@@ -642,8 +814,15 @@ int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y,
   const int bn = pick_bn(s.cout, m_tiles);
   P.n_tiles = s.cout / bn;
   CUtensorMap tm;
+  if (!stem && bn >= 128 && cta2_enabled()) return launch_cta2(w, ktot, s.cout, bn, P, m_tiles, st);
   if (int rc = make_tmap_bf16_2d(&tm, w, ktot, s.cout, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
   if (stem) return DISPATCH_BN(bn, false, true, tm, P, m_tiles, 1, st);
+  if (is_plain_gemm(s, stem)) {
+    CUtensorMap ta;     // x as [pixels][cin]
+    if (int rc = make_tmap_bf16_2d(&ta, x, s.cin, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cin) * 2, BM))
+      return rc;
+    return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st, &ta);
+  }
   return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st);
 }
 
@@ -668,7 +847,14 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
     const int m_tiles = static_cast<int>((P.pixels + BM - 1) / BM);
     const int bn = pick_bn(s.cin, m_tiles);
     P.n_tiles = s.cin / bn;
+    if (bn >= 128 && cta2_enabled()) return launch_cta2(wt, ktot, s.cin, bn, P, m_tiles, st);
     if (int rc = make_tmap_bf16_2d(&tm, wt, ktot, s.cin, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
+    if (is_plain_gemm(s, false)) {
+      CUtensorMap ta;   // dy as [pixels][cout]
+      if (int rc = make_tmap_bf16_2d(&ta, dy, s.cout, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cout) * 2, BM))
+        return rc;
+      return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st, &ta);
+    }
     return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st);
   }
   // stride 2: one launch per output-pixel parity class; a class without any tap receives no gradient (zeros)
@@ -698,6 +884,10 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
     const int m_tiles = static_cast<int>((Q.pixels + BM - 1) / BM);
     const int bn = pick_bn(s.cin, m_tiles);
     Q.n_tiles = s.cin / bn;
+    if (bn >= 128 && cta2_enabled()) {
+      if (int rc = launch_cta2(wt, ktot, s.cin, bn, Q, m_tiles, st)) return rc;
+      continue;
+    }
     if (int rc = make_tmap_bf16_2d(&tm, wt, ktot, s.cin, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
     if (int rc = DISPATCH_BN(bn, false, false, tm, Q, m_tiles, 1, st)) return rc;
   }
@@ -747,6 +937,12 @@ int conv_wgrad_partials(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
   if (int rc = make_tmap_bf16_2d(&tm, dy, s.cout, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cout) * 2, 64))
     return rc;
   if (stem) return DISPATCH_BN(bn, true, true, tm, P, m_tiles, splits, st);
+  if (is_plain_gemm(s, stem)) {
+    CUtensorMap ta;     // x as [pixels][cin], 64-pixel x 64-channel boxes
+    if (int rc = make_tmap_bf16_2d(&ta, x, s.cin, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cin) * 2, 64))
+      return rc;
+    return DISPATCH_BN(bn, true, false, tm, P, m_tiles, splits, st, &ta);
+  }
   return DISPATCH_BN(bn, true, false, tm, P, m_tiles, splits, st);
 }
 

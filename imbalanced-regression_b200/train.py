@@ -158,20 +158,57 @@ def train(train_loader, model, optimizer, epoch, args):
     return losses.avg
 
 
-def validate(val_loader, model, prefix='Val'):
+def shot_metrics(preds, labels, train_labels, many_shot_thr=100, low_shot_thr=20):
+    """Many / median / low-shot MSE, L1 and G-Mean (agedb-dir/train.py:338-391), reduced on the GPU in one pass:
+    an exact int64 histogram of int(train_label) + dirb200_shot_metrics over the predictions.  `preds` / `labels`
+    may be torch tensors (any device) or numpy arrays; returns the reference's nested dict (+ 'overall')."""
+    import _lib
+    dev = torch.device('cuda', torch.cuda.current_device())
+    as_dev = lambda a: torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a,
+                                       dtype=torch.float32).reshape(-1).to(dev).contiguous()
+    if not isinstance(preds, (torch.Tensor, np.ndarray)):
+        raise TypeError(f'Type ({type(preds)}) of predictions not supported')
+    p, l, t = as_dev(preds), as_dev(labels), as_dev(train_labels)
+    assert p.numel() == l.numel()
+    nbins = int(max(float(t.max()) if t.numel() else 0.0, float(l.max()) if l.numel() else 0.0, 0.0)) + 2
+    hist = torch.zeros(nbins, dtype=torch.int64, device=dev)
+    _lib.call("dirb200_int_label_histogram", _lib.ptr(t), t.numel(), nbins, _lib.ptr(hist), _lib.stream_ptr())
+    out = torch.empty(4, 4, dtype=torch.float64, device=dev)
+    _lib.call("dirb200_shot_metrics", _lib.ptr(p), _lib.ptr(l), p.numel(), _lib.ptr(hist), nbins, int(many_shot_thr),
+              int(low_shot_thr), _lib.ptr(out), _lib.stream_ptr())
+    o = out.cpu().numpy()
+    shot_dict = defaultdict(dict)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        for row, name in enumerate(('overall', 'many', 'median', 'low')):
+            cnt = o[row, 0]
+            shot_dict[name]['mse'] = o[row, 1] / cnt
+            shot_dict[name]['l1'] = o[row, 2] / cnt
+            shot_dict[name]['gmean'] = float(np.exp(o[row, 3] / cnt))
+    return shot_dict
+
+
+def validate(val_loader, model, train_labels=None, prefix='Val'):
+    """agedb-dir/train.py:286-335: eval-mode forward over the loader; predictions stay on the device and the
+    overall + shot metrics come from ONE reduction kernel at the end (the reference copies every batch to the host
+    and loops over np.unique(labels) there)."""
     model.eval()
-    se, ae, n, logs = 0., 0., 0, []
+    preds, labels = [], []
     with torch.no_grad():
         for (inputs, targets, _) in val_loader:
             inputs, targets = inputs.cuda(non_blocking=True), targets.cuda(non_blocking=True)
-            err = (model(inputs) - targets).abs().reshape(-1)
-            se += float((err ** 2).sum())
-            ae += float(err.sum())
-            logs.append(torch.log(err.clamp_min(1e-10)).cpu())
-            n += err.numel()
-    gmean = float(torch.exp(torch.cat(logs).mean())) if logs else float('nan')
-    print(f" * {prefix}: MSE {se / max(n, 1):.3f}\tL1 {ae / max(n, 1):.3f}\tG-Mean {gmean:.3f}")
-    return se / max(n, 1), ae / max(n, 1), gmean
+            preds.append(model(inputs).reshape(-1).float())
+            labels.append(targets.reshape(-1).float())
+    if not preds:
+        return float('nan'), float('nan'), float('nan')
+    preds, labels = torch.cat(preds), torch.cat(labels)
+    shot = shot_metrics(preds, labels, train_labels if train_labels is not None else labels.new_zeros(0))
+    ov = shot['overall']
+    print(f" * Overall: MSE {ov['mse']:.3f}\tL1 {ov['l1']:.3f}\tG-Mean {ov['gmean']:.3f}")
+    if train_labels is not None:
+        for name in ('many', 'median', 'low'):
+            d = shot[name]
+            print(f" * {name.capitalize()}: MSE {d['mse']:.3f}\tL1 {d['l1']:.3f}\tG-Mean {d['gmean']:.3f}")
+    return ov['mse'], ov['l1'], ov['gmean']
 
 
 def main(argv=None):
@@ -212,6 +249,8 @@ def main(argv=None):
                                    pin_memory=True, drop_last=False)
     train_loader, val_loader, test_loader = mk(train_dataset, True), mk(val_dataset, False), mk(test_dataset, False)
     print(f"Training data size: {len(train_dataset)}")
+    # shot metrics compare against the WHOLE training label column (reference: df_train['age'], train.py:121)
+    train_labels = np.asarray(train_dataset.labels if args.synthetic else parts['train']['age'].values)
 
     print('=====> Building model...')
     model = resnet50(fds=args.fds, bucket_num=args.bucket_num, bucket_start=args.bucket_start,
@@ -224,7 +263,7 @@ def main(argv=None):
         assert args.resume, 'Specify a trained model using [args.resume]'
         checkpoint = torch.load(args.resume)
         model.load_state_dict(checkpoint['state_dict'], strict=False)
-        validate(test_loader, model, prefix='Test')
+        validate(test_loader, model, train_labels=train_labels, prefix='Test')
         return
 
     if args.retrain_fc:
@@ -253,7 +292,7 @@ def main(argv=None):
     for epoch in range(args.start_epoch, args.epoch):
         adjust_learning_rate(optimizer, epoch, args)
         train_loss = train(train_loader, model, optimizer, epoch, args)
-        val_mse, val_l1, val_gmean = validate(val_loader, model)
+        val_mse, val_l1, val_gmean = validate(val_loader, model, train_labels=train_labels)
         metric = val_mse if args.loss == 'mse' else val_l1
         is_best = metric < args.best_loss
         args.best_loss = min(metric, args.best_loss)

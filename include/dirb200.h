@@ -159,6 +159,20 @@ int dirb200_lds_weights(const float* labels, int64_t n, int max_target, int rewe
 int dirb200_lds_table_lookup(const float* values, int64_t n, float mult, int max_bin, const float* table,
                              float* weights_out, void* stream);
 
+/* ------------------------------------------------ evaluation metrics ---- */
+/* hist[int(label)] += 1 for 0 <= int(label) < nbins (int64, bit-exact, ADDS; no clamping): the per-label-value
+ * training counts that shot_metrics compares against, agedb-dir/train.py:339,350. */
+int dirb200_int_label_histogram(const float* labels, int64_t n, int nbins, int64_t* hist, void* stream);
+
+/* Overall and many / median / low-shot error sums of a prediction vector in one pass (replaces the host loop over
+ * np.unique(labels) of shot_metrics, agedb-dir/train.py:338-391, and the MSE / L1 / G-Mean meters of validate,
+ * :286-335).  A sample is "many"-shot when the training count of its label value is > many_shot_thr, "low" when
+ * it is < low_shot_thr (label values absent from training or not integer valued count 0), else "median".
+ * out16 (double[4][4], OVERWRITTEN): rows = overall, many, median, low; columns = count, sum (pred-label)^2,
+ * sum |pred-label|, sum log|pred-label|  ->  mse = c1/c0, l1 = c2/c0, gmean = exp(c3/c0). */
+int dirb200_shot_metrics(const float* preds, const float* labels, int64_t n, const int64_t* train_hist, int nbins,
+                         int many_shot_thr, int low_shot_thr, double* out16, void* stream);
+
 /* ------------------------------------------------- convolution stack ---- */
 /* Activations are NHWC bf16; weights arrive in the reference's fp32
  * [Cout][Cin][KH][KW] layout (agedb-dir/resnet.py:46-51,79,112-118, i.e. the

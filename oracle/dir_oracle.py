@@ -476,3 +476,29 @@ class FDSVariantState(FDSState):
             bsz, c, h, w = shape
             return x.reshape(bsz, h, w, c).transpose(0, 3, 1, 2)
         return x
+
+
+# --------------------------------------------------------------------------
+# evaluation metrics
+# --------------------------------------------------------------------------
+def shot_metrics(preds, labels, train_labels, many_shot_thr: int = 100, low_shot_thr: int = 20) -> dict:
+    """Many / median / low-shot MSE, L1, G-Mean -- follows agedb-dir/train.py:338-391 (+ 'overall', :286-335).
+
+    Group of a test sample = by the number of training samples whose int(label) equals the sample's label value:
+    > many_shot_thr -> many, < low_shot_thr -> low, else median (train.py:366-381).  Vectorised instead of the
+    reference's loop over np.unique(labels); sums in float64."""
+    preds = np.asarray(preds, dtype=np.float32).reshape(-1)
+    labels = np.asarray(labels, dtype=np.float32).reshape(-1)
+    tl = np.asarray(train_labels).astype(int).reshape(-1)                     # train.py:339
+    counts = np.asarray([np.count_nonzero(tl == l) for l in labels])         # len(train_labels[train_labels == l])
+    err = (preds - labels).astype(np.float64)                                 # float32 difference, widened
+    groups = {"overall": np.ones(labels.shape, bool), "many": counts > many_shot_thr, "low": counts < low_shot_thr}
+    groups["median"] = ~groups["many"] & ~groups["low"]
+    out = {}
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for name, m in groups.items():
+            n = np.count_nonzero(m)
+            e = err[m]
+            out[name] = {"mse": np.sum(e * e) / n, "l1": np.sum(np.abs(e)) / n,
+                         "gmean": float(np.exp(np.sum(np.log(np.abs(e))) / n)), "count": int(n)}
+    return out

@@ -1,0 +1,119 @@
+"""Standalone GPU check + per-layer timing of the conv GEMMs (not collected by pytest).
+
+    DIRB200_CTA2=1 python tests/cta2_check.py parity     # CTA-pair kernels vs torch (same checks as test_gpu_conv)
+    DIRB200_CTA2=0 python tests/cta2_check.py time       # per-layer fprop/dgrad times, batch 256 ResNet-50 shapes
+    DIRB200_CTA2=1 python tests/cta2_check.py time
+
+DIRB200_CTA2 is read once per process, hence the separate invocations.
+"""
+import json
+import os
+import sys
+import traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "imbalanced-regression_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+PARITY = [
+    # n, h, w, cin, cout, k, stride, pad
+    (2, 8, 8, 64, 256, 1, 1, 0),        # one pair tile, peer half entirely out of range
+    (2, 8, 8, 128, 128, 3, 2, 1),       # stride-2 dgrad parity classes
+    (2, 8, 8, 256, 512, 1, 2, 0),
+    (3, 7, 7, 512, 512, 3, 1, 1),       # ragged M (147 rows = 2 m-tiles), 72 k-blocks
+    (1, 14, 14, 1024, 256, 1, 1, 0),    # 16 k-blocks > ring depth
+    (4, 7, 7, 512, 2048, 1, 1, 0),      # 16 n-tiles
+    (5, 9, 11, 64, 128, 3, 2, 1),       # odd sizes
+    (16, 56, 56, 64, 256, 1, 1, 0),     # BN=256 path: 392 m-tiles -> 196 pair tiles over 74 clusters
+    (16, 28, 28, 128, 128, 3, 1, 1),    # BN=128 pair path, 98 m-tiles, 18 k-blocks
+    (37, 14, 14, 256, 256, 3, 1, 1),    # odd number of m-tiles (57): last pair has an empty peer half
+    (64, 14, 14, 256, 1024, 1, 1, 0),   # several tiles per cluster, accumulator double buffering
+]
+
+# (name, n, h, w, cin, cout, k, stride, pad): batch-256 ResNet-50 layers with Cout (fprop) / Cin (dgrad) >= 128
+LAYERS = [
+    ("l1.c3 64->256 1x1 56", 256, 56, 56, 64, 256, 1, 1, 0),
+    ("l1.c1 256->64 1x1 56", 256, 56, 56, 256, 64, 1, 1, 0),
+    ("l2.c2 128->128 3x3 28", 256, 28, 28, 128, 128, 3, 1, 1),
+    ("l2.c3 128->512 1x1 28", 256, 28, 28, 128, 512, 1, 1, 0),
+    ("l2.c1 512->128 1x1 28", 256, 28, 28, 512, 128, 1, 1, 0),
+    ("l3.c2 256->256 3x3 14", 256, 14, 14, 256, 256, 3, 1, 1),
+    ("l3.c3 256->1024 1x1 14", 256, 14, 14, 256, 1024, 1, 1, 0),
+    ("l3.c1 1024->256 1x1 14", 256, 14, 14, 1024, 256, 1, 1, 0),
+    ("l4.c2 512->512 3x3 7", 256, 7, 7, 512, 512, 3, 1, 1),
+    ("l4.c3 512->2048 1x1 7", 256, 7, 7, 512, 2048, 1, 1, 0),
+    ("l4.c1 2048->512 1x1 7", 256, 7, 7, 2048, 512, 1, 1, 0),
+    ("l3.ds 512->1024 1x1/2 28", 256, 28, 28, 512, 1024, 1, 2, 0),
+    ("l3.c2s 256->256 3x3/2 28", 256, 28, 28, 256, 256, 3, 2, 1),
+]
+
+
+def parity():
+    from test_gpu_conv import run_conv
+    bad = 0
+    for cfg in PARITY:
+        try:
+            run_conv(*cfg)
+            torch.cuda.synchronize()
+            print("PASS", cfg, flush=True)
+        except Exception as e:  # noqa: BLE001
+            bad += 1
+            print("FAIL", cfg, repr(e)[:300], flush=True)
+            traceback.print_exc()
+            try:
+                torch.cuda.synchronize()
+            except Exception:  # noqa: BLE001  (sticky CUDA error: nothing more can run in this process)
+                print("CUDA context lost; stopping", flush=True)
+                break
+    print(f"parity: {len(PARITY) - bad}/{len(PARITY)} ok (DIRB200_CTA2={os.environ.get('DIRB200_CTA2', '0')})")
+    return bad
+
+
+def time_layers(reps=10):
+    import _lib, _convlib  # noqa: F401
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for name, n, h, w, cin, cout, k, stride, pad in LAYERS:
+        ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        x = torch.randn(n, h, w, cin, device="cuda").to(torch.bfloat16)
+        dy = torch.randn(n, ho, wo, cout, device="cuda").to(torch.bfloat16)
+        wf = (torch.randn(cout, k, k, cin, device="cuda") / (cin * k * k) ** 0.5).to(torch.bfloat16)
+        wd = wf.permute(3, 1, 2, 0).contiguous()
+        y = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device="cuda")
+        dx = torch.empty(n, h, w, cin, dtype=torch.bfloat16, device="cuda")
+        shape = (n, h, w, cin, cout, k, k, stride, pad)
+        st = _lib.stream_ptr()
+        res = {}
+        for which in ("fprop", "dgrad"):
+            ts = []
+            for it in range(reps + 2):
+                flush.fill_(it & 1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                if which == "fprop":
+                    _lib.call("dirb200_conv_fprop", _lib.ptr(x), _lib.ptr(wf), _lib.ptr(y), *shape, 0, st)
+                else:
+                    _lib.call("dirb200_conv_dgrad", _lib.ptr(dy), _lib.ptr(wd), _lib.ptr(dx), *shape, st)
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    ts.append(e0.elapsed_time(e1))
+            ms = sorted(ts)[len(ts) // 2]
+            flops = 2.0 * n * ho * wo * cout * cin * k * k
+            res[which] = {"ms": round(ms, 4), "tflops": round(flops / ms / 1e9, 1)}
+        out[name] = res
+        print(f"{name:28s} fprop {res['fprop']['ms']:.3f} ms {res['fprop']['tflops']:7.1f} TF/s   "
+              f"dgrad {res['dgrad']['ms']:.3f} ms {res['dgrad']['tflops']:7.1f} TF/s", flush=True)
+    tag = os.environ.get("DIRB200_CTA2", "0")
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"conv_layers_cta2_{tag}.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
+    if mode == "parity":
+        sys.exit(1 if parity() else 0)
+    time_layers()

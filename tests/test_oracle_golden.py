@@ -191,3 +191,14 @@ def test_nyud2_bucket_weights_host_matches_reference():
         for lds_on in (0, 1):
             bw = datasets.depth_bucket_weights([int(v) for v in g["train_bucket_num"]], rw, lds=bool(lds_on))
             assert_close(bw, g[f"bw_{rw}_{lds_on}"], rtol=1e-6, atol=0, what=f"{rw} {lds_on}")
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_shot_metrics_match_reference(tag):
+    # fixture: the reference's own shot_metrics on the AgeDB test labels (tests/golden/make_golden_metrics.py)
+    g = golden("metrics")
+    sd = O.shot_metrics(g[f"{tag}_preds"], g[f"{tag}_labels"], g["train_labels"])
+    got = [[sd[k][m] for m in ("mse", "l1", "gmean")] for k in ("many", "median", "low")]
+    assert_close(got, g[f"{tag}_ref"], rtol=1e-6, atol=1e-12, what=f"shot metrics {tag}")
+    assert_close([sd["overall"][m] for m in ("mse", "l1", "gmean")], g[f"{tag}_overall"], rtol=1e-6, atol=1e-12)
+    assert sd["many"]["count"] + sd["median"]["count"] + sd["low"]["count"] == sd["overall"]["count"] == 2140
