@@ -750,8 +750,14 @@ static int launch_igemm(const CUtensorMap& tm, const IgemmParams& P, int m_tiles
 
 // GEMM-N tile width: 256 halves the A-operand traffic per FLOP (the conv kernels are bound by L2->SM operand
 // bandwidth), used when it still leaves >= 2 tiles per SM; else 128; 64 for 64-channel layers.
-static int pick_bn(int n_dim, long long m_tiles, int splits = 1) {
-  if (n_dim % 256 == 0 && m_tiles * (n_dim / 256) * splits >= 2LL * num_sms()) return 256;
+// gather_fed (A operand through the cp.async gather, i.e. every conv that is not a plain 1x1 GEMM): measured, the
+// gather sustains one 16 KB A tile per ~0.6 us per SM whatever BN is, so the launch time is (waves x k-blocks) and the
+// widest tile always wins once at least half of the SMs have work.
+static int pick_bn(int n_dim, long long m_tiles, bool gather_fed = false) {
+  if (n_dim % 256 == 0) {
+    const long long t256 = m_tiles * (n_dim / 256);
+    if (t256 >= 2LL * num_sms() || (gather_fed && 2 * t256 >= num_sms())) return 256;
+  }
   if (n_dim % 128 == 0) return 128;
   return 64;
 }
@@ -811,7 +817,7 @@ int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y,
   for (int i = 0; i < 9; ++i) P.tap_list[i] = i;
   P.ldc = s.cout; P.out = y;
   const int m_tiles = static_cast<int>((P.pixels + BM - 1) / BM);
-  const int bn = pick_bn(s.cout, m_tiles);
+  const int bn = pick_bn(s.cout, m_tiles, !is_plain_gemm(s, stem));
   P.n_tiles = s.cout / bn;
   CUtensorMap tm;
   if (!stem && bn >= 128 && cta2_enabled()) return launch_cta2(w, ktot, s.cout, bn, P, m_tiles, st);
@@ -845,7 +851,7 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
     for (int i = 0; i < 9; ++i) P.tap_list[i] = i;
     P.num_kblocks = ktot / 64;
     const int m_tiles = static_cast<int>((P.pixels + BM - 1) / BM);
-    const int bn = pick_bn(s.cin, m_tiles);
+    const int bn = pick_bn(s.cin, m_tiles, !is_plain_gemm(s, false));
     P.n_tiles = s.cin / bn;
     if (bn >= 128 && cta2_enabled()) return launch_cta2(wt, ktot, s.cin, bn, P, m_tiles, st);
     if (int rc = make_tmap_bf16_2d(&tm, wt, ktot, s.cin, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
@@ -882,7 +888,7 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
     Q.pixels = static_cast<long long>(s.n) * Q.hm * Q.wm;
     Q.num_kblocks = Q.ntaps_c * Q.cpb;
     const int m_tiles = static_cast<int>((Q.pixels + BM - 1) / BM);
-    const int bn = pick_bn(s.cin, m_tiles);
+    const int bn = pick_bn(s.cin, m_tiles, true);
     Q.n_tiles = s.cin / bn;
     if (bn >= 128 && cta2_enabled()) {
       if (int rc = launch_cta2(wt, ktot, s.cin, bn, Q, m_tiles, st)) return rc;
@@ -896,17 +902,33 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
 
 static int wgrad_bn(const ConvShape& s) { return s.cout % 256 == 0 ? 256 : (s.cout % 128 == 0 ? 128 : 64); }
 
+// Split-K factor of the wgrad GEMM (K = pixels).  The persistent CTAs walk tiles x splits work items in waves of
+// num_sms; one item costs its k-blocks plus an epilogue worth ~6 k-blocks (128 x BN fp32 partials), so the launch
+// costs about waves x (k-blocks per split + 6).  Picking the minimiser avoids the "one item too many" third wave the
+// old ceil(2 * sms / tiles) rule produced for the 3x3 layers (e.g. 9 tiles x 33 splits = 297 items on 148 SMs).
 int conv_wgrad_splits(const ConvShape& s) {
   const long long pixels = static_cast<long long>(s.n) * s.ho * s.wo;
   const int kblocks = static_cast<int>((pixels + 63) / 64);
   const int chunks = s.kh * s.kw * s.cin / 64;
   const int bn = wgrad_bn(s);
   const int tiles = ((chunks + 1) / 2) * (s.cout / bn);
-  int splits = (2 * num_sms() + tiles - 1) / tiles;
-  if (splits < 1) splits = 1;
-  const int max_splits = (kblocks + 7) / 8;             // at least 8 k-blocks per split
-  if (splits > max_splits) splits = max_splits < 1 ? 1 : max_splits;
-  return splits;
+  const int sms = num_sms();
+  int max_splits = (kblocks + 7) / 8;                   // at least 8 k-blocks per split
+  if (max_splits < 1) max_splits = 1;
+  int hi = (4 * sms + tiles - 1) / tiles;
+  if (hi > max_splits) hi = max_splits;
+  int best = 1;
+  long long best_cost = -1;
+  for (int sp = 1; sp <= hi; ++sp) {
+    const long long waves = (static_cast<long long>(tiles) * sp + sms - 1) / sms;
+    const long long per = (kblocks + sp - 1) / sp;
+    const long long cost = waves * (per + 6);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = sp;
+    }
+  }
+  return best;
 }
 
 size_t conv_wgrad_workspace_bytes(const ConvShape& s) {

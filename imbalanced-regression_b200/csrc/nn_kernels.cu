@@ -66,27 +66,43 @@ __device__ __forceinline__ void column_reduce_finish(float (&acc)[K][8], int cg,
   }
 }
 
-// Sum of slot `slot` of the per-CTA partials [nblocks][K][c] for channel ch, computed by a (32, 32) thread block:
-// the 32 warps stride over the CTAs (two independent loads in flight each), 32 lanes cover 32 consecutive channels
-// (coalesced 128-byte reads); valid in threads with threadIdx.y == 0 after the call.
-__device__ __forceinline__ double sum_partials(const float* __restrict__ partial, int nblocks, int K, int slot, int c,
-                                               int ch, double (*sh)[32]) {
-  double t0 = 0.0, t1 = 0.0;
+// Sums of two slots (s0, s1) of the per-CTA partials [nblocks][K][c] for channel ch, computed by a (32, 32) thread
+// block: the 32 warps stride over the CTAs, 32 lanes cover 32 consecutive channels (coalesced 128-byte reads), and
+// both slots are fetched in the same pass so that four independent loads are in flight per thread (these tiny
+// kernels sit on the critical path between two streaming kernels, 106 times per step: pure latency).
+// Valid in threads with threadIdx.y == 0 after the call.
+__device__ __forceinline__ void sum_partials2(const float* __restrict__ partial, int nblocks, int K, int s0, int s1,
+                                              int c, int ch, double (*sh)[32], double& r0, double& r1) {
+  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
   if (ch < c) {
     int b = threadIdx.y;
     for (; b + 32 < nblocks; b += 64) {
-      t0 += (double)partial[((size_t)b * K + slot) * c + ch];
-      t1 += (double)partial[((size_t)(b + 32) * K + slot) * c + ch];
+      const float x0 = partial[((size_t)b * K + s0) * c + ch];
+      const float y0 = partial[((size_t)b * K + s1) * c + ch];
+      const float x1 = partial[((size_t)(b + 32) * K + s0) * c + ch];
+      const float y1 = partial[((size_t)(b + 32) * K + s1) * c + ch];
+      a0 += (double)x0;
+      b0 += (double)y0;
+      a1 += (double)x1;
+      b1 += (double)y1;
     }
-    if (b < nblocks) t0 += (double)partial[((size_t)b * K + slot) * c + ch];
+    if (b < nblocks) {
+      a0 += (double)partial[((size_t)b * K + s0) * c + ch];
+      b0 += (double)partial[((size_t)b * K + s1) * c + ch];
+    }
   }
-  sh[threadIdx.y][threadIdx.x] = t0 + t1;
+  sh[threadIdx.y][threadIdx.x] = a0 + a1;
   __syncthreads();
-  double r = 0.0;
+  r0 = 0.0;
   if (threadIdx.y == 0)
-    for (int w = 0; w < 32; ++w) r += sh[w][threadIdx.x];
+    for (int w = 0; w < 32; ++w) r0 += sh[w][threadIdx.x];
   __syncthreads();
-  return r;
+  sh[threadIdx.y][threadIdx.x] = b0 + b1;
+  __syncthreads();
+  r1 = 0.0;
+  if (threadIdx.y == 0)
+    for (int w = 0; w < 32; ++w) r1 += sh[w][threadIdx.x];
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(256, 4)
@@ -129,8 +145,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblock
                                    float* __restrict__ scale, float* __restrict__ shift) {
   __shared__ double sh[32][32];
   const int i = blockIdx.x * 32 + threadIdx.x;
-  const double sx = sum_partials(partial, nblocks, 2, 0, c, i, sh);
-  const double sq = sum_partials(partial, nblocks, 2, 1, c, i, sh);
+  double sx, sq;
+  sum_partials2(partial, nblocks, 2, 0, 1, c, i, sh, sx, sq);
   if (threadIdx.y != 0 || i >= c) return;
   const double n = (double)rows;
   const double m = sx / n;
@@ -283,8 +299,8 @@ __global__ void bn_bwd_coeffs_kernel(const float* __restrict__ partial, int nblo
                                      float* __restrict__ grad_beta, float* __restrict__ coef /* [3][c] */) {
   __shared__ double sh[32][32];
   const int i = blockIdx.x * 32 + threadIdx.x;
-  const double db = sum_partials(partial, nblocks, K, 0, c, i, sh);
-  const double s1 = sum_partials(partial, nblocks, K, gslot, c, i, sh);
+  double db, s1;
+  sum_partials2(partial, nblocks, K, 0, gslot, c, i, sh, db, s1);
   if (threadIdx.y != 0 || i >= c) return;
   const double n = (double)rows, is = (double)invstd[i], ga = (double)gamma[i], mu = (double)mean[i];
   const double dg = is * (s1 - mu * db);          // sum dz * xhat from the raw moments
