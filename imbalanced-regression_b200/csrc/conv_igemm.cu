@@ -49,6 +49,8 @@ struct IgemmParams {
   int total_chunks;          // wgrad: kh*kw*cpb (64-row chunks of the K_total x Cout result)
   int m_tiles, n_tiles;      // tiles along GEMM M / N
   int num_tiles;             // m_tiles * n_tiles * splits (persistent CTAs walk them round-robin)
+  int a_mode;                // ATMA kernels: 1 = A is a plain [pixels][channels] matrix (tiled TMA), 2 = im2col TMA
+  int i2c_stride, i2c_lo;    // im2col: base pixel of GEMM row (y, x) = (y * i2c_stride + i2c_lo, x * i2c_stride + i2c_lo)
   int ldc;                   // output row stride in elements (Cout for fprop, Cin for dgrad, Cout for wgrad partials)
   void* out;                 // bf16 [pixels][ldc]   or   fp32 [splits][total_chunks*64][ldc]
 };
@@ -407,6 +409,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
         int split, m_tile, n_tile, kb_begin, nk;
         decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
         const int n0 = n_tile * BN;
+        int tile_w0 = 0, tile_h0 = 0, tile_n0 = 0;     // im2col base pixel of the tile's first GEMM row
+        if constexpr (ATMA && !WGRAD) {
+          if (P.a_mode == 2) {
+            const long long p0 = static_cast<long long>(m_tile) * BM;
+            const int hw = P.hm * P.wm;
+            tile_n0 = static_cast<int>(p0 / hw);
+            const int rem = static_cast<int>(p0 - static_cast<long long>(tile_n0) * hw);
+            const int y0 = rem / P.wm, x0 = rem - y0 * P.wm;
+            tile_w0 = x0 * P.i2c_stride + P.i2c_lo;
+            tile_h0 = y0 * P.i2c_stride + P.i2c_lo;
+          }
+        }
         for (int it = 0; it < nk; ++it, ++cnt) {
           const int s = static_cast<int>(cnt % nstages);
           const uint32_t ph = (cnt / nstages) & 1;
@@ -422,15 +436,44 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           }
           if constexpr (ATMA) {
             if constexpr (!WGRAD) {
-              // A tile: 128 pixel rows x 64 channels of the [pixels][channels] matrix (rows past the end: zeros)
+              // A tile: 128 pixel rows x 64 channels (rows past the end / padding: zeros)
               mbar_arrive_expect_tx(full_bar(s), C::kBBytes + C::kABytes);
-              tma_load_2d(a_addr(s), &tmap_a, full_bar(s), kb * BK, m_tile * BM);
+              if (P.a_mode == 1) {
+                tma_load_2d(a_addr(s), &tmap_a, full_bar(s), kb * BK, m_tile * BM);
+              } else {
+                const int tc = kb / P.cpb;
+                const int tp = P.tap_list[tc];
+                int r = tp / P.kw, sx = tp - r * P.kw;
+                if (P.transposed) {               // dgrad: dy pixel (y + pad - r, x + pad - s) = base + (k-1-r, k-1-s)
+                  r = P.kh - 1 - r;
+                  sx = P.kw - 1 - sx;
+                }
+                tma_load_im2col_4d(a_addr(s), &tmap_a, full_bar(s), (kb - tc * P.cpb) * BK, tile_w0, tile_h0, tile_n0,
+                                   static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+              }
             } else {
               // A tile: 64 pixels x (up to) two 64-channel chunks, MN-major like the dY tile
               const int nchunks = min(2, P.total_chunks - 2 * m_tile);
               mbar_arrive_expect_tx(full_bar(s), C::kBBytes + nchunks * 8192);
-              for (int i = 0; i < nchunks; ++i)
-                tma_load_2d(a_addr(s) + i * 8192, &tmap_a, full_bar(s), (2 * m_tile + i) * 64, kb * 64);
+              if (P.a_mode == 1) {
+                for (int i = 0; i < nchunks; ++i)
+                  tma_load_2d(a_addr(s) + i * 8192, &tmap_a, full_bar(s), (2 * m_tile + i) * 64, kb * 64);
+              } else {
+                // the k-block's first pixel -> base pixel; every chunk = (filter tap, 64 channels)
+                const long long p0 = static_cast<long long>(kb) * 64;
+                const int hw = P.hm * P.wm;
+                const int n0i = static_cast<int>(p0 / hw);
+                const int rem = static_cast<int>(p0 - static_cast<long long>(n0i) * hw);
+                const int y0 = rem / P.wm, x0 = rem - y0 * P.wm;
+                for (int i = 0; i < nchunks; ++i) {
+                  const int gchunk = 2 * m_tile + i;
+                  const int tap = gchunk / P.cpb;
+                  const int r = tap / P.kw, sx = tap - r * P.kw;
+                  tma_load_im2col_4d(a_addr(s) + i * 8192, &tmap_a, full_bar(s), (gchunk - tap * P.cpb) * 64,
+                                     x0 * P.i2c_stride + P.i2c_lo, y0 * P.i2c_stride + P.i2c_lo, n0i,
+                                     static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+                }
+              }
             }
           } else {
             mbar_arrive_expect_tx(full_bar(s), C::kBBytes);
@@ -654,6 +697,47 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t
   return DIRB200_OK;
 }
 
+// im2col-mode map of an NHWC bf16 tensor: 64 channels x `pixels_per_col` output positions per load, 128-byte swizzle.
+// lower / upper: offsets of the base-pixel bounding box from 0 / from the extent (same for W and H); trav: traversal
+// stride (= conv stride).  Parameters as cutlass/conv/collective/detail.hpp derives them (fprop: lower = -pad,
+// upper = pad - (k - 1); dgrad: lower = pad - (k - 1), upper = lower + extent(dx) - extent(dy)).
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+int make_tmap_im2col_bf16(CUtensorMap* tm, const void* ptr, int c, int w, int h, int n, int lower_w, int lower_h,
+                          int upper_w, int upper_h, int trav, int pixels_per_col) {
+  static EncodeIm2colFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(p);
+  }
+  if (!fn) {
+    set_error("cuTensorMapEncodeIm2col entry point not available");
+    return DIRB200_ERR_CUDA;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  int lower[2] = {lower_w, lower_h}, upper[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1, (cuuint32_t)trav, (cuuint32_t)trav, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower, upper, 64,
+                  (cuuint32_t)pixels_per_col, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeIm2col failed (%d) c=%d w=%d h=%d n=%d lower=%d,%d upper=%d,%d stride=%d", (int)r, c, w, h,
+              n, lower_w, lower_h, upper_w, upper_h, trav);
+    return DIRB200_ERR_CUDA;
+  }
+  // same driver workaround as cute's make_im2col_tma_copy_desc (drivers <= 13.1, tensors < 128 KiB)
+  int drv = 0;
+  if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 && (size_t)c * w * h * n * 2 < 131072)
+    reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  return DIRB200_OK;
+}
+
 template <int BN, bool WGRAD, bool STEM, bool BSTAT, bool ATMA = false>
 static int launch_igemm_impl(const CUtensorMap& tm, const CUtensorMap& tma, const IgemmParams& Q, cudaStream_t st) {
   using C = Cfg<BN, !WGRAD>;
@@ -789,6 +873,15 @@ static bool atma_enabled() {
 static bool is_plain_gemm(const ConvShape& s, bool stem) {
   return !stem && s.kh == 1 && s.kw == 1 && s.stride == 1 && s.pad == 0 && atma_enabled();
 }
+// DIRB200_IM2COL=1: every other non-stem conv (3x3, strided) takes its A operand through im2col-mode TMA
+// (fprop, stride-1 dgrad, wgrad); the stride-2 dgrad parity classes and the stem keep the cp.async gather.
+static bool im2col_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DIRB200_IM2COL");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on && atma_enabled();
+}
 
 // CTA-pair launch of an fprop / dgrad GEMM: B = wmat [n_dim][ktot] (K-major), each CTA TMA-loads bn/2 of its rows.
 static int launch_cta2(const __nv_bfloat16* wmat, int ktot, int n_dim, int bn, const IgemmParams& P, int m_tiles,
@@ -827,6 +920,15 @@ int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y,
     CUtensorMap ta;     // x as [pixels][cin]
     if (int rc = make_tmap_bf16_2d(&ta, x, s.cin, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cin) * 2, BM))
       return rc;
+    P.a_mode = 1;
+    return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st, &ta);
+  }
+  if (im2col_enabled()) {
+    CUtensorMap ta;     // x [n,h,w,cin], base pixel (ho*stride - pad, wo*stride - pad)
+    if (int rc = make_tmap_im2col_bf16(&ta, x, s.cin, s.w, s.h, s.n, -s.pad, -s.pad, s.pad - (s.kw - 1),
+                                       s.pad - (s.kh - 1), s.stride, BM))
+      return rc;
+    P.a_mode = 2; P.i2c_stride = s.stride; P.i2c_lo = -s.pad;
     return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st, &ta);
   }
   return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st);
@@ -859,6 +961,15 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
       CUtensorMap ta;   // dy as [pixels][cout]
       if (int rc = make_tmap_bf16_2d(&ta, dy, s.cout, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cout) * 2, BM))
         return rc;
+      P.a_mode = 1;
+      return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st, &ta);
+    }
+    if (im2col_enabled() && s.kh == s.kw) {
+      CUtensorMap ta;   // dy [n,ho,wo,cout], base pixel (y + pad - (k-1), x + pad - (k-1)), tap offsets reversed
+      const int lo = s.pad - (s.kh - 1);
+      if (int rc = make_tmap_im2col_bf16(&ta, dy, s.cout, s.wo, s.ho, s.n, lo, lo, lo + s.w - s.wo, lo + s.h - s.ho, 1, BM))
+        return rc;
+      P.a_mode = 2; P.i2c_stride = 1; P.i2c_lo = lo;
       return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st, &ta);
     }
     return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st);
@@ -963,6 +1074,15 @@ int conv_wgrad_partials(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
     CUtensorMap ta;     // x as [pixels][cin], 64-pixel x 64-channel boxes
     if (int rc = make_tmap_bf16_2d(&ta, x, s.cin, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cin) * 2, 64))
       return rc;
+    P.a_mode = 1;
+    return DISPATCH_BN(bn, true, false, tm, P, m_tiles, splits, st, &ta);
+  }
+  if (im2col_enabled()) {
+    CUtensorMap ta;     // x [n,h,w,cin]: 64 output positions x 64 channels per load
+    if (int rc = make_tmap_im2col_bf16(&ta, x, s.cin, s.w, s.h, s.n, -s.pad, -s.pad, s.pad - (s.kw - 1),
+                                       s.pad - (s.kh - 1), s.stride, 64))
+      return rc;
+    P.a_mode = 2; P.i2c_stride = s.stride; P.i2c_lo = -s.pad;
     return DISPATCH_BN(bn, true, false, tm, P, m_tiles, splits, st, &ta);
   }
   return DISPATCH_BN(bn, true, false, tm, P, m_tiles, splits, st);

@@ -75,6 +75,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tma
       : "memory");
 }
 
+// im2col-mode TMA load of an NHWC tensor (rank 4: C, W, H, N): `pixelsPerColumn` output positions starting at the
+// base pixel (w, h, n) -- walking the descriptor's bounding box with its traversal strides -- each displaced by the
+// filter-tap offset (off_w, off_h); `channelsPerPixel` channels from c; out-of-image elements arrive as zeros.
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c, int w,
+                                                   int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t holder_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder_smem), "r"(ncols)
