@@ -403,7 +403,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
         }
         tma_load_2d(bstat_base + kb * C::kBBytes, &tmap_b, bstat_bar, kcoord * BK, 0);
       }
-    } else if (lane == 0) {
+    } else if (!BSTAT) {
+      // the whole warp walks the ring (converged); one elected lane issues
       uint32_t cnt = 0;
       for (int t = tile_start; t < P.num_tiles; t += tile_stride) {
         int split, m_tile, n_tile, kb_begin, nk;
@@ -426,70 +427,73 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           const uint32_t ph = (cnt / nstages) & 1;
           mbar_wait(empty_bar(s), ph ^ 1u);
           const int kb = kb_begin + it;
-          if constexpr (CTA2) {
-            // this CTA's half of the B tile; both halves are accounted on the leader's barrier
-            if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * C::kBBytes);
-            const int tc = kb / P.cpb;
-            const int kcoord = P.tap_list[tc] * P.cpb + (kb - tc * P.cpb);
-            tma_load_2d_cta2(b_addr(s), &tmap_b, full_bar(s), kcoord * BK, n0 + static_cast<int>(rank) * C::kBRows);
-            continue;
-          }
-          if constexpr (ATMA) {
-            if constexpr (!WGRAD) {
-              // A tile: 128 pixel rows x 64 channels (rows past the end / padding: zeros)
-              mbar_arrive_expect_tx(full_bar(s), C::kBBytes + C::kABytes);
-              if (P.a_mode == 1) {
-                tma_load_2d(a_addr(s), &tmap_a, full_bar(s), kb * BK, m_tile * BM);
-              } else {
-                const int tc = kb / P.cpb;
-                const int tp = P.tap_list[tc];
-                int r = tp / P.kw, sx = tp - r * P.kw;
-                if (P.transposed) {               // dgrad: dy pixel (y + pad - r, x + pad - s) = base + (k-1-r, k-1-s)
-                  r = P.kh - 1 - r;
-                  sx = P.kw - 1 - sx;
-                }
-                tma_load_im2col_4d(a_addr(s), &tmap_a, full_bar(s), (kb - tc * P.cpb) * BK, tile_w0, tile_h0, tile_n0,
-                                   static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
-              }
-            } else {
-              // A tile: 64 pixels x (up to) two 64-channel chunks, MN-major like the dY tile
-              const int nchunks = min(2, P.total_chunks - 2 * m_tile);
-              mbar_arrive_expect_tx(full_bar(s), C::kBBytes + nchunks * 8192);
-              if (P.a_mode == 1) {
-                for (int i = 0; i < nchunks; ++i)
-                  tma_load_2d(a_addr(s) + i * 8192, &tmap_a, full_bar(s), (2 * m_tile + i) * 64, kb * 64);
-              } else {
-                // the k-block's first pixel -> base pixel; every chunk = (filter tap, 64 channels)
-                const long long p0 = static_cast<long long>(kb) * 64;
-                const int hw = P.hm * P.wm;
-                const int n0i = static_cast<int>(p0 / hw);
-                const int rem = static_cast<int>(p0 - static_cast<long long>(n0i) * hw);
-                const int y0 = rem / P.wm, x0 = rem - y0 * P.wm;
-                for (int i = 0; i < nchunks; ++i) {
-                  const int gchunk = 2 * m_tile + i;
-                  const int tap = gchunk / P.cpb;
-                  const int r = tap / P.kw, sx = tap - r * P.kw;
-                  tma_load_im2col_4d(a_addr(s) + i * 8192, &tmap_a, full_bar(s), (gchunk - tap * P.cpb) * 64,
-                                     x0 * P.i2c_stride + P.i2c_lo, y0 * P.i2c_stride + P.i2c_lo, n0i,
-                                     static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
-                }
-              }
-            }
-          } else {
-            mbar_arrive_expect_tx(full_bar(s), C::kBBytes);
-          }
-          if constexpr (!WGRAD) {
-            int kcoord = kb;
-            if constexpr (!STEM) {
+          if (elect_one()) {
+            if constexpr (CTA2) {
+              // this CTA's half of the B tile; both halves are accounted on the leader's barrier
+              if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * C::kBBytes);
               const int tc = kb / P.cpb;
-              kcoord = P.tap_list[tc] * P.cpb + (kb - tc * P.cpb);
-            }
-            tma_load_2d(b_addr(s), &tmap_b, full_bar(s), kcoord * BK, n0);
-          } else {
+              const int kcoord = P.tap_list[tc] * P.cpb + (kb - tc * P.cpb);
+              tma_load_2d_cta2(b_addr(s), &tmap_b, full_bar(s), kcoord * BK, n0 + static_cast<int>(rank) * C::kBRows);
+            } else {
+              if constexpr (ATMA) {
+                if constexpr (!WGRAD) {
+                  // A tile: 128 pixel rows x 64 channels (rows past the end / padding: zeros)
+                  mbar_arrive_expect_tx(full_bar(s), C::kBBytes + C::kABytes);
+                  if (P.a_mode == 1) {
+                    tma_load_2d(a_addr(s), &tmap_a, full_bar(s), kb * BK, m_tile * BM);
+                  } else {
+                    const int tc = kb / P.cpb;
+                    const int tp = P.tap_list[tc];
+                    int r = tp / P.kw, sx = tp - r * P.kw;
+                    if (P.transposed) {               // dgrad: dy pixel (y + pad - r, x + pad - s) = base + (k-1-r, k-1-s)
+                      r = P.kh - 1 - r;
+                      sx = P.kw - 1 - sx;
+                    }
+                    tma_load_im2col_4d(a_addr(s), &tmap_a, full_bar(s), (kb - tc * P.cpb) * BK, tile_w0, tile_h0, tile_n0,
+                                       static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+                  }
+                } else {
+                  // A tile: 64 pixels x (up to) two 64-channel chunks, MN-major like the dY tile
+                  const int nchunks = min(2, P.total_chunks - 2 * m_tile);
+                  mbar_arrive_expect_tx(full_bar(s), C::kBBytes + nchunks * 8192);
+                  if (P.a_mode == 1) {
+                    for (int i = 0; i < nchunks; ++i)
+                      tma_load_2d(a_addr(s) + i * 8192, &tmap_a, full_bar(s), (2 * m_tile + i) * 64, kb * 64);
+                  } else {
+                    // the k-block's first pixel -> base pixel; every chunk = (filter tap, 64 channels)
+                    const long long p0 = static_cast<long long>(kb) * 64;
+                    const int hw = P.hm * P.wm;
+                    const int n0i = static_cast<int>(p0 / hw);
+                    const int rem = static_cast<int>(p0 - static_cast<long long>(n0i) * hw);
+                    const int y0 = rem / P.wm, x0 = rem - y0 * P.wm;
+                    for (int i = 0; i < nchunks; ++i) {
+                      const int gchunk = 2 * m_tile + i;
+                      const int tap = gchunk / P.cpb;
+                      const int r = tap / P.kw, sx = tap - r * P.kw;
+                      tma_load_im2col_4d(a_addr(s) + i * 8192, &tmap_a, full_bar(s), (gchunk - tap * P.cpb) * 64,
+                                         x0 * P.i2c_stride + P.i2c_lo, y0 * P.i2c_stride + P.i2c_lo, n0i,
+                                         static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+                    }
+                  }
+                }
+              } else {
+                mbar_arrive_expect_tx(full_bar(s), C::kBBytes);
+              }
+              if constexpr (!WGRAD) {
+                int kcoord = kb;
+                if constexpr (!STEM) {
+                  const int tc = kb / P.cpb;
+                  kcoord = P.tap_list[tc] * P.cpb + (kb - tc * P.cpb);
+                }
+                tma_load_2d(b_addr(s), &tmap_b, full_bar(s), kcoord * BK, n0);
+              } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(b_addr(s) + i * 8192, &tmap_b, full_bar(s), n0 + 64 * i, kb * 64);
+                for (int i = 0; i < BN / 64; ++i)
+                  tma_load_2d(b_addr(s) + i * 8192, &tmap_b, full_bar(s), n0 + 64 * i, kb * 64);
+              }
+            }
           }
+          __syncwarp();
         }
       }
     }
@@ -509,7 +513,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           }
         }
       }
-    } else if (lane == 0) {
+    } else {
+      // the whole warp walks the ring (converged: operands stay in uniform registers); one elected lane issues
       constexpr uint32_t idesc = make_idesc(CTA2 ? 2 * BM : BM, BN, WGRAD ? 1 : 0, WGRAD ? 1 : 0);
       uint32_t cnt = 0, tcount = 0;
       if constexpr (BSTAT) mbar_wait(bstat_bar, 0);
@@ -531,20 +536,26 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
               make_smem_desc(BSTAT ? bstat_base + static_cast<uint32_t>(kb_begin + it) * C::kBBytes : b_addr(s),
                              WGRAD ? 8192u : 16u, 1024u);
           constexpr uint32_t kadv = WGRAD ? (2048u >> 4) : (32u >> 4);   // one UMMA_K (=16) step, in 16-byte units
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            if constexpr (CTA2)
-              umma_bf16_cta2(tmem_d, adesc + static_cast<uint64_t>(k * kadv), bdesc + static_cast<uint64_t>(k * kadv),
-                             idesc, (it > 0 || k > 0) ? 1u : 0u);
-            else
-              umma_bf16(tmem_d, adesc + static_cast<uint64_t>(k * kadv), bdesc + static_cast<uint64_t>(k * kadv), idesc,
-                        (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              if constexpr (CTA2)
+                umma_bf16_cta2(tmem_d, adesc + static_cast<uint64_t>(k * kadv), bdesc + static_cast<uint64_t>(k * kadv),
+                               idesc, (it > 0 || k > 0) ? 1u : 0u);
+              else
+                umma_bf16(tmem_d, adesc + static_cast<uint64_t>(k * kadv), bdesc + static_cast<uint64_t>(k * kadv), idesc,
+                          (it > 0 || k > 0) ? 1u : 0u);
+            }
+            if constexpr (CTA2) umma_commit_cta2(empty_bar(s));     // frees the stage in both CTAs
+            else umma_commit(empty_bar(s));
           }
-          if constexpr (CTA2) umma_commit_cta2(empty_bar(s));     // frees the stage in both CTAs
-          else umma_commit(empty_bar(s));
+          __syncwarp();
         }
-        if constexpr (CTA2) umma_commit_cta2(tfull_bar(acc));     // both CTAs' epilogues may drain their halves
-        else umma_commit(tfull_bar(acc));
+        if (elect_one()) {
+          if constexpr (CTA2) umma_commit_cta2(tfull_bar(acc));     // both CTAs' epilogues may drain their halves
+          else umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
       }
     }
     __syncwarp();

@@ -50,6 +50,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// One lane of the (fully converged) warp: the single-thread issue of TMA / tcgen05 instructions.  Issuing from
+// `if (elect_one())` in a CONVERGED warp -- rather than from a divergent `if (lane == 0)` region -- lets the compiler
+// keep descriptors / coordinates in uniform registers; in a divergent region every UTCHMMA / UTMALDG is wrapped in
+// an ELECT + R2UR.BROADCAST "uniformisation" loop (~15 instructions per MMA), which bounded the whole GEMM at
+// ~0.6 us per k-block whatever the tile shape.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- cp.async
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
