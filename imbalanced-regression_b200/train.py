@@ -181,8 +181,8 @@ def shot_metrics(preds, labels, train_labels, many_shot_thr=100, low_shot_thr=20
     with np.errstate(divide='ignore', invalid='ignore'):
         for row, name in enumerate(('overall', 'many', 'median', 'low')):
             cnt = o[row, 0]
-            shot_dict[name]['mse'] = o[row, 1] / cnt
-            shot_dict[name]['l1'] = o[row, 2] / cnt
+            shot_dict[name]['mse'] = float(o[row, 1] / cnt)          # plain floats: they end up in checkpoints
+            shot_dict[name]['l1'] = float(o[row, 2] / cnt)
             shot_dict[name]['gmean'] = float(np.exp(o[row, 3] / cnt))
     return shot_dict
 
