@@ -36,8 +36,18 @@ def launches(src, dst):
             return 0.0
         v, u = d[k]
         return v * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1, "Gbyte": 1e3}[u]
+    note = None
     idx = [i for i, r in enumerate(rows) if r["name"] == "adam_kernel"]
-    step = rows[idx[0] + 1:idx[1] + 1] if len(idx) > 1 else rows
+    pidx = [i for i, r in enumerate(rows) if r["name"].startswith("prep_weights_all_kernel")]
+    if len(idx) > 1:                       # one step = (adam, next adam]
+        step = rows[idx[0] + 1:idx[1] + 1]
+    elif len(pidx) > 1:                    # short capture: one step = [weight prep, next weight prep)
+        step = rows[pidx[0]:pidx[1]]
+        note = ("NOTE: the capture held one complete step only, the FIRST step after the model was built -- it carries "
+                "~160 one-time `FillFunctor` launches (lazily created gradient views); a steady-state step has 538 "
+                "launches (bench.py `gpu_launches_per_step`).  The conv / BN launches are those of every step.")
+    else:
+        step = rows
     tot = collections.defaultdict(lambda: [0, 0.0, 0.0])
     for d in step:
         a = tot[d["name"]]
@@ -47,7 +57,7 @@ def launches(src, dst):
     total = sum(a[1] for a in tot.values())
     out = [f"# ncu launch list of ONE training step ({len(step)} launches, batch 256, 1xB200)", "",
            f"source: `{src}` (`ncu --metrics gpu__time_duration.sum[,dram__bytes_*] --clock-control none`; "
-           "per-launch times are cold-cache and serialised: compare SHARES)", "",
+           "per-launch times are cold-cache and serialised: compare SHARES)", ""] + ([note, ""] if note else []) + [
            "| kernel | launches | ms | share | DRAM GB |", "|---|---:|---:|---:|---:|"]
     for k, a in sorted(tot.items(), key=lambda kv: -kv[1][1]):
         out.append(f"| `{k}` | {a[0]} | {a[1] / 1000:.3f} | {100 * a[1] / total:.1f}% | {a[2] / 1000:.2f} |")
