@@ -44,3 +44,40 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(_lib.Dirb200Error):
         weighted_l1_loss(torch.zeros(4, 1), torch.zeros(4, 1))
+
+
+def test_wgrad_split_search_never_leaves_a_straggler_wave():
+    """Host-side scheduling of the wgrad split-K GEMM (csrc/conv_igemm.cu: conv_wgrad_splits), observable without a
+    GPU through dirb200_conv_wgrad_workspace_bytes = splits * K_total * Cout * 4 (num_sms() falls back to 148 when no
+    device is present).  For every conv of the batch-256 ResNet-50: the work items (tiles x splits) must fill the
+    persistent CTAs' waves to >= 85 % -- the earlier ceil(2*SMs/tiles) rule left e.g. 297 items (a third wave for one
+    item) on the 3x3 layers -- and every split keeps >= 8 k-blocks."""
+    import _lib, _convlib  # noqa: F401
+    sms = 148
+    convs = []          # (h, cin, cout, k, stride, pad)
+    h, inpl = 56, 64
+    for li, nb in enumerate((3, 4, 6, 3)):
+        pl = 64 << li
+        for b in range(nb):
+            s = 2 if (b == 0 and li > 0) else 1
+            convs += [(h, inpl, pl, 1, 1, 0), (h, pl, pl, 3, s, 1), (h // s, pl, pl * 4, 1, 1, 0)]
+            if b == 0:
+                convs.append((h, inpl, pl * 4, 1, s, 0))
+            inpl, h = pl * 4, h // s
+    assert len(convs) == 52
+    worst = 1.0
+    for (hh, cin, cout, k, s, p) in convs:
+        nbytes = _lib.raw("dirb200_conv_wgrad_workspace_bytes")(256, hh, hh, cin, cout, k, k, s, p, 0)
+        splits = nbytes // (k * k * cin * cout * 4)
+        assert splits >= 1 and nbytes == splits * k * k * cin * cout * 4
+        ho = (hh + 2 * p - k) // s + 1
+        kblocks = (256 * ho * ho + 63) // 64
+        bn = 256 if cout % 256 == 0 else (128 if cout % 128 == 0 else 64)
+        tiles = ((k * k * cin // 64 + 1) // 2) * (cout // bn)
+        items = tiles * splits
+        waves = -(-items // sms)
+        fill = items / (waves * sms)
+        worst = min(worst, fill)
+        assert fill >= 0.85, (hh, cin, cout, k, s, splits, items)
+        assert kblocks // splits >= 8
+    assert worst >= 0.85
