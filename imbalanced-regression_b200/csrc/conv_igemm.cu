@@ -167,7 +167,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
   using C = Cfg<BN, !WGRAD, CTA2>;
   static_assert(!(BSTAT && WGRAD), "B-stationary mode is for fprop/dgrad");
   static_assert(!CTA2 || (!WGRAD && !STEM && !BSTAT && BN >= 128), "CTA pairs: fprop/dgrad with BN >= 128 only");
-  static_assert(!ATMA || (!STEM && !BSTAT && !CTA2), "TMA-fed A operand: plain 1x1 stride-1 GEMMs, one CTA");
+  static_assert(!ATMA || (!STEM && !BSTAT), "TMA-fed A operand: not for the stem / B-stationary forms");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + C::kBarOffset;
@@ -211,6 +211,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
       for (int s = 0; s < C::kStages; ++s) {
         // gather threads + the TMA thread's expect_tx arrival; pair leader: + the peer's relayed arrival;
         // pair peer: gather threads only (its B bytes are counted on the leader's barrier)
+        // (pairs with TMA-fed A: everything is counted on the leader's barrier by its one expect_tx arrival)
         mbar_init(full_bar(s), ATMA ? 1
                                     : (CTA2 ? (rank == 0 ? kProducerThreads + 2 : kProducerThreads)
                                             : kProducerThreads + (BSTAT ? 0 : 1)));
@@ -430,8 +431,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           if (elect_one()) {
             if constexpr (CTA2) {
               // this CTA's half of the B tile; both halves are accounted on the leader's barrier
-              if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * C::kBBytes);
+              if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * (C::kBBytes + (ATMA ? C::kABytes : 0)));
               const int tc = kb / P.cpb;
+              if constexpr (ATMA) {
+                // ... and this CTA's 128 A rows (UNVERIFIED on hardware: enabled by DIRB200_CTA2=2 only)
+                if (P.a_mode == 1) {
+                  tma_load_2d_cta2(a_addr(s), &tmap_a, full_bar(s), kb * BK, m_tile * BM);
+                } else {
+                  const int tp = P.tap_list[tc];
+                  int r = tp / P.kw, sx = tp - r * P.kw;
+                  if (P.transposed) {
+                    r = P.kh - 1 - r;
+                    sx = P.kw - 1 - sx;
+                  }
+                  tma_load_im2col_4d_cta2(a_addr(s), &tmap_a, full_bar(s), (kb - tc * P.cpb) * BK, tile_w0, tile_h0,
+                                          tile_n0, static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+                }
+              }
               const int kcoord = P.tap_list[tc] * P.cpb + (kb - tc * P.cpb);
               tma_load_2d_cta2(b_addr(s), &tmap_b, full_bar(s), kcoord * BK, n0 + static_cast<int>(rank) * C::kBRows);
             } else {
@@ -501,7 +517,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
     // ============================== MMA issuer ==============================
     if (CTA2 && rank != 0) {
       // pair peer: no MMAs to issue -- relay "my gathered A rows of this stage have landed" to the leader's barrier
-      if (lane == 0) {
+      // (nothing to relay when the A rows come by TMA: their bytes are counted on the leader's barrier directly)
+      if (lane == 0 && !ATMA) {
         uint32_t cnt = 0;
         for (int t = tile_start; t < P.num_tiles; t += tile_stride) {
           int split, m_tile, n_tile, kb_begin, nk;
@@ -765,10 +782,10 @@ static int launch_igemm_impl(const CUtensorMap& tm, const CUtensorMap& tma, cons
 }
 
 // CTA-pair variant: (2,1,1) clusters, one pair per two SMs; Q.m_tiles / Q.num_tiles count 256-row pair tiles.
-template <int BN>
-static int launch_igemm_cta2(const CUtensorMap& tm, const IgemmParams& Q, cudaStream_t st) {
+template <int BN, bool ATMA = false>
+static int launch_igemm_cta2(const CUtensorMap& tm, const CUtensorMap& tma, const IgemmParams& Q, cudaStream_t st) {
   using C = Cfg<BN, true, true>;
-  auto kern = igemm_kernel<BN, false, false, false, true>;
+  auto kern = igemm_kernel<BN, false, false, false, true, ATMA>;
   static bool configured = false;
   if (!configured) {
     DIRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -800,19 +817,23 @@ static int launch_igemm_cta2(const CUtensorMap& tm, const IgemmParams& Q, cudaSt
   }
   const int pairs = Q.num_tiles < max_pairs ? Q.num_tiles : max_pairs;
   cfg.gridDim = dim3(2 * pairs, 1, 1);
-  DIRB_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, tm, Q));
+  DIRB_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, tma, Q));
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
 
-// DIRB200_CTA2=1 routes the fprop / dgrad GEMMs with BN >= 128 through CTA pairs (tcgen05 cta_group::2).
-static bool cta2_enabled() {
-  static const bool on = [] {
+// DIRB200_CTA2=1 routes the fprop / dgrad GEMMs with BN >= 128 through CTA pairs (tcgen05 cta_group::2), A operand by
+// the cp.async gather (validated on B200).  DIRB200_CTA2=2 additionally feeds the pairs' A operand by TMA wherever
+// the single-CTA path would (tiled for plain GEMMs, im2col with DIRB200_IM2COL=1) -- the canonical 2-SM pipeline;
+// written after the round's GPU budget was spent: compiles, NOT yet run on hardware, never selected by default.
+static int cta2_mode() {
+  static const int mode = [] {
     const char* e = getenv("DIRB200_CTA2");
-    return e != nullptr && e[0] == '1';
+    return (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
   }();
-  return on;
+  return mode;
 }
+static bool cta2_enabled() { return cta2_mode() != 0; }
 
 // tma != nullptr: the A operand is a plain [pixels][channels] matrix (1x1 stride-1 conv) and is loaded by TMA too
 template <int BN, bool WGRAD, bool STEM>
@@ -896,13 +917,14 @@ static bool im2col_enabled() {
 
 // CTA-pair launch of an fprop / dgrad GEMM: B = wmat [n_dim][ktot] (K-major), each CTA TMA-loads bn/2 of its rows.
 static int launch_cta2(const __nv_bfloat16* wmat, int ktot, int n_dim, int bn, const IgemmParams& P, int m_tiles,
-                       cudaStream_t st) {
+                       cudaStream_t st, const CUtensorMap* tma = nullptr) {
   CUtensorMap tm;
   if (int rc = make_tmap_bf16_2d(&tm, wmat, ktot, n_dim, static_cast<uint64_t>(ktot) * 2, bn / 2)) return rc;
   IgemmParams Q = P;
   Q.m_tiles = (m_tiles + 1) / 2;                 // 256-row pair tiles
   Q.num_tiles = Q.m_tiles * P.n_tiles;
-  return bn == 256 ? launch_igemm_cta2<256>(tm, Q, st) : launch_igemm_cta2<128>(tm, Q, st);
+  if (tma) return bn == 256 ? launch_igemm_cta2<256, true>(tm, *tma, Q, st) : launch_igemm_cta2<128, true>(tm, *tma, Q, st);
+  return bn == 256 ? launch_igemm_cta2<256>(tm, tm, Q, st) : launch_igemm_cta2<128>(tm, tm, Q, st);
 }
 
 // Y[n,ho,wo,cout] = conv(X[n,h,w,cin], W[cout][kh][kw][cin])
@@ -924,7 +946,23 @@ int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y,
   const int bn = pick_bn(s.cout, m_tiles, !is_plain_gemm(s, stem));
   P.n_tiles = s.cout / bn;
   CUtensorMap tm;
-  if (!stem && bn >= 128 && cta2_enabled()) return launch_cta2(w, ktot, s.cout, bn, P, m_tiles, st);
+  if (!stem && bn >= 128 && cta2_enabled()) {
+    if (cta2_mode() == 2 && (is_plain_gemm(s, stem) || im2col_enabled())) {      // pairs with a TMA-fed A operand
+      CUtensorMap ta;
+      if (is_plain_gemm(s, stem)) {
+        if (int rc = make_tmap_bf16_2d(&ta, x, s.cin, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cin) * 2, BM))
+          return rc;
+        P.a_mode = 1;
+      } else {
+        if (int rc = make_tmap_im2col_bf16(&ta, x, s.cin, s.w, s.h, s.n, -s.pad, -s.pad, s.pad - (s.kw - 1),
+                                           s.pad - (s.kh - 1), s.stride, BM))
+          return rc;
+        P.a_mode = 2; P.i2c_stride = s.stride; P.i2c_lo = -s.pad;
+      }
+      return launch_cta2(w, ktot, s.cout, bn, P, m_tiles, st, &ta);
+    }
+    return launch_cta2(w, ktot, s.cout, bn, P, m_tiles, st);
+  }
   if (int rc = make_tmap_bf16_2d(&tm, w, ktot, s.cout, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
   if (stem) return DISPATCH_BN(bn, false, true, tm, P, m_tiles, 1, st);
   if (is_plain_gemm(s, stem)) {
@@ -966,7 +1004,23 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
     const int m_tiles = static_cast<int>((P.pixels + BM - 1) / BM);
     const int bn = pick_bn(s.cin, m_tiles, !is_plain_gemm(s, false));
     P.n_tiles = s.cin / bn;
-    if (bn >= 128 && cta2_enabled()) return launch_cta2(wt, ktot, s.cin, bn, P, m_tiles, st);
+    if (bn >= 128 && cta2_enabled()) {
+      if (cta2_mode() == 2 && (is_plain_gemm(s, false) || (im2col_enabled() && s.kh == s.kw))) {
+        CUtensorMap ta;
+        if (is_plain_gemm(s, false)) {
+          if (int rc = make_tmap_bf16_2d(&ta, dy, s.cout, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cout) * 2, BM))
+            return rc;
+          P.a_mode = 1;
+        } else {
+          const int lo = s.pad - (s.kh - 1);
+          if (int rc = make_tmap_im2col_bf16(&ta, dy, s.cout, s.wo, s.ho, s.n, lo, lo, lo + s.w - s.wo, lo + s.h - s.ho, 1, BM))
+            return rc;
+          P.a_mode = 2; P.i2c_stride = 1; P.i2c_lo = lo;
+        }
+        return launch_cta2(wt, ktot, s.cin, bn, P, m_tiles, st, &ta);
+      }
+      return launch_cta2(wt, ktot, s.cin, bn, P, m_tiles, st);
+    }
     if (int rc = make_tmap_bf16_2d(&tm, wt, ktot, s.cin, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
     if (is_plain_gemm(s, false)) {
       CUtensorMap ta;   // dy as [pixels][cout]

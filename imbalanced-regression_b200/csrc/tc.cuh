@@ -167,6 +167,15 @@ __device__ __forceinline__ void tma_load_2d_cta2(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(tmap), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
 }
+// im2col-mode variant of the above (cute::SM100_TMA_2SM_LOAD_IM2COL_4D)
+__device__ __forceinline__ void tma_load_im2col_4d_cta2(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c, int w,
+                                                        int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(tmap), "r"(bar & 0xFEFFFFFFu), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_cta2(uint32_t holder_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder_smem), "r"(ncols)
                : "memory");
