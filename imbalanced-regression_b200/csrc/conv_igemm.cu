@@ -6,9 +6,9 @@
 // Persistent kernel: one CTA per SM walks the 128 x BN output tiles round-robin; the smem ring and the two
 // TMEM accumulators run across tile boundaries, so loads, MMAs and epilogues of neighbouring tiles overlap:
 //   warps 0-3  gather the A operand (im2col rows) global -> swizzled smem with 16-byte cp.async
-//              (zero-fill = padding);
-//   warp 4     streams the B operand (weights, or dY for wgrad) with TMA;
-//   warp 5     owns TMEM and issues tcgen05.mma from one elected thread;
+//              (zero-fill = padding) -- idle when A is a plain matrix (1x1 stride-1 convs) or im2col TMA is on;
+//   warp 4     streams the B operand (weights, or dY for wgrad) with TMA, and the A operand in the TMA-fed forms;
+//   warp 5     owns TMEM and issues tcgen05.mma (warp converged, one elected lane issues);
 //   warps 6-9  epilogue: tcgen05.ld TMEM -> registers -> global, then hand the accumulator back.
 // mbarriers: full/empty per smem stage, full/empty per TMEM accumulator.
 //
@@ -244,7 +244,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
       // pixel and the quarter-warps fetch it with shuffles.
       const int j = lane & 7;          // 16-byte column served by this thread
       const int q = lane >> 3;         // row within a group of 4
-      const int ntaps = STEM ? P.kh : P.kh * P.kw;
       uint32_t cnt = 0;                // k-blocks produced so far (ring position)
       for (int t = tile_start; t < P.num_tiles; t += tile_stride) {
         int split, m_tile, n_tile, kb_begin, nk;
