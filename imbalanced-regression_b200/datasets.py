@@ -131,3 +131,47 @@ def depth_pixel_weights(depth, bucket_weights):
     _lib.call("dirb200_lds_table_lookup", _lib.ptr(d), d.numel(), 10.0, table.numel() - 1, _lib.ptr(table),
               _lib.ptr(out), _lib.stream_ptr())
     return out
+
+
+# ------------------------------------------------------------------ STS-B re-weighting / LDS
+def stsb_weights_from_bins(bins, reweight, lds=False, lds_kernel='gaussian', lds_ks=5, lds_sigma=2, bucket_num=50):
+    """Host part of sts-b-dir/tasks.py:44-73 (50 numbers + one gather over <= 6k sentence pairs, once per run): bin
+    histogram, sqrt for 'sqrt_inv', LDS convolve (zero padded; scipy keeps an integer histogram integer, as the
+    reference's call does), weight = float32(1 / value[bin]) rescaled to mean 1.  `bins`: int bucket index per sample.
+    Returns (weights float32 [N], hist int64 [bucket_num])."""
+    from scipy.ndimage import convolve1d
+    assert reweight in {'inverse', 'sqrt_inv'}
+    bins = np.asarray(bins, dtype=np.int64).reshape(-1)
+    hist = np.bincount(bins, minlength=bucket_num).astype(np.int64)
+    value_lst = np.sqrt(hist) if reweight == 'sqrt_inv' else hist
+    print(f"Using re-weighting: [{reweight.upper()}]")
+    if lds:
+        window = get_lds_kernel_window(lds_kernel, lds_ks, lds_sigma)
+        print(f'Using LDS: [{lds_kernel.upper()}] ({lds_ks}/{lds_sigma})')
+        value_lst = convolve1d(value_lst, weights=window, mode='constant')
+    with np.errstate(divide='ignore'):
+        weights = (1.0 / np.asarray(value_lst)[bins]).astype(np.float32)
+    scaling = np.float32(len(weights)) / np.sum(weights)
+    return (np.float32(scaling) * weights).astype(np.float32), hist
+
+
+def stsb_prepare_weights(scores, reweight, lds=False, lds_kernel='gaussian', lds_ks=5, lds_sigma=2, bucket_num=50,
+                         device=None):
+    """Loss weights of the STS-B loader (sts-b-dir/tasks.py:44-73).  The score -> bucket rule (np.histogram edges over
+    [0, 5] in float32, 5.0 in the last bucket) is the same bit-exact kernel the STS-B FDS module bins with
+    (dirb200_fds_bin_rows, DIRB200_BIN_EDGES5), so LDS and FDS can never disagree about a sample's bucket; the
+    50-number table work stays on the host.  Returns a float32 CUDA tensor [N], or None for reweight == 'none'."""
+    assert reweight in {'none', 'inverse', 'sqrt_inv'}
+    assert reweight != 'none' if lds else True, "Set reweight to 'inverse' (default) or 'sqrt_inv' when using LDS"
+    if reweight == 'none':
+        return None
+    device = device or torch.device('cuda')
+    lab = torch.as_tensor(np.asarray(scores), dtype=torch.float32).reshape(-1).to(device).contiguous()
+    _lib.require_cuda(lab)
+    n = lab.numel()
+    bins = torch.empty(n, dtype=torch.int32, device=device)
+    flags = torch.zeros(2, dtype=torch.int32, device=device)
+    _lib.call("dirb200_fds_bin_rows", _lib.ptr(lab), n, bucket_num, 0, _lib.BIN_EDGES5, _lib.ptr(flags), _lib.ptr(bins),
+              _lib.stream_ptr())
+    weights, _ = stsb_weights_from_bins(bins.cpu().numpy(), reweight, lds, lds_kernel, lds_ks, lds_sigma, bucket_num)
+    return torch.from_numpy(weights).to(device)

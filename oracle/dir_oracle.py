@@ -502,3 +502,26 @@ def shot_metrics(preds, labels, train_labels, many_shot_thr: int = 100, low_shot
             out[name] = {"mse": np.sum(e * e) / n, "l1": np.sum(np.abs(e)) / n,
                          "gmean": float(np.exp(np.sum(np.log(np.abs(e))) / n)), "count": int(n)}
     return out
+
+
+# --------------------------------------------------------------------------
+# STS-B re-weighting / LDS
+# --------------------------------------------------------------------------
+def stsb_lds_weights(scores, reweight: str, lds: bool = False, lds_kernel: str = "gaussian", lds_ks: int = 5,
+                     lds_sigma: float = 2, bucket_num: int = 50):
+    """Per-sentence-pair loss weights of sts-b-dir/tasks.py:44-73: histogram of the float32 scores over `bucket_num`
+    equal bins of [0, 5] (np.histogram edges in the scores' dtype; score == 5 -> last bin), sqrt for 'sqrt_inv',
+    optional LDS convolve (zero padded; an integer histogram -- the 'inverse' path -- is truncated back to integers
+    by scipy, as in the age datasets), w = float32(1 / value[bin]) rescaled to mean 1.  No clipping of the counts
+    here (unlike agedb-dir/datasets.py:66-67).  Returns (hist int64[bucket_num], weights float32[N])."""
+    assert reweight in ("inverse", "sqrt_inv")
+    s = np.asarray(scores, dtype=np.float32).reshape(-1)
+    bins = bin_index_edges5(s, bucket_num, 0).astype(np.int64)
+    hist = np.bincount(bins, minlength=bucket_num).astype(np.int64)
+    val = np.sqrt(hist.astype(np.float64)) if reweight == "sqrt_inv" else hist
+    if lds:
+        val = convolve1d_constant(val, lds_kernel_window(lds_kernel, lds_ks, lds_sigma))
+    with np.errstate(divide="ignore"):
+        w = (1.0 / np.asarray(val)[bins]).astype(np.float32)            # np.float32(1 / x)        tasks.py:69
+    scaling = np.float32(len(w)) / np.sum(w)                             # float32 sum             tasks.py:70
+    return hist, (np.float32(scaling) * w).astype(np.float32)

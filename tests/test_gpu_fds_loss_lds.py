@@ -290,3 +290,19 @@ def test_nyud2_pixel_weights_and_dense_loss_vs_reference():
     ref = (((pred.detach() - depth) ** 2) * w).mean()
     assert_close(l.item(), ref.item(), rtol=1e-5)
     assert_close(pred.grad.cpu().numpy(), (2 * (pred.detach() - depth) * w / depth.numel()).cpu().numpy(), rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("inv", dict(reweight="inverse")),
+    ("sqrt_lds_gau_5_2", dict(reweight="sqrt_inv", lds=True, lds_kernel="gaussian", lds_ks=5, lds_sigma=2)),
+    ("inv_lds_tri_5", dict(reweight="inverse", lds=True, lds_kernel="triang", lds_ks=5, lds_sigma=2)),
+])
+def test_stsb_lds_weights_vs_reference_golden(tag, kw):
+    """sts-b-dir/tasks.py:44-73 on the real STS-B training scores: GPU bucket rule + host table vs the fixture made
+    by the reference's own lines (tests/golden/make_golden_stsb_lds.py)."""
+    from datasets import stsb_prepare_weights
+    g = golden("lds_stsb")
+    w = stsb_prepare_weights(g["scores"], **kw)
+    assert w.is_cuda and w.dtype == torch.float32 and w.numel() == g["scores"].size
+    assert_close(w.cpu().numpy(), g[f"w_{tag}"], rtol=2e-6, atol=0, what=tag)
+    assert stsb_prepare_weights(g["scores"], "none") is None

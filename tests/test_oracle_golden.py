@@ -202,3 +202,31 @@ def test_shot_metrics_match_reference(tag):
     assert_close(got, g[f"{tag}_ref"], rtol=1e-6, atol=1e-12, what=f"shot metrics {tag}")
     assert_close([sd["overall"][m] for m in ("mse", "l1", "gmean")], g[f"{tag}_overall"], rtol=1e-6, atol=1e-12)
     assert sd["many"]["count"] + sd["median"]["count"] + sd["low"]["count"] == sd["overall"]["count"] == 2140
+
+
+STSB_LDS = {"inv": dict(reweight="inverse"), "sqrt": dict(reweight="sqrt_inv"),
+            "inv_lds_gau_5_2": dict(reweight="inverse", lds=True, lds_kernel="gaussian", lds_ks=5, lds_sigma=2),
+            "sqrt_lds_gau_5_2": dict(reweight="sqrt_inv", lds=True, lds_kernel="gaussian", lds_ks=5, lds_sigma=2),
+            "sqrt_lds_lap_9_1": dict(reweight="sqrt_inv", lds=True, lds_kernel="laplace", lds_ks=9, lds_sigma=1),
+            "inv_lds_tri_5": dict(reweight="inverse", lds=True, lds_kernel="triang", lds_ks=5, lds_sigma=2)}
+
+
+@pytest.mark.parametrize("tag", sorted(STSB_LDS))
+def test_stsb_lds_weights_match_reference(tag):
+    # fixture: the reference's own weighting lines (sts-b-dir/tasks.py:44-73) on the real STS-B training scores
+    g = golden("lds_stsb")
+    hist, w = O.stsb_lds_weights(g["scores"], **STSB_LDS[tag])
+    assert np.array_equal(hist, g["hist"])                                   # integer work: bit-exact
+    assert_close(w, g[f"w_{tag}"], rtol=2e-6, atol=0, what=tag)
+
+
+@pytest.mark.parametrize("tag", sorted(STSB_LDS))
+def test_stsb_host_mirror_from_oracle_bins(tag):
+    # the host half of datasets.stsb_prepare_weights (everything except the GPU binning kernel), fed with the
+    # oracle's bucket indices
+    import datasets
+    g = golden("lds_stsb")
+    bins = O.bin_index_edges5(g["scores"], 50, 0)
+    w, hist = datasets.stsb_weights_from_bins(bins, **STSB_LDS[tag])
+    assert np.array_equal(hist, g["hist"])
+    assert_close(w, g[f"w_{tag}"], rtol=2e-6, atol=0, what=tag)
