@@ -1,10 +1,14 @@
-"""Standalone GPU check + per-layer timing of the conv GEMMs (not collected by pytest).
+"""Standalone GPU check + per-layer timing of the conv GEMMs under the kernel's run-time switches (not collected
+by pytest; tests/test_gpu_conv_variants.py runs the parity half in subprocesses).
 
-    DIRB200_CTA2=1 python tests/cta2_check.py parity     # CTA-pair kernels vs torch (same checks as test_gpu_conv)
-    DIRB200_CTA2=0 python tests/cta2_check.py time       # per-layer fprop/dgrad times, batch 256 ResNet-50 shapes
-    DIRB200_CTA2=1 python tests/cta2_check.py time
+    DIRB200_CTA2=1   python tests/cta2_check.py parity   # CTA pairs (cta_group::2), gather-fed A      [validated]
+    DIRB200_IM2COL=1 python tests/cta2_check.py parity   # im2col-mode TMA for the 3x3 / strided convs  [validated]
+    DIRB200_ATMA=0   python tests/cta2_check.py parity   # cp.async gather for every conv               [validated]
+    DIRB200_CTA2=2 [DIRB200_IM2COL=1] python tests/cta2_check.py parity   # pairs with TMA-fed A: NOT yet run on hardware
+    <switches> python tests/cta2_check.py time           # per-layer fprop/dgrad times, batch-256 ResNet-50 shapes
+                                                          # (also written to gpurun_out/conv_layers_cta2_<mode>.json)
 
-DIRB200_CTA2 is read once per process, hence the separate invocations.
+The switches are read once per process, hence the separate invocations.  Round-1 results: profiles/r1_conv_layers.md.
 """
 import json
 import os
