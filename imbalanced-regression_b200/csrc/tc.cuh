@@ -53,8 +53,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // One lane of the (fully converged) warp: the single-thread issue of TMA / tcgen05 instructions.  Issuing from
 // `if (elect_one())` in a CONVERGED warp -- rather than from a divergent `if (lane == 0)` region -- lets the compiler
 // keep descriptors / coordinates in uniform registers; in a divergent region every UTCHMMA / UTMALDG is wrapped in
-// an ELECT + R2UR.BROADCAST "uniformisation" loop (~15 instructions per MMA), which bounded the whole GEMM at
-// ~0.6 us per k-block whatever the tile shape.
+// an ELECT + R2UR.BROADCAST "uniformisation" loop (~15 instructions per MMA; measured cost on the conv GEMMs: 2-3 %).
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
