@@ -166,7 +166,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
              const IgemmParams P) {
   using C = Cfg<BN, !WGRAD, CTA2>;
   static_assert(!(BSTAT && WGRAD), "B-stationary mode is for fprop/dgrad");
-  static_assert(!CTA2 || (!WGRAD && !STEM && !BSTAT && BN >= 128), "CTA pairs: fprop/dgrad with BN >= 128 only");
+  static_assert(!CTA2 || (!STEM && !BSTAT && BN >= 128), "CTA pairs: non-stem GEMMs with BN >= 128 only");
+  static_assert(!(CTA2 && WGRAD && ATMA), "wgrad pairs: gather-fed A only so far");
   static_assert(!ATMA || (!STEM && !BSTAT), "TMA-fed A operand: not for the stem / B-stationary forms");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -428,7 +429,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           mbar_wait(empty_bar(s), ph ^ 1u);
           const int kb = kb_begin + it;
           if (elect_one()) {
-            if constexpr (CTA2) {
+            if constexpr (CTA2 && WGRAD) {
+              // wgrad pairs (UNVERIFIED on hardware, DIRB200_CTA2=3 only): this CTA's BN/2 columns of the dY tile
+              if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * C::kBBytes);
+#pragma unroll
+              for (int i = 0; i < C::kBRows / 64; ++i)
+                tma_load_2d_cta2(b_addr(s) + i * 8192, &tmap_b, full_bar(s),
+                                 n0 + static_cast<int>(rank) * C::kBRows + 64 * i, kb * 64);
+            } else if constexpr (CTA2) {
               // this CTA's half of the B tile; both halves are accounted on the leader's barrier
               if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * (C::kBBytes + (ATMA ? C::kABytes : 0)));
               const int tc = kb / P.cpb;
@@ -781,10 +789,10 @@ static int launch_igemm_impl(const CUtensorMap& tm, const CUtensorMap& tma, cons
 }
 
 // CTA-pair variant: (2,1,1) clusters, one pair per two SMs; Q.m_tiles / Q.num_tiles count 256-row pair tiles.
-template <int BN, bool ATMA = false>
+template <int BN, bool ATMA = false, bool WGRAD = false>
 static int launch_igemm_cta2(const CUtensorMap& tm, const CUtensorMap& tma, const IgemmParams& Q, cudaStream_t st) {
-  using C = Cfg<BN, true, true>;
-  auto kern = igemm_kernel<BN, false, false, false, true, ATMA>;
+  using C = Cfg<BN, !WGRAD, true>;
+  auto kern = igemm_kernel<BN, WGRAD, false, false, true, ATMA>;
   static bool configured = false;
   if (!configured) {
     DIRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -825,10 +833,12 @@ static int launch_igemm_cta2(const CUtensorMap& tm, const CUtensorMap& tma, cons
 // the cp.async gather (validated on B200).  DIRB200_CTA2=2 additionally feeds the pairs' A operand by TMA wherever
 // the single-CTA path would (tiled for plain GEMMs, im2col with DIRB200_IM2COL=1) -- the canonical 2-SM pipeline;
 // written after the round's GPU budget was spent: compiles, NOT yet run on hardware, never selected by default.
+// DIRB200_CTA2=3 = mode 2 plus CTA pairs for the wgrad GEMMs (gather-fed A, relay as in mode 1) -- same status as
+// mode 2: compiles, not yet run on hardware.
 static int cta2_mode() {
   static const int mode = [] {
     const char* e = getenv("DIRB200_CTA2");
-    return (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+    return (e != nullptr && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 0;
   }();
   return mode;
 }
@@ -946,7 +956,7 @@ int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y,
   P.n_tiles = s.cout / bn;
   CUtensorMap tm;
   if (!stem && bn >= 128 && cta2_enabled()) {
-    if (cta2_mode() == 2 && (is_plain_gemm(s, stem) || im2col_enabled())) {      // pairs with a TMA-fed A operand
+    if (cta2_mode() >= 2 && (is_plain_gemm(s, stem) || im2col_enabled())) {      // pairs with a TMA-fed A operand
       CUtensorMap ta;
       if (is_plain_gemm(s, stem)) {
         if (int rc = make_tmap_bf16_2d(&ta, x, s.cin, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cin) * 2, BM))
@@ -1004,7 +1014,7 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
     const int bn = pick_bn(s.cin, m_tiles, !is_plain_gemm(s, false));
     P.n_tiles = s.cin / bn;
     if (bn >= 128 && cta2_enabled()) {
-      if (cta2_mode() == 2 && (is_plain_gemm(s, false) || (im2col_enabled() && s.kh == s.kw))) {
+      if (cta2_mode() >= 2 && (is_plain_gemm(s, false) || (im2col_enabled() && s.kh == s.kw))) {
         CUtensorMap ta;
         if (is_plain_gemm(s, false)) {
           if (int rc = make_tmap_bf16_2d(&ta, dy, s.cout, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cout) * 2, BM))
@@ -1086,8 +1096,10 @@ int conv_wgrad_splits(const ConvShape& s) {
   const int kblocks = static_cast<int>((pixels + 63) / 64);
   const int chunks = s.kh * s.kw * s.cin / 64;
   const int bn = wgrad_bn(s);
-  const int tiles = ((chunks + 1) / 2) * (s.cout / bn);
-  const int sms = num_sms();
+  const bool pairs = cta2_mode() == 3 && bn >= 128;     // work items are 256-row pair tiles on SM pairs
+  const int m_tiles = (chunks + 1) / 2;
+  const int tiles = (pairs ? (m_tiles + 1) / 2 : m_tiles) * (s.cout / bn);
+  const int sms = pairs ? num_sms() / 2 : num_sms();
   int max_splits = (kblocks + 7) / 8;                   // at least 8 k-blocks per split
   if (max_splits < 1) max_splits = 1;
   int hi = (4 * sms + tiles - 1) / tiles;
@@ -1134,6 +1146,12 @@ int conv_wgrad_partials(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
   if (int rc = make_tmap_bf16_2d(&tm, dy, s.cout, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cout) * 2, 64))
     return rc;
   if (stem) return DISPATCH_BN(bn, true, true, tm, P, m_tiles, splits, st);
+  if (cta2_mode() == 3 && bn >= 128) {                  // wgrad pairs, gather-fed A
+    IgemmParams Q = P;
+    Q.m_tiles = (m_tiles + 1) / 2;
+    Q.num_tiles = Q.m_tiles * P.n_tiles * splits;
+    return bn == 256 ? launch_igemm_cta2<256, false, true>(tm, tm, Q, st) : launch_igemm_cta2<128, false, true>(tm, tm, Q, st);
+  }
   if (is_plain_gemm(s, stem)) {
     CUtensorMap ta;     // x as [pixels][cin], 64-pixel x 64-channel boxes
     if (int rc = make_tmap_bf16_2d(&ta, x, s.cin, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cin) * 2, 64))

@@ -5,6 +5,7 @@ by pytest; tests/test_gpu_conv_variants.py runs the parity half in subprocesses)
     DIRB200_IM2COL=1 python tests/cta2_check.py parity   # im2col-mode TMA for the 3x3 / strided convs  [validated]
     DIRB200_ATMA=0   python tests/cta2_check.py parity   # cp.async gather for every conv               [validated]
     DIRB200_CTA2=2 [DIRB200_IM2COL=1] python tests/cta2_check.py parity   # pairs with TMA-fed A: NOT yet run on hardware
+    DIRB200_CTA2=3 ...                                   # mode 2 + wgrad pairs:  NOT yet run on hardware
     <switches> python tests/cta2_check.py time           # per-layer fprop/dgrad times, batch-256 ResNet-50 shapes
                                                           # (also written to gpurun_out/conv_layers_cta2_<mode>.json)
 
