@@ -112,7 +112,7 @@ def run_reference(args):
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": WORKLOAD, "sample": sample},
            "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                            "sample": sample},
+                            "sample": sample, "fds_ms": cpu_fds_timings()},
            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -122,6 +122,34 @@ def cpu_threads():
     """Host threads for the CPU arm: all cores up to 32 -- beyond that torch's CPU conv/BN kernels on a small batch
     slow down badly (measured on the 128-thread B200 host: 0.05-0.5 img/s with 128 threads)."""
     return max(1, min(os.cpu_count() or 1, 32))
+
+
+def cpu_fds_timings():
+    """the FDS stages on the host CPU (oracle port, numpy): `update_running_stats` over the AgeDB-sized
+    feature matrix (N = 12 208 x 2048) and `smooth` on one batch (B = 256), median of 3 runs, in ms.  Reported next
+    to the step baseline; never fails the bench (None on any error)."""
+    try:
+        from oracle import dir_oracle as O
+        rng = np.random.RandomState(0)
+        n, d = 12208, 2048
+        feats = np.maximum(rng.randn(n, d).astype(np.float32) + 0.5, 0)
+        lab = synthetic_labels(n, 3)
+        st = O.FDSState(d, 101, 0, kernel="gaussian", ks=5, sigma=2)
+        st.update_last_epoch_stats(0)
+        upd, smo = [], []
+        for ep in range(3):
+            t0 = time.perf_counter()
+            st.update_running_stats(feats, lab, ep)
+            upd.append(time.perf_counter() - t0)
+            st.update_last_epoch_stats(ep + 1)
+        for _ in range(3):
+            t0 = time.perf_counter()
+            st.smooth(feats[:256], lab[:256], 3)
+            smo.append(time.perf_counter() - t0)
+        return {"update_running_stats_n12208_ms": round(1e3 * sorted(upd)[1], 2),
+                "smooth_b256_ms": round(1e3 * sorted(smo)[1], 2), "impl": "oracle/dir_oracle.py (numpy)"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:200]}
 
 
 def cpu_baseline_sample(seconds_budget=20.0):
@@ -142,7 +170,8 @@ def cpu_baseline_sample(seconds_budget=20.0):
         n += 1
     dt = time.perf_counter() - t0
     return {"value": bs * n / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} steps of batch {bs} after 1 warm-up (oracle/train_ref.py: torch fp32 CPU kernels)"}
+            "sample": f"{n} steps of batch {bs} after 1 warm-up (oracle/train_ref.py: torch fp32 CPU kernels)",
+            "fds_ms": cpu_fds_timings()}
 
 
 # ----------------------------------------------------------------------------- GPU arm
