@@ -253,11 +253,12 @@ int dirb200_lds_table_lookup(const float* values, int64_t n, float mult, int max
   return DIRB200_OK;
 }
 
-int dirb200_lds_weights(const float* labels, int64_t n, int max_target, int reweight, const double* window_host,
-                        int ks, const int64_t* hist, double* scratch, float* weights_out, void* stream) {
+int dirb200_lds_weights_sharded(const float* labels, int64_t n, int64_t n_total, int max_target, int reweight,
+                                const double* window_host, int ks, const int64_t* hist, double* scratch,
+                                float* weights_out, void* stream) {
   DIRB_CHECK_ARG(reweight == DIRB200_REWEIGHT_SQRT_INV || reweight == DIRB200_REWEIGHT_INVERSE,
                  "lds_weights: reweight must be sqrt_inv or inverse");
-  DIRB_CHECK_ARG(n > 0 && max_target > 0 && max_target <= 8192 && labels && hist && scratch && weights_out,
+  DIRB_CHECK_ARG(n > 0 && n_total >= n && max_target > 0 && max_target <= 8192 && labels && hist && scratch && weights_out,
                  "lds_weights: bad arguments");
   DIRB_CHECK_ARG(ks == 0 || (window_host && (ks & 1) && ks <= 33), "lds_weights: ks must be 0 or odd <= 33");
   LdsWindow w;
@@ -265,11 +266,19 @@ int dirb200_lds_weights(const float* labels, int64_t n, int max_target, int rewe
   for (int i = 0; i < ks / 2; ++i)
     DIRB_CHECK_ARG(window_host[i] == window_host[ks - 1 - i], "lds_weights: window must be symmetric");
   cudaStream_t st = as_stream(stream);
-  lds_bins_kernel<<<1, 128, 0, st>>>(reinterpret_cast<const long long*>(hist), max_target, reweight, w, ks, n, scratch);
+  // the per-bin table and the len / sum(w) normaliser come from the histogram of the WHOLE column (n_total labels)
+  lds_bins_kernel<<<1, 128, 0, st>>>(reinterpret_cast<const long long*>(hist), max_target, reweight, w, ks, n_total,
+                                     scratch);
   DIRB_LAUNCHED();
   lds_gather_kernel<<<grid_for2(n, 256, 4 * num_sms()), 256, 0, st>>>(labels, n, max_target, scratch, weights_out);
   DIRB_LAUNCHED();
   return DIRB200_OK;
+}
+
+int dirb200_lds_weights(const float* labels, int64_t n, int max_target, int reweight, const double* window_host,
+                        int ks, const int64_t* hist, double* scratch, float* weights_out, void* stream) {
+  return dirb200_lds_weights_sharded(labels, n, n, max_target, reweight, window_host, ks, hist, scratch, weights_out,
+                                     stream);
 }
 
 }  // extern "C"

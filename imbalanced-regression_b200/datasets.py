@@ -21,10 +21,16 @@ print = logging.info
 
 
 def lds_prepare_weights(labels, reweight, max_target=121, lds=False, lds_kernel='gaussian', lds_ks=5, lds_sigma=2,
-                        device=None, return_hist=False):
+                        device=None, return_hist=False, sharded=False):
     """GPU implementation of AgeDB._prepare_weights.  Returns a float32 CUDA
     tensor [N] (or None for reweight == 'none'); with return_hist also the
-    int64 histogram.  Histograms all-reduce across ranks when labels are sharded."""
+    int64 histogram.
+
+    `labels` must be the WHOLE training label column (what the reference's dataset object holds) -- train.py builds
+    the dataset over the whole split on every rank and shards by sampler.  `sharded=True` is for callers that hold
+    only `rank::world` of the column: the int64 histogram and the sample count are then SUM-all-reduced over the
+    default process group before the per-bin table and the len/sum(w) normaliser are formed, which gives every
+    sample exactly the weight the unsharded call gives it."""
     assert reweight in {'none', 'inverse', 'sqrt_inv'}
     assert reweight != 'none' if lds else True, \
         "Set reweight to 'sqrt_inv' (default) or 'inverse' when using LDS"
@@ -34,6 +40,14 @@ def lds_prepare_weights(labels, reweight, max_target=121, lds=False, lds_kernel=
     hist = torch.zeros(max_target, dtype=torch.int64, device=device)
     st = _lib.stream_ptr()
     _lib.call("dirb200_lds_histogram", _lib.ptr(lab), n, max_target, _lib.ptr(hist), st)
+    n_total = n
+    if sharded:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            cnt = torch.tensor([n], dtype=torch.int64, device=device)
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+            n_total = int(cnt.item())
     if n == 0 or reweight == 'none':
         return (None, hist) if return_hist else None
     print(f"Using re-weighting: [{reweight.upper()}]")
@@ -44,7 +58,7 @@ def lds_prepare_weights(labels, reweight, max_target=121, lds=False, lds_kernel=
         print(f'Using LDS: [{lds_kernel.upper()}] ({lds_ks}/{lds_sigma})')
     scratch = torch.empty(2 * max_target + 2, dtype=torch.float64, device=device)
     weights = torch.empty(n, dtype=torch.float32, device=device)
-    _lib.call("dirb200_lds_weights", _lib.ptr(lab), n, max_target, _lib.REWEIGHT[reweight],
+    _lib.call("dirb200_lds_weights_sharded", _lib.ptr(lab), n, n_total, max_target, _lib.REWEIGHT[reweight],
               None if window is None else window.ctypes.data_as(_lib.P), ks, _lib.ptr(hist), _lib.ptr(scratch),
               _lib.ptr(weights), st)
     return (weights, hist) if return_hist else weights

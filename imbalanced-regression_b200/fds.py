@@ -197,6 +197,10 @@ class FDS(nn.Module):
         _lib.call("dirb200_fds_accumulate", _lib.ptr(features), _lib.ptr(bins), n, d, nb, _lib.ptr(acc["sums"]),
                   _lib.ptr(acc["sumsq"]), _lib.ptr(acc["counts"]), _lib.ptr(acc["ws"]), acc["ws"].numel(), st)
 
+    def abort_epoch_stats(self):
+        """Drop a streamed collection without touching the tables (update_running_stats' gate failed, fds.py:85)."""
+        self._acc = None
+
     @classmethod
     def reduce_accumulators(cls, acc):
         """Merge the per-rank (count, sum x, sum x^2) accumulators: plain SUM all-reduces (the fp64 sums make

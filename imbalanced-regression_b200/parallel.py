@@ -12,10 +12,46 @@ epoch inside fds.FDS.
 import torch
 import torch.distributed as dist
 import torch.nn as nn
+from torch.utils.data import Sampler
 
 
 def is_distributed():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class ShardSampler(Sampler):
+    """This rank's slice of the index space 0..n-1: `rank::world` of one global order (a permutation seeded by
+    `seed + epoch` when `shuffle`, identical on every rank).  `pad=True` wraps the order around to a multiple of
+    `world` first, so every rank yields the same number of indices -- a training epoch then runs the same number of
+    steps (= gradient all-reduces) everywhere; `pad=False` gives the exact partition (every index once across the
+    ranks), which is what a statistics pass over the training set needs."""
+
+    def __init__(self, n, rank=0, world=1, shuffle=True, pad=True, seed=0):
+        assert 0 <= rank < world and n >= 0
+        self.n, self.rank, self.world, self.shuffle, self.pad, self.seed = n, rank, world, shuffle, pad, seed
+        self.epoch = 0
+
+    def set_epoch(self, epoch):
+        self.epoch = int(epoch)
+
+    def indices(self):
+        if self.shuffle:
+            g = torch.Generator().manual_seed(self.seed + self.epoch)
+            order = torch.randperm(self.n, generator=g)
+        else:
+            order = torch.arange(self.n)
+        if self.pad and self.n % self.world and self.n > 0:
+            extra = self.world - self.n % self.world
+            order = torch.cat([order, order[:extra]]) if extra <= self.n else order.repeat(self.world)[:self.__len__() * self.world]
+        return order[self.rank::self.world].numpy()
+
+    def __iter__(self):
+        return iter(self.indices().tolist())
+
+    def __len__(self):
+        if self.pad:
+            return (self.n + self.world - 1) // self.world
+        return len(range(self.rank, self.n, self.world))
 
 
 class DataParallel(nn.Module):
@@ -28,9 +64,10 @@ class DataParallel(nn.Module):
 
     def reduce_gradients(self, async_op=False):
         """Sum the flat gradient buffer across ranks (one NCCL all-reduce)."""
+        grads = self.module.flat_grads()     # also (re)attaches every .grad to its view of the flat buffer
         if not is_distributed():
             return None
-        return dist.all_reduce(self.module.flat_grads(), op=dist.ReduceOp.SUM, async_op=async_op)
+        return dist.all_reduce(grads, op=dist.ReduceOp.SUM, async_op=async_op)
 
     def broadcast_parameters(self, src=0):
         if is_distributed():

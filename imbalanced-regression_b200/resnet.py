@@ -285,11 +285,17 @@ class ResNet(nn.Module):
                 p.grad = v
 
     # ------------------------------------------------------------ native nets
+    MAX_NETS = 4      # distinct input shapes kept alive (train batch, train tail, val/test batch, val/test tail)
+
     def _net(self, shape):
-        net = self._nets.get(shape)
+        """Native runner for input `shape` (created on first use).  The cache is LRU: a new shape evicts only the
+        least recently used runner -- a normal epoch alternates between four shapes and must not rebuild any."""
+        net = self._nets.pop(shape, None)
         if net is None:
-            if len(self._nets) >= 3:
-                self._free_nets()
+            while len(self._nets) >= self.MAX_NETS:
+                _, old = next(iter(self._nets.items()))
+                self._nets.pop(next(iter(self._nets)))
+                _lib.raw("dirb200_resnet_destroy")(old)
             n, c, h, w = shape
             assert c == 3, "expected NCHW input with 3 channels"
             handle = c_void_p()
@@ -297,7 +303,8 @@ class ResNet(nn.Module):
             _lib.call("dirb200_resnet_create", n, h, w, arr, 4, ctypes.byref(handle))
             assert _lib.raw("dirb200_resnet_param_count")(handle) == self._flat["backbone"], "parameter layout mismatch"
             assert _lib.raw("dirb200_resnet_running_count")(handle) == self._flat["running"].numel()
-            net = self._nets[shape] = handle
+            net = handle
+        self._nets[shape] = net          # most recently used last
         return net
 
     def _free_nets(self):
@@ -323,6 +330,9 @@ class ResNet(nn.Module):
         return enc
 
     def _run_backward(self, shape, g):
+        if shape not in self._nets:
+            raise _lib.Dirb200Error(f"backward for input shape {shape}: its runner (and the activations of the forward "
+                                    "pass) was evicted -- more than MAX_NETS shapes ran between forward and backward")
         self._ensure_grads()
         g = g.detach().to(torch.float32).contiguous()
         _lib.call("dirb200_resnet_backward", self._net(shape), _lib.ptr(g), _lib.ptr(self._flat["params"]),
@@ -358,6 +368,13 @@ class ResNet(nn.Module):
 
     # ---------------------------------------------------------------- forward
     def forward(self, x, targets=None, epoch=None):
+        if self.training and torch.is_grad_enabled():
+            # every .grad must be its view of the flat gradient buffer BEFORE autograd accumulates into it (the fused
+            # optimizers and the all-reduce work on the flat buffer); with a frozen backbone (--retrain_fc) the
+            # runner's backward, which used to attach them, never runs
+            lw = self.linear.weight
+            if self._grad_views is None or lw.grad is None or lw.grad.data_ptr() != self._grad_views[-2].data_ptr():
+                self._ensure_grads()
         need_bwd = self.training and torch.is_grad_enabled() and \
             any(p.requires_grad for p in self._flat_param_list()[:-2])
         if need_bwd:

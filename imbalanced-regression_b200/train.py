@@ -9,7 +9,10 @@ Differences that matter:
   * the epoch-end FDS refresh (train.py:269-281 of the reference) streams each
     batch's features into the on-device per-bin accumulators -- no
     GPU->CPU->GPU round trip of the feature matrix, statistics all-reduced
-    across ranks;
+    across ranks -- in the reference's order: collection pass with the old
+    tables, then update_last_epoch_stats, then the running-statistics update;
+  * LDS weights always come from the WHOLE training label column (every rank
+    computes the same table); shards are equal-length index slices;
   * arguments are parsed inside main() (importing this file has no side
     effects) and `--synthetic N` trains on N synthetic samples (no dataset /
     network needed);
@@ -30,7 +33,7 @@ from loss import *  # noqa: F401,F403  (looked up by name, as the reference does
 from datasets import AgeDB, IMDBWIKI, lds_prepare_weights
 from utils import AverageMeter, ProgressMeter, adjust_learning_rate, prepare_folders, save_checkpoint
 from optim import FusedAdam, FusedSGD
-from parallel import DataParallel, is_distributed
+from parallel import DataParallel, ShardSampler, is_distributed
 
 print = logging.info
 
@@ -116,7 +119,23 @@ class SyntheticAges(Dataset):
             np.asarray([w], np.float32)
 
 
-def train(train_loader, model, optimizer, epoch, args):
+def _label_column(loader):
+    """Every label the loader will yield this epoch (its sampler's indices of the dataset's label column)."""
+    ds = loader.dataset
+    col = np.asarray(ds.labels if hasattr(ds, 'labels') else ds.df[ds.label_column].values, dtype=np.float32)
+    sampler = getattr(loader, 'sampler', None)
+    if isinstance(sampler, ShardSampler):
+        return col[sampler.indices()]
+    return col
+
+
+def train(train_loader, model, optimizer, epoch, args, stats_loader=None):
+    """One epoch (agedb-dir/train.py:234-283).  `stats_loader`: loader of the epoch-end FDS collection pass when it
+    differs from `train_loader` (N > 1: the training sampler pads the shards to equal length so that every rank runs
+    the same number of all-reduces; the collection pass must see every sample exactly once, so it uses the exact
+    shards)."""
+    if isinstance(getattr(train_loader, 'sampler', None), ShardSampler):
+        train_loader.sampler.set_epoch(epoch)
     batch_time, data_time = AverageMeter('Time', ':6.2f'), AverageMeter('Data', ':6.4f')
     losses = AverageMeter(f'Loss ({args.loss.upper()})', ':.3f')
     progress = ProgressMeter(len(train_loader), [batch_time, data_time, losses], prefix="Epoch: [{}]".format(epoch))
@@ -144,17 +163,24 @@ def train(train_loader, model, optimizer, epoch, args):
 
     if args.fds and epoch >= args.start_update:
         print(f"Create Epoch [{epoch}] features of all training data...")
+        # Reference order (agedb-dir/train.py:269-281): FIRST the collection pass -- train-mode forward under no_grad,
+        # so FDS.smooth still calibrates with the tables of the PREVIOUS refresh and the collected features are the
+        # smoothed ones -- THEN update_last_epoch_stats (rebinding + stencil), THEN update_running_stats.  The
+        # per-bin sums are streamed into device accumulators batch by batch (no GPU->CPU->GPU round trip) and only
+        # finalised after the last-epoch tables have moved, exactly where the reference calls update_running_stats.
         fds = model.module.FDS
-        fds.update_last_epoch_stats(epoch)                       # order as the reference: train.py:280-281
-        if epoch >= fds._epoch_host:
-            all_labels = torch.as_tensor(np.asarray(train_loader.dataset.labels if hasattr(train_loader.dataset, 'labels')
-                                                    else train_loader.dataset.df['age'].values), dtype=torch.float32)
-            fds.begin_epoch_stats(all_labels.cuda())
-            with torch.no_grad():
-                for (inputs, targets, _) in train_loader:
-                    _, feature = model(inputs.cuda(non_blocking=True), targets.cuda(non_blocking=True), epoch)
-                    fds.accumulate_batch(feature, targets.cuda(non_blocking=True))
+        loader = stats_loader if stats_loader is not None else train_loader
+        fds.begin_epoch_stats(torch.as_tensor(_label_column(loader), dtype=torch.float32).cuda())
+        with torch.no_grad():
+            for (inputs, targets, _) in loader:
+                targets = targets.cuda(non_blocking=True)
+                _, feature = model(inputs.cuda(non_blocking=True), targets, epoch)
+                fds.accumulate_batch(feature, targets)
+        fds.update_last_epoch_stats(epoch)
+        if epoch >= fds._epoch_host:            # gate of update_running_stats (fds.py:85), evaluated after the update
             fds.finish_epoch_stats(epoch)
+        else:
+            fds.abort_epoch_stats()
     return losses.avg
 
 
@@ -231,8 +257,11 @@ def main(argv=None):
     print(f"Store name: {args.store_name}")
 
     print('=====> Preparing data...')
+    # Every rank builds the dataset over the WHOLE training split, so the LDS histogram, clip, smoothing and the
+    # len/sum(w) normaliser see the same label column the reference sees (datasets.py:55-83); the mini-batches are
+    # sharded by the sampler (rank::world of one global permutation per epoch).
     if args.synthetic:
-        train_dataset = SyntheticAges(args.synthetic, args.img_size, args, seed=rank)
+        train_dataset = SyntheticAges(args.synthetic, args.img_size, args, seed=0)
         val_dataset = SyntheticAges(max(args.synthetic // 8, args.batch_size), args.img_size, args, seed=999, train=False)
         test_dataset = val_dataset
     else:
@@ -240,14 +269,18 @@ def main(argv=None):
         df = pd.read_csv(os.path.join(args.data_dir, f"{args.dataset}.csv"))
         cls = AgeDB if args.dataset == 'agedb' else IMDBWIKI
         parts = {s: df[df['split'] == s] for s in ('train', 'val', 'test')}
-        train_dataset = cls(data_dir=args.data_dir, df=parts['train'][rank::world], img_size=args.img_size, split='train',
+        train_dataset = cls(data_dir=args.data_dir, df=parts['train'], img_size=args.img_size, split='train',
                             reweight=args.reweight, lds=args.lds, lds_kernel=args.lds_kernel, lds_ks=args.lds_ks,
                             lds_sigma=args.lds_sigma)
         val_dataset = cls(data_dir=args.data_dir, df=parts['val'], img_size=args.img_size, split='val')
         test_dataset = cls(data_dir=args.data_dir, df=parts['test'], img_size=args.img_size, split='test')
-    mk = lambda ds, sh: DataLoader(ds, batch_size=args.batch_size, shuffle=sh, num_workers=args.workers,
-                                   pin_memory=True, drop_last=False)
-    train_loader, val_loader, test_loader = mk(train_dataset, True), mk(val_dataset, False), mk(test_dataset, False)
+    mk = lambda ds, sampler: DataLoader(ds, batch_size=args.batch_size, sampler=sampler, shuffle=False,
+                                        num_workers=args.workers, pin_memory=True, drop_last=False)
+    n_train = len(train_dataset)
+    train_loader = mk(train_dataset, ShardSampler(n_train, rank, world, shuffle=True, pad=True))
+    stats_loader = train_loader if world == 1 else mk(train_dataset, ShardSampler(n_train, rank, world, shuffle=False,
+                                                                                  pad=False))
+    val_loader, test_loader = mk(val_dataset, None), mk(test_dataset, None)
     print(f"Training data size: {len(train_dataset)}")
     # shot metrics compare against the WHOLE training label column (reference: df_train['age'], train.py:121)
     train_labels = np.asarray(train_dataset.labels if args.synthetic else parts['train']['age'].values)
@@ -291,7 +324,7 @@ def main(argv=None):
 
     for epoch in range(args.start_epoch, args.epoch):
         adjust_learning_rate(optimizer, epoch, args)
-        train_loss = train(train_loader, model, optimizer, epoch, args)
+        train_loss = train(train_loader, model, optimizer, epoch, args, stats_loader=stats_loader)
         val_mse, val_l1, val_gmean = validate(val_loader, model, train_labels=train_labels)
         metric = val_mse if args.loss == 'mse' else val_l1
         is_best = metric < args.best_loss

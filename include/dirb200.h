@@ -154,6 +154,14 @@ int dirb200_lds_weights(const float* labels, int64_t n, int max_target, int rewe
                         const double* window_host, int ks, const int64_t* hist,
                         double* scratch, float* weights_out, void* stream);
 
+/* Same, for a label column sharded over ranks: `hist` is the histogram of the WHOLE column (the per-rank
+ * dirb200_lds_histogram outputs SUM-all-reduced, int64, exact) and `n_total` its length; the per-bin table and the
+ * len / sum(w) normaliser (agedb-dir/datasets.py:81-82) are formed from those, the gather covers this rank's
+ * `n` labels.  dirb200_lds_weights == this with n_total = n.  SURVEY.md section 8e(3). */
+int dirb200_lds_weights_sharded(const float* labels, int64_t n, int64_t n_total, int max_target, int reweight,
+                                const double* window_host, int ks, const int64_t* hist, double* scratch,
+                                float* weights_out, void* stream);
+
 /* Dense per-element weight lookup of nyud2-dir/loaddata.py:52-64: weights_out[i] = table[min(int(values[i] * mult),
  * max_bin)] (mult = 10, max_bin = 99 for depth maps; table = the bucket weights, device pointer). */
 int dirb200_lds_table_lookup(const float* values, int64_t n, float mult, int max_bin, const float* table,

@@ -53,6 +53,15 @@ def _worker(rank, world, port, tmp):
     assert np.allclose(m[has], mean[has], rtol=1e-5, atol=1e-7)
     assert np.allclose(v[has], var[has], rtol=1e-5, atol=1e-7)
 
+    # ---- LDS: the int64 label histograms of the rank::world shards all-reduce to the histogram of the whole
+    # column, so the per-bin table / normaliser every rank derives equals the unsharded one (datasets.py:55-83)
+    ages = rng.randint(0, 140, size=1001).astype(np.float32)
+    hist = torch.from_numpy(O.lds_histogram(ages[rank::world], 121).astype(np.int64))
+    cnt = torch.tensor([len(ages[rank::world])], dtype=torch.int64)
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    assert int(cnt) == 1001 and np.array_equal(hist.numpy(), O.lds_histogram(ages, 121))
+
     # ---- gradient all-reduce + 1/world
     class Dummy(torch.nn.Module):
         def __init__(self):
@@ -75,3 +84,31 @@ def test_world2_gloo_fds_merge_and_grad_allreduce(tmp_path):
     port = 29000 + (os.getpid() % 1000)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_shard_sampler_partitions_and_pads():
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [os.path.join(root, "imbalanced-regression_b200")]
+    from parallel import ShardSampler
+    for n, world in ((191509, 8), (12208, 8), (10, 4), (3, 8), (16, 2), (7, 1)):
+        for shuffle in (False, True):
+            exact = [ShardSampler(n, r, world, shuffle=shuffle, pad=False, seed=5) for r in range(world)]
+            padded = [ShardSampler(n, r, world, shuffle=shuffle, pad=True, seed=5) for r in range(world)]
+            for s in exact + padded:
+                s.set_epoch(3)
+            # exact shards: every index exactly once across the ranks (the FDS collection pass)
+            allidx = np.concatenate([s.indices() for s in exact])
+            assert sorted(allidx.tolist()) == list(range(n))
+            assert all(len(s) == len(s.indices()) for s in exact + padded)
+            # padded shards: the same length on every rank (same number of all-reduces), covering every index
+            lens = {len(s) for s in padded}
+            assert lens == {(n + world - 1) // world}
+            assert set(np.concatenate([s.indices() for s in padded]).tolist()) == set(range(n))
+    # a new epoch reshuffles, identically on every rank
+    a, b = ShardSampler(100, 0, 2, seed=1), ShardSampler(100, 1, 2, seed=1)
+    a.set_epoch(0); b.set_epoch(0)
+    e0 = np.concatenate([a.indices(), b.indices()])
+    a.set_epoch(1); b.set_epoch(1)
+    e1 = np.concatenate([a.indices(), b.indices()])
+    assert sorted(e0.tolist()) == sorted(e1.tolist()) == list(range(100)) and not np.array_equal(e0, e1)

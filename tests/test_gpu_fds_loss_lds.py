@@ -205,6 +205,31 @@ def test_lds_weights_vs_reference_golden(tag):
     assert n >= 4
 
 
+@pytest.mark.parametrize("world", [2, 8])
+def test_lds_weights_of_shards_equal_unsharded(world):
+    """A label column split rank::world: histograms summed (the int64 all-reduce of datasets.lds_prepare_weights with
+    sharded=True) + the sharded weights entry give every sample bit-for-bit the weight of the unsharded call."""
+    import _lib
+    from datasets import lds_prepare_weights
+    from utils import get_lds_kernel_window
+    labels = golden("lds")["imdb_wiki_labels"].astype(np.float32)
+    for rw, lds_on in (("sqrt_inv", True), ("inverse", True), ("inverse", False)):
+        whole = lds_prepare_weights(labels, rw, lds=lds_on, lds_kernel="gaussian", lds_ks=5, lds_sigma=2).cpu().numpy()
+        hist = torch.zeros(121, dtype=torch.int64, device=DEV)
+        shards = [T(labels[r::world]) for r in range(world)]
+        for sh in shards:                    # == SUM all-reduce of the per-rank histograms
+            _lib.call("dirb200_lds_histogram", _lib.ptr(sh), sh.numel(), 121, _lib.ptr(hist), _lib.stream_ptr())
+        assert np.array_equal(hist.cpu().numpy(), O.lds_histogram(labels))
+        window = np.ascontiguousarray(get_lds_kernel_window("gaussian", 5, 2), dtype=np.float64) if lds_on else None
+        for r, sh in enumerate(shards):
+            out = torch.empty_like(sh)
+            scratch = torch.empty(2 * 121 + 2, dtype=torch.float64, device=DEV)
+            _lib.call("dirb200_lds_weights_sharded", _lib.ptr(sh), sh.numel(), len(labels), 121, _lib.REWEIGHT[rw],
+                      None if window is None else window.ctypes.data_as(_lib.P), 0 if window is None else len(window),
+                      _lib.ptr(hist), _lib.ptr(scratch), _lib.ptr(out), _lib.stream_ptr())
+            assert np.array_equal(out.cpu().numpy(), whole[r::world]), (rw, lds_on, r)
+
+
 def test_lds_histogram_clamps_and_accumulates():
     import _lib
     lab = T([0, 0.9, 1, 119.5, 120, 121, 186, 500])
