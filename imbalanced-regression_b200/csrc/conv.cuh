@@ -8,8 +8,11 @@ struct ConvShape {
   int n, h, w, cin, cout, kh, kw, stride, pad, ho, wo;
 };
 
+// stat_partial (optional): the epilogue also accumulates, per output channel, the sum and the sum of squares of the
+// stored outputs into stat_partial[row][2][cout] (row = (CTA, epilogue warp); *stat_rows rows are in use; the buffer
+// must be all-zero on entry outside what this launch writes) -- the BatchNorm batch statistics without re-reading y.
 int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, const ConvShape& s, bool stem,
-               cudaStream_t st);
+               cudaStream_t st, float* stat_partial = nullptr, int* stat_rows = nullptr);
 int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* dx, const ConvShape& s,
                cudaStream_t st);
 int conv_wgrad_splits(const ConvShape& s);

@@ -29,6 +29,28 @@ constexpr int kProducerThreads = 128;   // warps 0-3
 constexpr int kTmaWarp = 4, kMmaWarp = 5; // warps 6-9: epilogue (warp & 3 = TMEM lane quarter)
 constexpr int kThreads = 320;
 
+// Division by a run-time constant as multiply-high + shift (n < 2^31, d >= 1): the k-loops of the producer / TMA
+// warps used to spend most of their time in the ~35-instruction SASS sequences of `/` by cpb, kw, hw, wm
+// (ncu source page, profiles/r2_conv_stalls.md) -- that, not the memory system, was the "gather rate".
+struct FastDiv {
+  uint32_t mul, shr, d;
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : (__umulhi(n, mul) >> shr); }
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+    q = div(n);
+    r = n - q * d;
+  }
+};
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{0u, 0u, d < 1 ? 1u : d};
+  if (f.d == 1) return f;
+  uint32_t lg = 0;
+  while ((1ull << lg) < f.d) ++lg;
+  const uint32_t p = 31 + lg;
+  f.mul = static_cast<uint32_t>(((1ull << p) + f.d - 1) / f.d);
+  f.shr = p - 32;
+  return f;
+}
+
 struct IgemmParams {
   const __nv_bfloat16* src;  // gathered tensor, NHWC
   int n, hs, ws, cs;         // its shape
@@ -42,6 +64,11 @@ struct IgemmParams {
   int nstages;               // B-stationary mode: A-ring depth that fits beside the resident weights
   int ntaps_c;               // taps visited by this launch
   int tap_list[9];           // their indices r*kw + s (identity when cls_on == 0)
+  // per visited tap (index = position in tap_list), filled by finish_params(): element offset of the tap from the
+  // row's origin in the gathered tensor, and the im2col-TMA offsets (flipped for dgrad)
+  long long tap_eoff[9];
+  unsigned short tap_r[9], tap_s[9];
+  FastDiv fd_hw, fd_wm, fd_cpb, fd_kw, fd_ntiles, fd_persplit;
   int cpb;                   // 64-channel blocks per filter tap (cs / 64); stem: unused
   long long pixels;          // n * hm * wm
   int num_kblocks;           // fprop/dgrad: kh*kw*cpb ; wgrad: ceil(pixels / 64)
@@ -53,6 +80,11 @@ struct IgemmParams {
   int i2c_stride, i2c_lo;    // im2col: base pixel of GEMM row (y, x) = (y * i2c_stride + i2c_lo, x * i2c_stride + i2c_lo)
   int ldc;                   // output row stride in elements (Cout for fprop, Cin for dgrad, Cout for wgrad partials)
   void* out;                 // bf16 [pixels][ldc]   or   fp32 [splits][total_chunks*64][ldc]
+  // fprop only, optional: per-column sum / sum of squares of the (bf16-rounded) output = the BatchNorm batch
+  // statistics of the layer, carried in the epilogue warps' registers over all tiles of the CTA and written once as
+  // stat_out[(blockIdx.x * 4 + epilogue warp)][2][ldc] (fp32; rows / columns a CTA does not own are left untouched:
+  // the buffer is kept all-zero between uses by its consumer, bn_finalize)
+  float* stat_out;
 };
 
 // CTA2: the tile is computed by a CTA pair (cta_group::2, UMMA M = 256): this CTA owns 128 of the 256 rows and stages
@@ -87,12 +119,9 @@ struct Cfg {
 // packed pixel: bit 31 valid | n (13 bits) << 18 | y (9 bits) << 9 | x (9 bits)
 __device__ __forceinline__ uint32_t pack_pixel(long long p, const IgemmParams& P) {
   if (p >= P.pixels) return 0u;
-  const uint32_t pp = static_cast<uint32_t>(p);
-  const uint32_t hw = static_cast<uint32_t>(P.hm * P.wm);
-  const uint32_t n = pp / hw;
-  const uint32_t rem = pp - n * hw;
-  const uint32_t y = rem / static_cast<uint32_t>(P.wm);
-  const uint32_t x = rem - y * static_cast<uint32_t>(P.wm);
+  uint32_t n, rem, y, x;
+  P.fd_hw.divmod(static_cast<uint32_t>(p), n, rem);
+  P.fd_wm.divmod(rem, y, x);
   return 0x80000000u | (n << 18) | (y << 9) | x;
 }
 
@@ -190,21 +219,41 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
   const int tile_start = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int tile_stride = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
-  // tile id -> (split, m_tile, n_tile); consecutive ids share the A rows (n fastest) for L2 reuse
+  // Tile walk.  wgrad: work items t = (split, m_tile, n_tile) handed out round-robin (n fastest).
+  // fprop / dgrad: every CTA (pair) keeps ONE n_tile for the whole launch -- CTA c owns n = c % n_tiles and walks
+  // m = c / n_tiles, + G, + 2G, ... (G = CTAs sharing that n); neighbouring CTAs still work on the same A rows at the
+  // same time (L2 reuse), and the epilogue can carry per-column sums (BN statistics) across all of its tiles in
+  // registers and flush them once.
+  int tile_first, tile_end, tile_step, fixed_n = 0;
+  if constexpr (WGRAD) {
+    tile_first = tile_start; tile_end = P.num_tiles; tile_step = tile_stride;
+  } else {
+    uint32_t gi, nn;
+    P.fd_ntiles.divmod(static_cast<uint32_t>(tile_start), gi, nn);
+    fixed_n = static_cast<int>(nn);
+    tile_first = static_cast<int>(gi);
+    tile_end = P.m_tiles;
+    tile_step = static_cast<int>(P.fd_ntiles.div(static_cast<uint32_t>(tile_stride - 1 - fixed_n))) + 1;
+  }
   auto decode_tile = [&](int t, int& split, int& m_tile, int& n_tile, int& kb_begin, int& nk) {
-    const int per_split = P.m_tiles * P.n_tiles;
-    split = t / per_split;
-    const int rem = t - split * per_split;
-    m_tile = rem / P.n_tiles;
-    n_tile = rem - m_tile * P.n_tiles;
-    if constexpr (CTA2) m_tile = 2 * m_tile + static_cast<int>(rank);   // this CTA's 128-row half
-    kb_begin = 0;
-    int kb_end = P.num_kblocks;
     if constexpr (WGRAD) {
+      uint32_t sp, rem, mt, nt;
+      P.fd_persplit.divmod(static_cast<uint32_t>(t), sp, rem);
+      P.fd_ntiles.divmod(rem, mt, nt);
+      split = static_cast<int>(sp);
+      m_tile = static_cast<int>(mt);
+      n_tile = static_cast<int>(nt);
+      if constexpr (CTA2) m_tile = 2 * m_tile + static_cast<int>(rank);   // this CTA's 128-row half
       kb_begin = split * P.kblocks_per_split;
-      kb_end = min(P.num_kblocks, kb_begin + P.kblocks_per_split);
+      const int kb_end = min(P.num_kblocks, kb_begin + P.kblocks_per_split);
+      nk = max(0, kb_end - kb_begin);
+    } else {
+      split = 0;
+      m_tile = CTA2 ? 2 * t + static_cast<int>(rank) : t;
+      n_tile = fixed_n;
+      kb_begin = 0;
+      nk = P.num_kblocks;
     }
-    nk = max(0, kb_end - kb_begin);
   };
 
   if (warp == kMmaWarp) {
@@ -245,8 +294,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
       // pixel and the quarter-warps fetch it with shuffles.
       const int j = lane & 7;          // 16-byte column served by this thread
       const int q = lane >> 3;         // row within a group of 4
-      uint32_t cnt = 0;                // k-blocks produced so far (ring position)
-      for (int t = tile_start; t < P.num_tiles; t += tile_stride) {
+      uint32_t rs = 0, rph = 0;        // ring position: stage, phase (no division / modulo in the k-loop)
+      for (int t = tile_first; t < tile_end; t += tile_step) {
         int split, m_tile, n_tile, kb_begin, nk;
         decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
         long long off8[8];             // fprop/dgrad: origin offsets (elements) of the 8 rows this thread serves
@@ -309,37 +358,35 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           if constexpr (STEM) {
             chunk_r = gchunk;                              // filter row r'
           } else {
-            const int tap = gchunk / P.cpb;
-            chunk_c0 = (gchunk - tap * P.cpb) * 64;
-            chunk_r = tap / P.kw;
-            chunk_s = tap - chunk_r * P.kw;
+            uint32_t tap, cb, cr, csx;
+            P.fd_cpb.divmod(static_cast<uint32_t>(gchunk), tap, cb);
+            P.fd_kw.divmod(tap, cr, csx);
+            chunk_c0 = static_cast<int>(cb) * 64;
+            chunk_r = static_cast<int>(cr);
+            chunk_s = static_cast<int>(csx);
           }
           tile_off = chunk * 8192 + (warp & 1) * 32 * 128;
         }
-        for (int it = 0; it < nk; ++it, ++cnt) {
-          const int s = static_cast<int>(cnt % nstages);
-          const uint32_t ph = (cnt / nstages) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1u);
+        int tc = 0, cb = 0;            // fprop/dgrad: visited-tap index and 64-channel block of the current k-block
+        long long stem_toff = 0;
+        for (int it = 0; it < nk; ++it) {
+          const int s = static_cast<int>(rs);
+          mbar_wait(empty_bar(s), rph ^ 1u);
+          if (++rs == nstages) { rs = 0; rph ^= 1u; }
           const int kb = kb_begin + it;
           const uint32_t dst_base = a_addr(s) + tile_off;
           if constexpr (!WGRAD) {
-            // warp-uniform tap offset
+            // warp-uniform tap offset (table filled on the host; counters instead of kb / cpb, tp / kw)
             int tp;
             long long toff;
             if constexpr (STEM) {
               tp = kb;
-              toff = static_cast<long long>(kb) * P.ws * P.cs;
+              toff = stem_toff;
+              stem_toff += static_cast<long long>(P.ws) * P.cs;
             } else {
-              const int tc = kb / P.cpb;
               tp = P.tap_list[tc];
-              const int c0 = (kb - tc * P.cpb) * 64;
-              int r = tp / P.kw, sx = tp - r * P.kw;
-              if (P.transposed) {
-                if (P.stride == 2) { r >>= 1; sx >>= 1; }
-                toff = c0 - static_cast<long long>(r * P.ws + sx) * P.cs;
-              } else {
-                toff = c0 + static_cast<long long>(r * P.ws + sx) * P.cs;
-              }
+              toff = P.tap_eoff[tc] + cb * 64;
+              if (++cb == P.cpb) { cb = 0; ++tc; }
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -399,38 +446,40 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
       for (int kb = 0; kb < P.num_kblocks; ++kb) {
         int kcoord = kb;
         if constexpr (!STEM) {
-          const int tc = kb / P.cpb;
-          kcoord = P.tap_list[tc] * P.cpb + (kb - tc * P.cpb);
+          uint32_t tcb, cbb;
+          P.fd_cpb.divmod(static_cast<uint32_t>(kb), tcb, cbb);
+          kcoord = P.tap_list[tcb] * P.cpb + static_cast<int>(cbb);
         }
         tma_load_2d(bstat_base + kb * C::kBBytes, &tmap_b, bstat_bar, kcoord * BK, 0);
       }
     } else if (!BSTAT) {
-      // the whole warp walks the ring (converged); one elected lane issues
-      uint32_t cnt = 0;
-      for (int t = tile_start; t < P.num_tiles; t += tile_stride) {
+      // the whole warp walks the ring (converged); one elected lane issues.  Ring position and the (tap, channel
+      // block) of the k-block are counters; tap coordinates come from the host-filled tables -- no division here.
+      uint32_t rs = 0, rph = 0;
+      for (int t = tile_first; t < tile_end; t += tile_step) {
         int split, m_tile, n_tile, kb_begin, nk;
         decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
         const int n0 = n_tile * BN;
         int tile_w0 = 0, tile_h0 = 0, tile_n0 = 0;     // im2col base pixel of the tile's first GEMM row
         if constexpr (ATMA && !WGRAD) {
           if (P.a_mode == 2) {
-            const long long p0 = static_cast<long long>(m_tile) * BM;
-            const int hw = P.hm * P.wm;
-            tile_n0 = static_cast<int>(p0 / hw);
-            const int rem = static_cast<int>(p0 - static_cast<long long>(tile_n0) * hw);
-            const int y0 = rem / P.wm, x0 = rem - y0 * P.wm;
-            tile_w0 = x0 * P.i2c_stride + P.i2c_lo;
-            tile_h0 = y0 * P.i2c_stride + P.i2c_lo;
+            uint32_t tn, rem, y0, x0;
+            P.fd_hw.divmod(static_cast<uint32_t>(m_tile) * BM, tn, rem);
+            P.fd_wm.divmod(rem, y0, x0);
+            tile_n0 = static_cast<int>(tn);
+            tile_w0 = static_cast<int>(x0) * P.i2c_stride + P.i2c_lo;
+            tile_h0 = static_cast<int>(y0) * P.i2c_stride + P.i2c_lo;
           }
         }
-        for (int it = 0; it < nk; ++it, ++cnt) {
-          const int s = static_cast<int>(cnt % nstages);
-          const uint32_t ph = (cnt / nstages) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1u);
+        int tc = 0, cb = 0;                            // fprop/dgrad: visited-tap index, 64-channel block
+        for (int it = 0; it < nk; ++it) {
+          const int s = static_cast<int>(rs);
+          mbar_wait(empty_bar(s), rph ^ 1u);
+          if (++rs == nstages) { rs = 0; rph ^= 1u; }
           const int kb = kb_begin + it;
           if (elect_one()) {
             if constexpr (CTA2 && WGRAD) {
-              // wgrad pairs (UNVERIFIED on hardware, DIRB200_CTA2=3 only): this CTA's BN/2 columns of the dY tile
+              // wgrad pairs: this CTA's BN/2 columns of the dY tile
               if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * C::kBBytes);
 #pragma unroll
               for (int i = 0; i < C::kBRows / 64; ++i)
@@ -439,42 +488,26 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
             } else if constexpr (CTA2) {
               // this CTA's half of the B tile; both halves are accounted on the leader's barrier
               if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * (C::kBBytes + (ATMA ? C::kABytes : 0)));
-              const int tc = kb / P.cpb;
               if constexpr (ATMA) {
-                // ... and this CTA's 128 A rows (UNVERIFIED on hardware: enabled by DIRB200_CTA2=2 only)
-                if (P.a_mode == 1) {
+                // ... and this CTA's 128 A rows
+                if (P.a_mode == 1)
                   tma_load_2d_cta2(a_addr(s), &tmap_a, full_bar(s), kb * BK, m_tile * BM);
-                } else {
-                  const int tp = P.tap_list[tc];
-                  int r = tp / P.kw, sx = tp - r * P.kw;
-                  if (P.transposed) {
-                    r = P.kh - 1 - r;
-                    sx = P.kw - 1 - sx;
-                  }
-                  tma_load_im2col_4d_cta2(a_addr(s), &tmap_a, full_bar(s), (kb - tc * P.cpb) * BK, tile_w0, tile_h0,
-                                          tile_n0, static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
-                }
+                else
+                  tma_load_im2col_4d_cta2(a_addr(s), &tmap_a, full_bar(s), cb * BK, tile_w0, tile_h0, tile_n0,
+                                          P.tap_s[tc], P.tap_r[tc]);
               }
-              const int kcoord = P.tap_list[tc] * P.cpb + (kb - tc * P.cpb);
+              const int kcoord = P.tap_list[tc] * P.cpb + cb;
               tma_load_2d_cta2(b_addr(s), &tmap_b, full_bar(s), kcoord * BK, n0 + static_cast<int>(rank) * C::kBRows);
             } else {
               if constexpr (ATMA) {
                 if constexpr (!WGRAD) {
                   // A tile: 128 pixel rows x 64 channels (rows past the end / padding: zeros)
                   mbar_arrive_expect_tx(full_bar(s), C::kBBytes + C::kABytes);
-                  if (P.a_mode == 1) {
+                  if (P.a_mode == 1)
                     tma_load_2d(a_addr(s), &tmap_a, full_bar(s), kb * BK, m_tile * BM);
-                  } else {
-                    const int tc = kb / P.cpb;
-                    const int tp = P.tap_list[tc];
-                    int r = tp / P.kw, sx = tp - r * P.kw;
-                    if (P.transposed) {               // dgrad: dy pixel (y + pad - r, x + pad - s) = base + (k-1-r, k-1-s)
-                      r = P.kh - 1 - r;
-                      sx = P.kw - 1 - sx;
-                    }
-                    tma_load_im2col_4d(a_addr(s), &tmap_a, full_bar(s), (kb - tc * P.cpb) * BK, tile_w0, tile_h0, tile_n0,
-                                       static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
-                  }
+                  else   // dgrad: dy pixel (y + pad - r, x + pad - s) = base + (k-1-r, k-1-s): flipped in the table
+                    tma_load_im2col_4d(a_addr(s), &tmap_a, full_bar(s), cb * BK, tile_w0, tile_h0, tile_n0,
+                                       P.tap_s[tc], P.tap_r[tc]);
                 } else {
                   // A tile: 64 pixels x (up to) two 64-channel chunks, MN-major like the dY tile
                   const int nchunks = min(2, P.total_chunks - 2 * m_tile);
@@ -484,17 +517,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
                       tma_load_2d(a_addr(s) + i * 8192, &tmap_a, full_bar(s), (2 * m_tile + i) * 64, kb * 64);
                   } else {
                     // the k-block's first pixel -> base pixel; every chunk = (filter tap, 64 channels)
-                    const long long p0 = static_cast<long long>(kb) * 64;
-                    const int hw = P.hm * P.wm;
-                    const int n0i = static_cast<int>(p0 / hw);
-                    const int rem = static_cast<int>(p0 - static_cast<long long>(n0i) * hw);
-                    const int y0 = rem / P.wm, x0 = rem - y0 * P.wm;
+                    uint32_t n0i, rem, y0, x0;
+                    P.fd_hw.divmod(static_cast<uint32_t>(kb) * 64u, n0i, rem);
+                    P.fd_wm.divmod(rem, y0, x0);
                     for (int i = 0; i < nchunks; ++i) {
-                      const int gchunk = 2 * m_tile + i;
-                      const int tap = gchunk / P.cpb;
-                      const int r = tap / P.kw, sx = tap - r * P.kw;
-                      tma_load_im2col_4d(a_addr(s) + i * 8192, &tmap_a, full_bar(s), (gchunk - tap * P.cpb) * 64,
-                                         x0 * P.i2c_stride + P.i2c_lo, y0 * P.i2c_stride + P.i2c_lo, n0i,
+                      uint32_t tap, cbk, r, sx;
+                      P.fd_cpb.divmod(static_cast<uint32_t>(2 * m_tile + i), tap, cbk);
+                      P.fd_kw.divmod(tap, r, sx);
+                      tma_load_im2col_4d(a_addr(s) + i * 8192, &tmap_a, full_bar(s), static_cast<int>(cbk) * 64,
+                                         static_cast<int>(x0) * P.i2c_stride + P.i2c_lo,
+                                         static_cast<int>(y0) * P.i2c_stride + P.i2c_lo, static_cast<int>(n0i),
                                          static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
                     }
                   }
@@ -503,11 +535,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
                 mbar_arrive_expect_tx(full_bar(s), C::kBBytes);
               }
               if constexpr (!WGRAD) {
-                int kcoord = kb;
-                if constexpr (!STEM) {
-                  const int tc = kb / P.cpb;
-                  kcoord = P.tap_list[tc] * P.cpb + (kb - tc * P.cpb);
-                }
+                const int kcoord = STEM ? kb : P.tap_list[tc] * P.cpb + cb;
                 tma_load_2d(b_addr(s), &tmap_b, full_bar(s), kcoord * BK, n0);
               } else {
 #pragma unroll
@@ -515,6 +543,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
                   tma_load_2d(b_addr(s) + i * 8192, &tmap_b, full_bar(s), n0 + 64 * i, kb * 64);
               }
             }
+          }
+          if constexpr (!WGRAD && !STEM) {
+            if (++cb == P.cpb) { cb = 0; ++tc; }
           }
           __syncwarp();
         }
@@ -526,33 +557,34 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
       // pair peer: no MMAs to issue -- relay "my gathered A rows of this stage have landed" to the leader's barrier
       // (nothing to relay when the A rows come by TMA: their bytes are counted on the leader's barrier directly)
       if (lane == 0 && !ATMA) {
-        uint32_t cnt = 0;
-        for (int t = tile_start; t < P.num_tiles; t += tile_stride) {
+        uint32_t rs = 0, rph = 0;
+        for (int t = tile_first; t < tile_end; t += tile_step) {
           int split, m_tile, n_tile, kb_begin, nk;
           decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
-          for (int it = 0; it < nk; ++it, ++cnt) {
-            const int s = static_cast<int>(cnt % nstages);
-            mbar_wait(full_bar(s), (cnt / nstages) & 1);
+          for (int it = 0; it < nk; ++it) {
+            const int s = static_cast<int>(rs);
+            mbar_wait(full_bar(s), rph);
             mbar_arrive_remote(mapa_rank(full_bar(s), 0));
+            if (++rs == nstages) { rs = 0; rph ^= 1u; }
           }
         }
       }
     } else {
       // the whole warp walks the ring (converged: operands stay in uniform registers); one elected lane issues
       constexpr uint32_t idesc = make_idesc(CTA2 ? 2 * BM : BM, BN, WGRAD ? 1 : 0, WGRAD ? 1 : 0);
-      uint32_t cnt = 0, tcount = 0;
+      uint32_t rs = 0, rph = 0, tcount = 0;
       if constexpr (BSTAT) mbar_wait(bstat_bar, 0);
-      for (int t = tile_start; t < P.num_tiles; t += tile_stride, ++tcount) {
+      for (int t = tile_first; t < tile_end; t += tile_step, ++tcount) {
         int split, m_tile, n_tile, kb_begin, nk;
         decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
         const int acc = tcount & 1;
         mbar_wait(tempty_bar(acc), ((tcount >> 1) & 1) ^ 1u);     // epilogue(s) have drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int it = 0; it < nk; ++it, ++cnt) {
-          const int s = static_cast<int>(cnt % nstages);
-          const uint32_t ph = (cnt / nstages) & 1;
-          mbar_wait(full_bar(s), ph);
+        for (int it = 0; it < nk; ++it) {
+          const int s = static_cast<int>(rs);
+          mbar_wait(full_bar(s), rph);
+          if (++rs == nstages) { rs = 0; rph ^= 1u; }
           tcgen05_fence_after();
           // K-major: 8-row atoms 1024 B apart; MN-major: 64-wide chunks 8192 B apart (LBO), 8-k atoms 1024 B (SBO)
           const uint64_t adesc = make_smem_desc(a_addr(s), WGRAD ? 8192u : 16u, 1024u);
@@ -588,7 +620,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32)
     const int row = quarter * 32 + lane;
     uint32_t tcount = 0;
-    for (int t = tile_start; t < P.num_tiles; t += tile_stride, ++tcount) {
+    float stat[WGRAD ? 1 : BN / C::kEpiCols][4] = {};   // BN statistics of this warp's rows (fprop with stat_out)
+    for (int t = tile_first; t < tile_end; t += tile_step, ++tcount) {
       int split, m_tile, n_tile, kb_begin, nk;
       decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
       const int acc = tcount & 1;
@@ -619,7 +652,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           }
           orow8[i] = orow;
         }
-#pragma unroll 1
+#pragma unroll
         for (int cb = 0; cb < BN / C::kEpiCols; ++cb) {
 #pragma unroll
           for (int c = 0; c < C::kEpiCols / 32; ++c) {
@@ -651,6 +684,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
               *reinterpret_cast<uint4*>(out_cols + orow8[i] * P.ldc) = val;
             }
           }
+          if (P.stat_out != nullptr) {
+            // column sums over this warp's 32 rows: lane l owns columns 2l, 2l+1 of the pass (one bf16x2 word per
+            // row; rows past the end of the tensor hold zeros).  Word (36 r + l): conflict-free.
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              uint32_t w;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(stage_base + r * C::kStageRowBytes + lane * 4));
+              const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+              s0 += lo;
+              s1 += hi;
+              q0 = fmaf(lo, lo, q0);
+              q1 = fmaf(hi, hi, q1);
+            }
+            stat[cb][0] += s0;
+            stat[cb][1] += s1;
+            stat[cb][2] += q0;
+            stat[cb][3] += q1;
+          }
           __syncwarp();                                         // staging tile is reused by the next pass / tile
         }
       } else {
@@ -677,6 +729,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
       if (lane == 0) {
         if (CTA2 && rank != 0) mbar_arrive_remote(mapa_rank(tempty_bar(acc), 0));   // the leader issues the MMAs
         else mbar_arrive(tempty_bar(acc));
+      }
+    }
+    if constexpr (!WGRAD) {
+      if (P.stat_out != nullptr && tile_first < tile_end) {
+        // one flush per (CTA, epilogue warp): [row][0][c] = sums, [row][1][c] = sums of squares
+        float* dst = P.stat_out + (static_cast<size_t>(blockIdx.x) * 4 + quarter) * 2 * P.ldc + fixed_n * BN + 2 * lane;
+#pragma unroll
+        for (int cb = 0; cb < BN / C::kEpiCols; ++cb) {
+          *reinterpret_cast<float2*>(dst + cb * C::kEpiCols) = make_float2(stat[cb][0], stat[cb][1]);
+          *reinterpret_cast<float2*>(dst + P.ldc + cb * C::kEpiCols) = make_float2(stat[cb][2], stat[cb][3]);
+        }
       }
     }
   }
@@ -773,9 +836,44 @@ int make_tmap_im2col_bf16(CUtensorMap* tm, const void* ptr, int c, int w, int h,
   return DIRB200_OK;
 }
 
+static thread_local int t_last_grid = 0;     // CTAs of the most recent igemm launch of this thread
+
+// Host-side completion of the launch parameters: reciprocal constants for every run-time divisor the kernel meets and
+// the per-tap tables (gather offset, im2col offsets) indexed by the position in tap_list.
+static IgemmParams finish_params(const IgemmParams& P) {
+  IgemmParams Q = P;
+  Q.fd_hw = make_fastdiv(static_cast<uint32_t>(Q.hm * Q.wm));
+  Q.fd_wm = make_fastdiv(static_cast<uint32_t>(Q.wm));
+  Q.fd_cpb = make_fastdiv(static_cast<uint32_t>(Q.cpb > 0 ? Q.cpb : 1));
+  Q.fd_kw = make_fastdiv(static_cast<uint32_t>(Q.kw > 0 ? Q.kw : 1));
+  Q.fd_ntiles = make_fastdiv(static_cast<uint32_t>(Q.n_tiles > 0 ? Q.n_tiles : 1));
+  Q.fd_persplit = make_fastdiv(static_cast<uint32_t>(Q.m_tiles * Q.n_tiles > 0 ? Q.m_tiles * Q.n_tiles : 1));
+  const int nt = Q.ntaps_c < 9 ? Q.ntaps_c : 9;
+  for (int i = 0; i < 9; ++i) {
+    Q.tap_eoff[i] = 0;
+    Q.tap_r[i] = Q.tap_s[i] = 0;
+  }
+  for (int i = 0; i < nt && Q.kw > 0; ++i) {
+    const int tp = Q.tap_list[i];
+    int r = tp / Q.kw, sx = tp - r * Q.kw;
+    if (Q.transposed) {
+      Q.tap_r[i] = static_cast<unsigned short>(Q.kh - 1 - r);
+      Q.tap_s[i] = static_cast<unsigned short>(Q.kw - 1 - sx);
+      if (Q.stride == 2) { r >>= 1; sx >>= 1; }
+      Q.tap_eoff[i] = -static_cast<long long>(r * Q.ws + sx) * Q.cs;
+    } else {
+      Q.tap_r[i] = static_cast<unsigned short>(r);
+      Q.tap_s[i] = static_cast<unsigned short>(sx);
+      Q.tap_eoff[i] = static_cast<long long>(r * Q.ws + sx) * Q.cs;
+    }
+  }
+  return Q;
+}
+
 template <int BN, bool WGRAD, bool STEM, bool BSTAT, bool ATMA = false>
-static int launch_igemm_impl(const CUtensorMap& tm, const CUtensorMap& tma, const IgemmParams& Q, cudaStream_t st) {
+static int launch_igemm_impl(const CUtensorMap& tm, const CUtensorMap& tma, const IgemmParams& Qin, cudaStream_t st) {
   using C = Cfg<BN, !WGRAD>;
+  const IgemmParams Q = finish_params(Qin);
   static bool configured = false;
   if (!configured) {
     DIRB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, WGRAD, STEM, BSTAT, false, ATMA>,
@@ -783,6 +881,7 @@ static int launch_igemm_impl(const CUtensorMap& tm, const CUtensorMap& tma, cons
     configured = true;
   }
   const int grid = Q.num_tiles < num_sms() ? Q.num_tiles : num_sms();
+  t_last_grid = grid;
   igemm_kernel<BN, WGRAD, STEM, BSTAT, false, ATMA><<<grid, kThreads, C::kSmemBytes, st>>>(tm, tma, Q);
   DIRB_LAUNCHED();
   return DIRB200_OK;
@@ -790,8 +889,9 @@ static int launch_igemm_impl(const CUtensorMap& tm, const CUtensorMap& tma, cons
 
 // CTA-pair variant: (2,1,1) clusters, one pair per two SMs; Q.m_tiles / Q.num_tiles count 256-row pair tiles.
 template <int BN, bool ATMA = false, bool WGRAD = false>
-static int launch_igemm_cta2(const CUtensorMap& tm, const CUtensorMap& tma, const IgemmParams& Q, cudaStream_t st) {
+static int launch_igemm_cta2(const CUtensorMap& tm, const CUtensorMap& tma, const IgemmParams& Qin, cudaStream_t st) {
   using C = Cfg<BN, !WGRAD, true>;
+  const IgemmParams Q = finish_params(Qin);
   auto kern = igemm_kernel<BN, WGRAD, false, false, true, ATMA>;
   static bool configured = false;
   if (!configured) {
@@ -824,51 +924,33 @@ static int launch_igemm_cta2(const CUtensorMap& tm, const CUtensorMap& tma, cons
   }
   const int pairs = Q.num_tiles < max_pairs ? Q.num_tiles : max_pairs;
   cfg.gridDim = dim3(2 * pairs, 1, 1);
+  t_last_grid = 2 * pairs;
   DIRB_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, tma, Q));
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
 
-// DIRB200_CTA2=1 routes the fprop / dgrad GEMMs with BN >= 128 through CTA pairs (tcgen05 cta_group::2), A operand by
-// the cp.async gather (validated on B200).  DIRB200_CTA2=2 additionally feeds the pairs' A operand by TMA wherever
-// the single-CTA path would (tiled for plain GEMMs, im2col with DIRB200_IM2COL=1) -- the canonical 2-SM pipeline;
-// written after the round's GPU budget was spent: compiles, NOT yet run on hardware, never selected by default.
-// DIRB200_CTA2=3 = mode 2 plus CTA pairs for the wgrad GEMMs (gather-fed A, relay as in mode 1) -- same status as
-// mode 2: compiles, not yet run on hardware.
-static int cta2_mode() {
-  static const int mode = [] {
+// CTA pairs (tcgen05 cta_group::2, 256 x 256 pair tiles, both operands by TMA) carry the fprop / stride-1 dgrad GEMMs
+// whose tile is 256 wide and at least 4 k-blocks deep: each CTA then stages 32 KB instead of 48 KB per k-block, and
+// those layers run at the L2->SM delivery limit (measured, profiles/r2_conv_layers.md: 5-15 % faster; shallower or
+// narrower GEMMs are epilogue / DRAM bound and lose a little to the cluster handshakes).  DIRB200_CTA2=0 disables.
+static bool pairs_enabled() {
+  static const bool on = [] {
     const char* e = getenv("DIRB200_CTA2");
-    return (e != nullptr && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 0;
+    return !(e != nullptr && e[0] == '0');
   }();
-  return mode;
+  return on;
 }
-static bool cta2_enabled() { return cta2_mode() != 0; }
 
 // tma != nullptr: the A operand is a plain [pixels][channels] matrix (1x1 stride-1 conv) and is loaded by TMA too
 template <int BN, bool WGRAD, bool STEM>
 static int launch_igemm(const CUtensorMap& tm, const IgemmParams& P, int m_tiles, int splits, cudaStream_t st,
                         const CUtensorMap* tma = nullptr) {
-  using C = Cfg<BN, !WGRAD>;
   IgemmParams Q = P;
   Q.m_tiles = m_tiles;
   Q.num_tiles = m_tiles * P.n_tiles * splits;
   if constexpr (!STEM) {
     if (tma) return launch_igemm_impl<BN, WGRAD, false, false, true>(tm, *tma, Q, st);
-  }
-  if constexpr (!WGRAD) {
-    // B stationary when one N tile covers the layer, the weights fit beside the A ring and there are enough
-    // tiles per CTA to amortise the one-off load
-    const int bbytes = P.num_kblocks * C::kBBytes;
-    int ns = (C::kBarOffset - bbytes) / C::kABytes;
-    if (ns > C::kStages) ns = C::kStages;
-    static const bool bstat_enabled = [] {
-      const char* e = getenv("DIRB200_BSTAT");
-      return e != nullptr && e[0] == '1';     // off by default: measured 3 % slower on ResNet-50 (L2 is not the limiter there)
-    }();
-    if (bstat_enabled && P.n_tiles == 1 && ns >= 4 && Q.num_tiles >= 4 * num_sms()) {
-      Q.nstages = ns;
-      return launch_igemm_impl<BN, false, STEM, true>(tm, tm, Q, st);
-    }
   }
   return launch_igemm_impl<BN, WGRAD, STEM, false>(tm, tm, Q, st);
 }
@@ -914,31 +996,41 @@ static bool atma_enabled() {
 static bool is_plain_gemm(const ConvShape& s, bool stem) {
   return !stem && s.kh == 1 && s.kw == 1 && s.stride == 1 && s.pad == 0 && atma_enabled();
 }
-// DIRB200_IM2COL=1: every other non-stem conv (3x3, strided) takes its A operand through im2col-mode TMA
-// (fprop, stride-1 dgrad, wgrad); the stride-2 dgrad parity classes and the stem keep the cp.async gather.
+// Every other non-stem conv (3x3, strided) takes its A operand through im2col-mode TMA (fprop, stride-1 dgrad, wgrad);
+// the stride-2 dgrad parity classes and the stem keep the cp.async gather.  DIRB200_IM2COL=0: gather for those too.
 static bool im2col_enabled() {
   static const bool on = [] {
     const char* e = getenv("DIRB200_IM2COL");
-    return e != nullptr && e[0] == '1';
+    return !(e != nullptr && e[0] == '0');
   }();
   return on && atma_enabled();
 }
 
 // CTA-pair launch of an fprop / dgrad GEMM: B = wmat [n_dim][ktot] (K-major), each CTA TMA-loads bn/2 of its rows.
-static int launch_cta2(const __nv_bfloat16* wmat, int ktot, int n_dim, int bn, const IgemmParams& P, int m_tiles,
-                       cudaStream_t st, const CUtensorMap* tma = nullptr) {
+static int launch_cta2(const __nv_bfloat16* wmat, int ktot, int n_dim, const IgemmParams& P, int m_tiles,
+                       cudaStream_t st, const CUtensorMap& tma) {
   CUtensorMap tm;
-  if (int rc = make_tmap_bf16_2d(&tm, wmat, ktot, n_dim, static_cast<uint64_t>(ktot) * 2, bn / 2)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tm, wmat, ktot, n_dim, static_cast<uint64_t>(ktot) * 2, 128)) return rc;
   IgemmParams Q = P;
   Q.m_tiles = (m_tiles + 1) / 2;                 // 256-row pair tiles
   Q.num_tiles = Q.m_tiles * P.n_tiles;
-  if (tma) return bn == 256 ? launch_igemm_cta2<256, true>(tm, *tma, Q, st) : launch_igemm_cta2<128, true>(tm, *tma, Q, st);
-  return bn == 256 ? launch_igemm_cta2<256>(tm, tm, Q, st) : launch_igemm_cta2<128>(tm, tm, Q, st);
+  return launch_igemm_cta2<256, true>(tm, tma, Q, st);
 }
+static bool want_pairs(int bn, int num_kblocks) { return pairs_enabled() && bn == 256 && num_kblocks >= 4; }
 
 // Y[n,ho,wo,cout] = conv(X[n,h,w,cin], W[cout][kh][kw][cin])
+static int conv_fprop_impl(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, const ConvShape& s, bool stem,
+                           cudaStream_t st, float* stat_partial);
+
 int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, const ConvShape& s, bool stem,
-               cudaStream_t st) {
+               cudaStream_t st, float* stat_partial, int* stat_rows) {
+  const int rc = conv_fprop_impl(x, w, y, s, stem, st, stat_partial);
+  if (stat_rows) *stat_rows = 4 * t_last_grid;    // one partial row per (CTA, epilogue warp)
+  return rc;
+}
+
+static int conv_fprop_impl(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, const ConvShape& s, bool stem,
+                           cudaStream_t st, float* stat_partial) {
   if (int rc = check_shape(s, stem, "conv_fprop")) return rc;
   const int ktot = s.kh * s.kw * s.cin;
   IgemmParams P{};
@@ -951,44 +1043,28 @@ int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y,
   DIRB_CHECK_ARG(stem || P.ntaps_c <= 9, "conv_fprop: at most 9 filter taps (got %dx%d)", s.kh, s.kw);
   for (int i = 0; i < 9; ++i) P.tap_list[i] = i;
   P.ldc = s.cout; P.out = y;
+  P.stat_out = stat_partial;
   const int m_tiles = static_cast<int>((P.pixels + BM - 1) / BM);
   const int bn = pick_bn(s.cout, m_tiles, !is_plain_gemm(s, stem));
   P.n_tiles = s.cout / bn;
-  CUtensorMap tm;
-  if (!stem && bn >= 128 && cta2_enabled()) {
-    if (cta2_mode() >= 2 && (is_plain_gemm(s, stem) || im2col_enabled())) {      // pairs with a TMA-fed A operand
-      CUtensorMap ta;
-      if (is_plain_gemm(s, stem)) {
-        if (int rc = make_tmap_bf16_2d(&ta, x, s.cin, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cin) * 2, BM))
-          return rc;
-        P.a_mode = 1;
-      } else {
-        if (int rc = make_tmap_im2col_bf16(&ta, x, s.cin, s.w, s.h, s.n, -s.pad, -s.pad, s.pad - (s.kw - 1),
-                                           s.pad - (s.kh - 1), s.stride, BM))
-          return rc;
-        P.a_mode = 2; P.i2c_stride = s.stride; P.i2c_lo = -s.pad;
-      }
-      return launch_cta2(w, ktot, s.cout, bn, P, m_tiles, st, &ta);
-    }
-    return launch_cta2(w, ktot, s.cout, bn, P, m_tiles, st);
-  }
-  if (int rc = make_tmap_bf16_2d(&tm, w, ktot, s.cout, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
-  if (stem) return DISPATCH_BN(bn, false, true, tm, P, m_tiles, 1, st);
-  if (is_plain_gemm(s, stem)) {
-    CUtensorMap ta;     // x as [pixels][cin]
+  CUtensorMap tm, ta;
+  bool tma_fed = false;
+  if (is_plain_gemm(s, stem)) {         // x as [pixels][cin]
     if (int rc = make_tmap_bf16_2d(&ta, x, s.cin, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cin) * 2, BM))
       return rc;
     P.a_mode = 1;
-    return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st, &ta);
-  }
-  if (im2col_enabled()) {
-    CUtensorMap ta;     // x [n,h,w,cin], base pixel (ho*stride - pad, wo*stride - pad)
+    tma_fed = true;
+  } else if (!stem && im2col_enabled()) {   // x [n,h,w,cin], base pixel (ho*stride - pad, wo*stride - pad)
     if (int rc = make_tmap_im2col_bf16(&ta, x, s.cin, s.w, s.h, s.n, -s.pad, -s.pad, s.pad - (s.kw - 1),
                                        s.pad - (s.kh - 1), s.stride, BM))
       return rc;
     P.a_mode = 2; P.i2c_stride = s.stride; P.i2c_lo = -s.pad;
-    return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st, &ta);
+    tma_fed = true;
   }
+  if (tma_fed && want_pairs(bn, P.num_kblocks)) return launch_cta2(w, ktot, s.cout, P, m_tiles, st, ta);
+  if (int rc = make_tmap_bf16_2d(&tm, w, ktot, s.cout, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
+  if (stem) return DISPATCH_BN(bn, false, true, tm, P, m_tiles, 1, st);
+  if (tma_fed) return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st, &ta);
   return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st);
 }
 
@@ -1013,39 +1089,24 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
     const int m_tiles = static_cast<int>((P.pixels + BM - 1) / BM);
     const int bn = pick_bn(s.cin, m_tiles, !is_plain_gemm(s, false));
     P.n_tiles = s.cin / bn;
-    if (bn >= 128 && cta2_enabled()) {
-      if (cta2_mode() >= 2 && (is_plain_gemm(s, false) || (im2col_enabled() && s.kh == s.kw))) {
-        CUtensorMap ta;
-        if (is_plain_gemm(s, false)) {
-          if (int rc = make_tmap_bf16_2d(&ta, dy, s.cout, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cout) * 2, BM))
-            return rc;
-          P.a_mode = 1;
-        } else {
-          const int lo = s.pad - (s.kh - 1);
-          if (int rc = make_tmap_im2col_bf16(&ta, dy, s.cout, s.wo, s.ho, s.n, lo, lo, lo + s.w - s.wo, lo + s.h - s.ho, 1, BM))
-            return rc;
-          P.a_mode = 2; P.i2c_stride = 1; P.i2c_lo = lo;
-        }
-        return launch_cta2(wt, ktot, s.cin, bn, P, m_tiles, st, &ta);
-      }
-      return launch_cta2(wt, ktot, s.cin, bn, P, m_tiles, st);
-    }
-    if (int rc = make_tmap_bf16_2d(&tm, wt, ktot, s.cin, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
-    if (is_plain_gemm(s, false)) {
-      CUtensorMap ta;   // dy as [pixels][cout]
+    CUtensorMap ta;
+    bool tma_fed = false;
+    if (is_plain_gemm(s, false)) {      // dy as [pixels][cout]
       if (int rc = make_tmap_bf16_2d(&ta, dy, s.cout, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cout) * 2, BM))
         return rc;
       P.a_mode = 1;
-      return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st, &ta);
-    }
-    if (im2col_enabled() && s.kh == s.kw) {
-      CUtensorMap ta;   // dy [n,ho,wo,cout], base pixel (y + pad - (k-1), x + pad - (k-1)), tap offsets reversed
+      tma_fed = true;
+    } else if (im2col_enabled() && s.kh == s.kw) {
+      // dy [n,ho,wo,cout], base pixel (y + pad - (k-1), x + pad - (k-1)), tap offsets reversed
       const int lo = s.pad - (s.kh - 1);
       if (int rc = make_tmap_im2col_bf16(&ta, dy, s.cout, s.wo, s.ho, s.n, lo, lo, lo + s.w - s.wo, lo + s.h - s.ho, 1, BM))
         return rc;
       P.a_mode = 2; P.i2c_stride = 1; P.i2c_lo = lo;
-      return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st, &ta);
+      tma_fed = true;
     }
+    if (tma_fed && want_pairs(bn, P.num_kblocks)) return launch_cta2(wt, ktot, s.cin, P, m_tiles, st, ta);
+    if (int rc = make_tmap_bf16_2d(&tm, wt, ktot, s.cin, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
+    if (tma_fed) return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st, &ta);
     return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st);
   }
   // stride 2: one launch per output-pixel parity class; a class without any tap receives no gradient (zeros)
@@ -1075,10 +1136,6 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
     const int m_tiles = static_cast<int>((Q.pixels + BM - 1) / BM);
     const int bn = pick_bn(s.cin, m_tiles, true);
     Q.n_tiles = s.cin / bn;
-    if (bn >= 128 && cta2_enabled()) {
-      if (int rc = launch_cta2(wt, ktot, s.cin, bn, Q, m_tiles, st)) return rc;
-      continue;
-    }
     if (int rc = make_tmap_bf16_2d(&tm, wt, ktot, s.cin, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
     if (int rc = DISPATCH_BN(bn, false, false, tm, Q, m_tiles, 1, st)) return rc;
   }
@@ -1096,10 +1153,9 @@ int conv_wgrad_splits(const ConvShape& s) {
   const int kblocks = static_cast<int>((pixels + 63) / 64);
   const int chunks = s.kh * s.kw * s.cin / 64;
   const int bn = wgrad_bn(s);
-  const bool pairs = cta2_mode() == 3 && bn >= 128;     // work items are 256-row pair tiles on SM pairs
   const int m_tiles = (chunks + 1) / 2;
-  const int tiles = (pairs ? (m_tiles + 1) / 2 : m_tiles) * (s.cout / bn);
-  const int sms = pairs ? num_sms() / 2 : num_sms();
+  const int tiles = m_tiles * (s.cout / bn);
+  const int sms = num_sms();
   int max_splits = (kblocks + 7) / 8;                   // at least 8 k-blocks per split
   if (max_splits < 1) max_splits = 1;
   int hi = (4 * sms + tiles - 1) / tiles;
@@ -1146,12 +1202,6 @@ int conv_wgrad_partials(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
   if (int rc = make_tmap_bf16_2d(&tm, dy, s.cout, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cout) * 2, 64))
     return rc;
   if (stem) return DISPATCH_BN(bn, true, true, tm, P, m_tiles, splits, st);
-  if (cta2_mode() == 3 && bn >= 128) {                  // wgrad pairs, gather-fed A
-    IgemmParams Q = P;
-    Q.m_tiles = (m_tiles + 1) / 2;
-    Q.num_tiles = Q.m_tiles * P.n_tiles * splits;
-    return bn == 256 ? launch_igemm_cta2<256, false, true>(tm, tm, Q, st) : launch_igemm_cta2<128, false, true>(tm, tm, Q, st);
-  }
   if (is_plain_gemm(s, stem)) {
     CUtensorMap ta;     // x as [pixels][cin], 64-pixel x 64-channel boxes
     if (int rc = make_tmap_bf16_2d(&ta, x, s.cin, static_cast<uint64_t>(P.pixels), static_cast<uint64_t>(s.cin) * 2, 64))

@@ -6,23 +6,27 @@ namespace dirb200 {
 
 int bn_partial_floats(int max_c);   // size of the per-CTA partial buffer shared by the column reductions
 int bn_stats(const __nv_bfloat16* y, int64_t rows, int c, float* partial, int* nblocks, cudaStream_t st);
-int bn_finalize(const float* partial, int nblocks, int64_t rows, int c, const float* gamma, const float* beta,
+// clear: zero every partial once read (partials written by the conv fprop epilogue, see IgemmParams::stat_out)
+int bn_finalize(float* partial, int nblocks, bool clear, int64_t rows, int c, const float* gamma, const float* beta,
                 float eps, float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
                 float* scale, float* shift, cudaStream_t st);
 int bn_eval_coeffs(int c, const float* gamma, const float* beta, float eps, const float* running_mean,
                    const float* running_var, float* scale, float* shift, cudaStream_t st);
+// mask_out (optional): [rows][c/8] bytes, bit j of byte (r, cg) = out[r][cg*8+j] > 0
 int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, const __nv_bfloat16* res,
              const __nv_bfloat16* res_y, const float* res_scale, const float* res_shift, bool relu, int64_t rows, int c,
-             __nv_bfloat16* out, cudaStream_t st);
-int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* act, const __nv_bfloat16* y,
-                  const float* mean, const float* invstd, const __nv_bfloat16* y2, const float* mean2,
-                  const float* invstd2, int64_t rows, int c, float* partial, int* nblocks, cudaStream_t st);
+             __nv_bfloat16* out, uint8_t* mask_out, cudaStream_t st);
+// BN backward, ReLU mask from (y, scale, shift) when mask == nullptr, else from the stored bit mask
+int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* y, const __nv_bfloat16* y2,
+                  const float* scale, const float* shift, const uint8_t* mask, int64_t rows, int c, float* partial,
+                  int* nblocks, cudaStream_t st);
 int bn_bwd_coeffs(const float* partial, int nblocks, int k, int gslot, int64_t rows, int c, const float* mean,
                   const float* invstd, const float* gamma, float* grad_gamma, float* grad_beta, float* coef,
                   cudaStream_t st);
-int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* act, const __nv_bfloat16* y,
-                 const float* coef, const __nv_bfloat16* y2, const float* coef2, int64_t rows, int c,
-                 __nv_bfloat16* dy, __nv_bfloat16* dy2, __nv_bfloat16* dz_out, cudaStream_t st);
+int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* y, const float* coef,
+                 const __nv_bfloat16* y2, const float* coef2, const float* scale, const float* shift,
+                 const uint8_t* mask, int64_t rows, int c, __nv_bfloat16* dy, __nv_bfloat16* dy2,
+                 __nv_bfloat16* dz_out, cudaStream_t st);
 int maxpool_fwd(const __nv_bfloat16* x, int n, int h, int w, int c, __nv_bfloat16* out, uint8_t* idx, cudaStream_t st);
 int maxpool_bwd(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const uint8_t* idx, int n, int h, int w, int c,
                 __nv_bfloat16* dx, cudaStream_t st);

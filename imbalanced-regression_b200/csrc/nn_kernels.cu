@@ -71,24 +71,32 @@ __device__ __forceinline__ void column_reduce_finish(float (&acc)[K][8], int cg,
 // both slots are fetched in the same pass so that four independent loads are in flight per thread (these tiny
 // kernels sit on the critical path between two streaming kernels, 106 times per step: pure latency).
 // Valid in threads with threadIdx.y == 0 after the call.
-__device__ __forceinline__ void sum_partials2(const float* __restrict__ partial, int nblocks, int K, int s0, int s1,
+// CLEAR: every value is replaced by zero once read (the fprop epilogue only writes the rows / columns its CTAs own
+// and relies on the rest of the buffer being zero).
+template <bool CLEAR = false>
+__device__ __forceinline__ void sum_partials2(float* __restrict__ partial, int nblocks, int K, int s0, int s1,
                                               int c, int ch, double (*sh)[32], double& r0, double& r1) {
   double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
   if (ch < c) {
     int b = threadIdx.y;
     for (; b + 32 < nblocks; b += 64) {
-      const float x0 = partial[((size_t)b * K + s0) * c + ch];
-      const float y0 = partial[((size_t)b * K + s1) * c + ch];
-      const float x1 = partial[((size_t)(b + 32) * K + s0) * c + ch];
-      const float y1 = partial[((size_t)(b + 32) * K + s1) * c + ch];
+      float* p00 = partial + ((size_t)b * K + s0) * c + ch;
+      float* p01 = partial + ((size_t)b * K + s1) * c + ch;
+      float* p10 = partial + ((size_t)(b + 32) * K + s0) * c + ch;
+      float* p11 = partial + ((size_t)(b + 32) * K + s1) * c + ch;
+      const float x0 = *p00, y0 = *p01, x1 = *p10, y1 = *p11;
+      if (CLEAR) { *p00 = 0.f; *p01 = 0.f; *p10 = 0.f; *p11 = 0.f; }
       a0 += (double)x0;
       b0 += (double)y0;
       a1 += (double)x1;
       b1 += (double)y1;
     }
     if (b < nblocks) {
-      a0 += (double)partial[((size_t)b * K + s0) * c + ch];
-      b0 += (double)partial[((size_t)b * K + s1) * c + ch];
+      float* p00 = partial + ((size_t)b * K + s0) * c + ch;
+      float* p01 = partial + ((size_t)b * K + s1) * c + ch;
+      a0 += (double)*p00;
+      b0 += (double)*p01;
+      if (CLEAR) { *p00 = 0.f; *p01 = 0.f; }
     }
   }
   sh[threadIdx.y][threadIdx.x] = a0 + a1;
@@ -138,7 +146,8 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ y, int64_t rows, int c, float*
 
 // mean / invstd / scale / shift from the accumulated sums; running statistics as nn.BatchNorm2d (momentum 0.1,
 // unbiased running variance).
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblocks, int64_t rows, int c,
+template <bool CLEAR>
+__global__ void bn_finalize_kernel(float* __restrict__ partial, int nblocks, int64_t rows, int c,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean_out, float* __restrict__ invstd_out,
@@ -146,7 +155,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblock
   __shared__ double sh[32][32];
   const int i = blockIdx.x * 32 + threadIdx.x;
   double sx, sq;
-  sum_partials2(partial, nblocks, 2, 0, 1, c, i, sh, sx, sq);
+  sum_partials2<CLEAR>(partial, nblocks, 2, 0, 1, c, i, sh, sx, sq);
   if (threadIdx.y != 0 || i >= c) return;
   const double n = (double)rows;
   const double m = sx / n;
@@ -184,11 +193,13 @@ __device__ __forceinline__ uint32_t f2_to_bf2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// mask_out (block outputs only): one byte per (row, channel group): bit j = out[row][cg*8 + j] > 0 -- the ReLU mask
+// the backward kernels need, 1/16 of the size of `out`.
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                 const __nv_bfloat16* __restrict__ res, const __nv_bfloat16* __restrict__ res_y,
                 const float* __restrict__ res_scale, const float* __restrict__ res_shift, int relu, int64_t rows,
-                int c, __nv_bfloat16* __restrict__ out) {
+                int c, __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ mask_out) {
   const int cgroups = c / 8;
   const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
   const V8 sc = loadf8(scale + cg * 8), sh = loadf8(shift + cg * 8);
@@ -206,6 +217,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
     if (res_y) RY = *reinterpret_cast<const uint4*>(res_y + off);
     const uint32_t yw[4] = {Y.x, Y.y, Y.z, Y.w}, rw[4] = {R.x, R.y, R.z, R.w}, ryw[4] = {RY.x, RY.y, RY.z, RY.w};
     uint32_t ow[4];
+    uint32_t bits = 0;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const float2 yv = bf2_to_f2(yw[w]);
@@ -225,68 +237,113 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
         b = fmaxf(b, 0.f);
       }
       ow[w] = f2_to_bf2(a, b);
+      // the stored (bf16-rounded) value > 0  <=>  magnitude bits non-zero after the ReLU
+      bits |= ((ow[w] & 0x00007fffu) ? 1u : 0u) << (2 * w);
+      bits |= ((ow[w] & 0x7fff0000u) ? 1u : 0u) << (2 * w + 1);
     }
     *reinterpret_cast<uint4*>(out + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    if (mask_out) mask_out[r * cgroups + cg] = static_cast<uint8_t>(bits);
   }
 }
 
-// ---- backward.  dz = (g1 [+ g2]) * (act > 0).  The reduction accumulates the raw moments
-//   S0 = sum dz,  S1 = sum dz*y  [, S2 = sum dz*y2 for the downsample-branch BN that shares dz];
-// dbeta = S0 and dgamma = invstd * (S1 - mean*S0) are formed in fp64 by bn_bwd_coeffs_kernel.  Keeping mean/invstd
-// out of the streaming loop keeps the kernel within 64 registers (no local-memory spills: the first version was
-// L1-bound on spill traffic, ncu profiles/).
-__global__ void __launch_bounds__(256, 4)
+// ---- backward.  dz = (g1 [+ g2]) * relu_mask.  The mask is never read from an activation tensor:
+//   MASK_FROM_Y  (conv -> BN -> ReLU):       mask = (y*scale + shift > 0), the same fmaf the forward evaluated, so the
+//                                            activation `a` is not touched by the backward pass at all;
+//   MASK_BITS    (block output, BN + residual + ReLU):  the 1-bit-per-element mask bn_apply stored.
+// The reduction accumulates the raw moments  S0 = sum dz,  S1 = sum dz*y  [, S2 = sum dz*y2 for the downsample-branch
+// BN that shares dz]; dbeta = S0 and dgamma = invstd * (S1 - mean*S0) are formed in fp64 by bn_bwd_coeffs_kernel.
+enum { MASK_FROM_Y = 0, MASK_BITS = 1 };
+
+template <int MODE>
+struct MaskSrc {
+  V8 sc, sh;                 // MASK_FROM_Y
+  const uint8_t* bits;       // MASK_BITS
+  int cgroups, cg;
+  __device__ __forceinline__ void init(const float* scale, const float* shift, const uint8_t* b, int cgroups_, int cg_) {
+    cgroups = cgroups_;
+    cg = cg_;
+    bits = b;
+    if (MODE == MASK_FROM_Y) {
+      sc = loadf8(scale + cg * 8);
+      sh = loadf8(shift + cg * 8);
+    }
+  }
+  __device__ __forceinline__ uint32_t load(int64_t r) const { return MODE == MASK_BITS ? bits[r * cgroups + cg] : 0u; }
+  // keep-mask of channel pair w given the raw conv output pair yv
+  __device__ __forceinline__ void apply(uint32_t m, int w, const float2& yv, float2& g) const {
+    if (MODE == MASK_FROM_Y) {
+      if (!(fmaf(yv.x, sc.v[2 * w], sh.v[2 * w]) > 0.f)) g.x = 0.f;
+      if (!(fmaf(yv.y, sc.v[2 * w + 1], sh.v[2 * w + 1]) > 0.f)) g.y = 0.f;
+    } else {
+      if (!((m >> (2 * w)) & 1u)) g.x = 0.f;
+      if (!((m >> (2 * w + 1)) & 1u)) g.y = 0.f;
+    }
+  }
+};
+
+template <int MODE, bool HAS_G2, bool HAS_Y2>
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
-                     const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ y,
-                     const __nv_bfloat16* __restrict__ y2, int64_t rows, int c, float* __restrict__ partial) {
+                     const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ y2,
+                     const float* __restrict__ scale, const float* __restrict__ shift,
+                     const uint8_t* __restrict__ mask, int64_t rows, int c, float* __restrict__ partial) {
   const int cgroups = c / 8;
   const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
-  float acc[3][8] = {};
+  constexpr int K = HAS_Y2 ? 3 : 2;
+  float acc[K][8] = {};
+  MaskSrc<MODE> ms;
+  ms.init(scale, shift, mask, cgroups, cg);
   const int64_t stride = (int64_t)gridDim.x * lanes;
-  for (int64_t r = blockIdx.x * (int64_t)lanes + lane; r < rows; r += stride) {
-    const int64_t off = r * c + cg * 8;
-    const uint4 G = *reinterpret_cast<const uint4*>(g1 + off);
-    const uint4 Y = *reinterpret_cast<const uint4*>(y + off);
-    uint4 G2 = make_uint4(0, 0, 0, 0), A = make_uint4(0, 0, 0, 0), Y2 = make_uint4(0, 0, 0, 0);
-    if (g2) G2 = *reinterpret_cast<const uint4*>(g2 + off);
-    if (act) A = *reinterpret_cast<const uint4*>(act + off);
-    if (y2) Y2 = *reinterpret_cast<const uint4*>(y2 + off);
-    const uint32_t gw[4] = {G.x, G.y, G.z, G.w}, g2w[4] = {G2.x, G2.y, G2.z, G2.w}, aw[4] = {A.x, A.y, A.z, A.w};
-    const uint32_t yw[4] = {Y.x, Y.y, Y.z, Y.w}, y2w[4] = {Y2.x, Y2.y, Y2.z, Y2.w};
+  // two rows per iteration: every load of both rows is issued before the first use
+  for (int64_t r0 = blockIdx.x * (int64_t)lanes + lane; r0 < rows; r0 += 2 * stride) {
+    const int64_t r1 = r0 + stride;
+    const bool two = r1 < rows;
+    const int64_t o0 = r0 * c + cg * 8, o1 = (two ? r1 : r0) * c + cg * 8;
+    uint4 G[2], Y[2], G2[2], Y2[2];
+    uint32_t M[2];
+    G[0] = *reinterpret_cast<const uint4*>(g1 + o0);
+    G[1] = *reinterpret_cast<const uint4*>(g1 + o1);
+    Y[0] = *reinterpret_cast<const uint4*>(y + o0);
+    Y[1] = *reinterpret_cast<const uint4*>(y + o1);
+    if (HAS_G2) {
+      G2[0] = *reinterpret_cast<const uint4*>(g2 + o0);
+      G2[1] = *reinterpret_cast<const uint4*>(g2 + o1);
+    }
+    if (HAS_Y2) {
+      Y2[0] = *reinterpret_cast<const uint4*>(y2 + o0);
+      Y2[1] = *reinterpret_cast<const uint4*>(y2 + o1);
+    }
+    M[0] = ms.load(r0);
+    M[1] = ms.load(two ? r1 : r0);
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      float2 g = bf2_to_f2(gw[w]);
-      if (g2) {
-        const float2 t = bf2_to_f2(g2w[w]);
-        g.x += t.x;
-        g.y += t.y;
-      }
-      if (act) {   // relu output > 0  <=>  magnitude bits non-zero (handles -0)
-        if ((aw[w] & 0x00007fffu) == 0u) g.x = 0.f;
-        if ((aw[w] & 0x7fff0000u) == 0u) g.y = 0.f;
-      }
-      const float2 yv = bf2_to_f2(yw[w]);
-      acc[0][2 * w] += g.x;
-      acc[0][2 * w + 1] += g.y;
-      acc[1][2 * w] = fmaf(g.x, yv.x, acc[1][2 * w]);
-      acc[1][2 * w + 1] = fmaf(g.y, yv.y, acc[1][2 * w + 1]);
-      if (y2) {
-        const float2 y2v = bf2_to_f2(y2w[w]);
-        acc[2][2 * w] = fmaf(g.x, y2v.x, acc[2][2 * w]);
-        acc[2][2 * w + 1] = fmaf(g.y, y2v.y, acc[2][2 * w + 1]);
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      const uint32_t gw[4] = {G[u].x, G[u].y, G[u].z, G[u].w}, yw[4] = {Y[u].x, Y[u].y, Y[u].z, Y[u].w};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        float2 g = bf2_to_f2(gw[w]);
+        if (HAS_G2) {
+          const uint32_t g2w[4] = {G2[u].x, G2[u].y, G2[u].z, G2[u].w};
+          const float2 t = bf2_to_f2(g2w[w]);
+          g.x += t.x;
+          g.y += t.y;
+        }
+        const float2 yv = bf2_to_f2(yw[w]);
+        ms.apply(M[u], w, yv, g);
+        acc[0][2 * w] += g.x;
+        acc[0][2 * w + 1] += g.y;
+        acc[1][2 * w] = fmaf(g.x, yv.x, acc[1][2 * w]);
+        acc[1][2 * w + 1] = fmaf(g.y, yv.y, acc[1][2 * w + 1]);
+        if (HAS_Y2) {
+          const uint32_t y2w[4] = {Y2[u].x, Y2[u].y, Y2[u].z, Y2[u].w};
+          const float2 y2v = bf2_to_f2(y2w[w]);
+          acc[K - 1][2 * w] = fmaf(g.x, y2v.x, acc[K - 1][2 * w]);
+          acc[K - 1][2 * w + 1] = fmaf(g.y, y2v.y, acc[K - 1][2 * w + 1]);
+        }
       }
     }
   }
-  if (y2) {
-    column_reduce_finish<3>(acc, cg, cgroups, c, partial);
-  } else {
-    float acc2[2][8];
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc2[k][j] = acc[k][j];
-    column_reduce_finish<2>(acc2, cg, cgroups, c, partial);
-  }
+  column_reduce_finish<K>(acc, cg, cgroups, c, partial);
 }
 
 // Per-channel coefficients of the BN backward, dy = A*dz + B*y + C with
@@ -300,7 +357,7 @@ __global__ void bn_bwd_coeffs_kernel(const float* __restrict__ partial, int nblo
   __shared__ double sh[32][32];
   const int i = blockIdx.x * 32 + threadIdx.x;
   double db, s1;
-  sum_partials2(partial, nblocks, K, 0, gslot, c, i, sh, db, s1);
+  sum_partials2<false>(const_cast<float*>(partial), nblocks, K, 0, gslot, c, i, sh, db, s1);
   if (threadIdx.y != 0 || i >= c) return;
   const double n = (double)rows, is = (double)invstd[i], ga = (double)gamma[i], mu = (double)mean[i];
   const double dg = is * (s1 - mu * db);          // sum dz * xhat from the raw moments
@@ -311,60 +368,73 @@ __global__ void bn_bwd_coeffs_kernel(const float* __restrict__ partial, int nblo
   grad_beta[i] += (float)db;
 }
 
-// dz = (g1 [+ g2]) * (act > 0);  dy = A*dz + B*y + C  (and the same for the second BN);  optionally writes dz.
+// dz = (g1 [+ g2]) * mask;  dy = A*dz + B*y + C  (and the same for the second BN);  optionally writes dz.
 // Same (channel group, row lane) mapping as bn_apply: coefficients live in registers.
-__global__ void __launch_bounds__(256)
+template <int MODE, bool HAS_G2, bool HAS_Y2, bool WRITE_DZ>
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
-                    const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ y,
-                    const float* __restrict__ coef, const __nv_bfloat16* __restrict__ y2,
-                    const float* __restrict__ coef2, int64_t rows, int c, __nv_bfloat16* __restrict__ dy,
+                    const __nv_bfloat16* __restrict__ y, const float* __restrict__ coef,
+                    const __nv_bfloat16* __restrict__ y2, const float* __restrict__ coef2,
+                    const float* __restrict__ scale, const float* __restrict__ shift,
+                    const uint8_t* __restrict__ mask, int64_t rows, int c, __nv_bfloat16* __restrict__ dy,
                     __nv_bfloat16* __restrict__ dy2, __nv_bfloat16* __restrict__ dz_out) {
   const int cgroups = c / 8;
   const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
   const V8 A = loadf8(coef + cg * 8), B = loadf8(coef + c + cg * 8), C = loadf8(coef + 2 * c + cg * 8);
   V8 A2{}, B2{}, C2{};
-  if (y2) {
+  if (HAS_Y2) {
     A2 = loadf8(coef2 + cg * 8);
     B2 = loadf8(coef2 + c + cg * 8);
     C2 = loadf8(coef2 + 2 * c + cg * 8);
   }
+  MaskSrc<MODE> ms;
+  ms.init(scale, shift, mask, cgroups, cg);
   const int64_t stride = (int64_t)gridDim.x * lanes;
-  for (int64_t r = blockIdx.x * (int64_t)lanes + lane; r < rows; r += stride) {
-    const int64_t off = r * c + cg * 8;
-    const uint4 G = *reinterpret_cast<const uint4*>(g1 + off);
-    const uint4 Y = *reinterpret_cast<const uint4*>(y + off);
-    uint4 G2 = make_uint4(0, 0, 0, 0), AC = make_uint4(0, 0, 0, 0), Y2 = make_uint4(0, 0, 0, 0);
-    if (g2) G2 = *reinterpret_cast<const uint4*>(g2 + off);
-    if (act) AC = *reinterpret_cast<const uint4*>(act + off);
-    if (y2) Y2 = *reinterpret_cast<const uint4*>(y2 + off);
-    const uint32_t gw[4] = {G.x, G.y, G.z, G.w}, g2w[4] = {G2.x, G2.y, G2.z, G2.w}, aw[4] = {AC.x, AC.y, AC.z, AC.w};
-    const uint32_t yw[4] = {Y.x, Y.y, Y.z, Y.w}, y2w[4] = {Y2.x, Y2.y, Y2.z, Y2.w};
-    uint32_t o1[4], o2[4], oz[4];
+  for (int64_t r0 = blockIdx.x * (int64_t)lanes + lane; r0 < rows; r0 += 2 * stride) {
+    const int64_t r1 = r0 + stride;
+    const bool two = r1 < rows;
+    const int64_t offs[2] = {r0 * c + cg * 8, (two ? r1 : r0) * c + cg * 8};
+    uint4 G[2], Y[2], G2[2], Y2[2];
+    uint32_t M[2];
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      float2 g = bf2_to_f2(gw[w]);
-      if (g2) {
-        const float2 t = bf2_to_f2(g2w[w]);
-        g.x += t.x;
-        g.y += t.y;
-      }
-      if (act) {
-        if ((aw[w] & 0x00007fffu) == 0u) g.x = 0.f;
-        if ((aw[w] & 0x7fff0000u) == 0u) g.y = 0.f;
-      }
-      if (dz_out) oz[w] = f2_to_bf2(g.x, g.y);
-      const float2 yv = bf2_to_f2(yw[w]);
-      o1[w] = f2_to_bf2(fmaf(A.v[2 * w], g.x, fmaf(B.v[2 * w], yv.x, C.v[2 * w])),
-                        fmaf(A.v[2 * w + 1], g.y, fmaf(B.v[2 * w + 1], yv.y, C.v[2 * w + 1])));
-      if (y2) {
-        const float2 y2v = bf2_to_f2(y2w[w]);
-        o2[w] = f2_to_bf2(fmaf(A2.v[2 * w], g.x, fmaf(B2.v[2 * w], y2v.x, C2.v[2 * w])),
-                          fmaf(A2.v[2 * w + 1], g.y, fmaf(B2.v[2 * w + 1], y2v.y, C2.v[2 * w + 1])));
-      }
+    for (int u = 0; u < 2; ++u) {
+      G[u] = *reinterpret_cast<const uint4*>(g1 + offs[u]);
+      Y[u] = *reinterpret_cast<const uint4*>(y + offs[u]);
+      if (HAS_G2) G2[u] = *reinterpret_cast<const uint4*>(g2 + offs[u]);
+      if (HAS_Y2) Y2[u] = *reinterpret_cast<const uint4*>(y2 + offs[u]);
     }
-    *reinterpret_cast<uint4*>(dy + off) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
-    if (y2) *reinterpret_cast<uint4*>(dy2 + off) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
-    if (dz_out) *reinterpret_cast<uint4*>(dz_out + off) = make_uint4(oz[0], oz[1], oz[2], oz[3]);
+    M[0] = ms.load(r0);
+    M[1] = ms.load(two ? r1 : r0);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      const uint32_t gw[4] = {G[u].x, G[u].y, G[u].z, G[u].w}, yw[4] = {Y[u].x, Y[u].y, Y[u].z, Y[u].w};
+      uint32_t o1[4], o2[4], oz[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        float2 g = bf2_to_f2(gw[w]);
+        if (HAS_G2) {
+          const uint32_t g2w[4] = {G2[u].x, G2[u].y, G2[u].z, G2[u].w};
+          const float2 t = bf2_to_f2(g2w[w]);
+          g.x += t.x;
+          g.y += t.y;
+        }
+        const float2 yv = bf2_to_f2(yw[w]);
+        ms.apply(M[u], w, yv, g);
+        if (WRITE_DZ) oz[w] = f2_to_bf2(g.x, g.y);
+        o1[w] = f2_to_bf2(fmaf(A.v[2 * w], g.x, fmaf(B.v[2 * w], yv.x, C.v[2 * w])),
+                          fmaf(A.v[2 * w + 1], g.y, fmaf(B.v[2 * w + 1], yv.y, C.v[2 * w + 1])));
+        if (HAS_Y2) {
+          const uint32_t y2w[4] = {Y2[u].x, Y2[u].y, Y2[u].z, Y2[u].w};
+          const float2 y2v = bf2_to_f2(y2w[w]);
+          o2[w] = f2_to_bf2(fmaf(A2.v[2 * w], g.x, fmaf(B2.v[2 * w], y2v.x, C2.v[2 * w])),
+                            fmaf(A2.v[2 * w + 1], g.y, fmaf(B2.v[2 * w + 1], y2v.y, C2.v[2 * w + 1])));
+        }
+      }
+      *reinterpret_cast<uint4*>(dy + offs[u]) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+      if (HAS_Y2) *reinterpret_cast<uint4*>(dy2 + offs[u]) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+      if (WRITE_DZ) *reinterpret_cast<uint4*>(dz_out + offs[u]) = make_uint4(oz[0], oz[1], oz[2], oz[3]);
+    }
   }
 }
 
@@ -546,7 +616,8 @@ __global__ void linear1_bwd_kernel(const float* __restrict__ g, const float* __r
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
-            float grad_scale) {
+            float grad_scale, const float* __restrict__ clip_coef) {
+  if (clip_coef) grad_scale *= clip_coef[0];
   const int64_t n4 = n / 4;
   const float step_size = lr / bc1;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -584,7 +655,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 // torch.optim.SGD with momentum (dampening 0, no nesterov), weight decay
 __global__ void __launch_bounds__(256)
 sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n, float lr,
-           float momentum, float weight_decay, int first_step, float grad_scale) {
+           float momentum, float weight_decay, int first_step, float grad_scale, const float* __restrict__ clip_coef) {
+  if (clip_coef) grad_scale *= clip_coef[0];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gr = g[i] * grad_scale;
     if (weight_decay != 0.f) gr = fmaf(weight_decay, p[i], gr);
@@ -594,6 +666,51 @@ sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict
       gr = b;
     }
     p[i] -= lr * gr;
+  }
+}
+
+// sum of (scale * g)^2 over the flat gradient: fp32 per thread, fp64 per block; the last block to finish (ticket)
+// adds the block partials and writes the clip coefficient.
+constexpr int kClipMaxGrid = 1024;
+__global__ void __launch_bounds__(256)
+grad_clip_kernel(const float* __restrict__ g, int64_t n, float scale, float max_norm, double* __restrict__ partials,
+                 unsigned int* __restrict__ ticket, float* __restrict__ out) {
+  __shared__ double sh[8];
+  __shared__ bool last;
+  float acc = 0.f;
+  const int64_t n4 = n / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    acc = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, acc))));
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) acc = fmaf(g[i], g[i], acc);
+  double t = warp_sum((double)acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += sh[w];
+    partials[blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double tot = 0.0;
+  for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) tot += ((volatile double*)partials)[i];
+  tot = warp_sum(tot);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += sh[w];
+    const float norm = (float)(sqrt(s) * (double)fabsf(scale));
+    const float coef = max_norm / (norm + 1e-6f);
+    out[0] = coef < 1.f ? coef : 1.f;
+    out[1] = norm;
+    *ticket = 0u;                          // ready for the next step
   }
 }
 
@@ -629,11 +746,15 @@ int bn_stats(const __nv_bfloat16* y, int64_t rows, int c, float* partial, int* n
   return DIRB200_OK;
 }
 
-int bn_finalize(const float* partial, int nblocks, int64_t rows, int c, const float* gamma, const float* beta,
+int bn_finalize(float* partial, int nblocks, bool clear, int64_t rows, int c, const float* gamma, const float* beta,
                 float eps, float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
                 float* scale, float* shift, cudaStream_t st) {
-  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, st>>>(partial, nblocks, rows, c, gamma, beta, eps, momentum, running_mean,
-                                                    running_var, mean, invstd, scale, shift);
+  if (clear)
+    bn_finalize_kernel<true><<<(c + 31) / 32, dim3(32, 32), 0, st>>>(partial, nblocks, rows, c, gamma, beta, eps, momentum,
+                                                                   running_mean, running_var, mean, invstd, scale, shift);
+  else
+    bn_finalize_kernel<false><<<(c + 31) / 32, dim3(32, 32), 0, st>>>(partial, nblocks, rows, c, gamma, beta, eps, momentum,
+                                                                    running_mean, running_var, mean, invstd, scale, shift);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
@@ -647,24 +768,35 @@ int bn_eval_coeffs(int c, const float* gamma, const float* beta, float eps, cons
 
 int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, const __nv_bfloat16* res,
              const __nv_bfloat16* res_y, const float* res_scale, const float* res_shift, bool relu, int64_t rows, int c,
-             __nv_bfloat16* out, cudaStream_t st) {
+             __nv_bfloat16* out, uint8_t* mask_out, cudaStream_t st) {
   const int cgroups = c / 8;
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_apply: unsupported channel count %d", c);
   bn_apply_kernel<<<stream_grid(rows, 256 / cgroups), 256, 0, st>>>(y, scale, shift, res, res_y, res_scale, res_shift,
-                                                                    relu ? 1 : 0, rows, c, out);
+                                                                    relu ? 1 : 0, rows, c, out, mask_out);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
 
-int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* act, const __nv_bfloat16* y,
-                  const float* mean, const float* invstd, const __nv_bfloat16* y2, const float* mean2,
-                  const float* invstd2, int64_t rows, int c, float* partial, int* nblocks, cudaStream_t st) {
+// mask == nullptr: conv -> BN -> ReLU layer, the ReLU mask is re-derived from y with (scale, shift);
+// mask != nullptr: block output, the bit mask bn_apply stored (g2 / y2: second incoming gradient / downsample branch).
+int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* y, const __nv_bfloat16* y2,
+                  const float* scale, const float* shift, const uint8_t* mask, int64_t rows, int c, float* partial,
+                  int* nblocks, cudaStream_t st) {
   const int cgroups = c / 8;
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_bwd_reduce: unsupported channel count %d", c);
+  DIRB_CHECK_ARG(mask || (scale && shift && !g2 && !y2), "bn_bwd_reduce: mask-from-y form takes one gradient, one BN");
   const int lanes = 256 / cgroups;
   *nblocks = reduce_grid(rows, lanes);
-  (void)mean; (void)invstd; (void)mean2; (void)invstd2;   // the moments are centred in bn_bwd_coeffs
-  bn_bwd_reduce_kernel<<<*nblocks, 256, 256 * 24 * sizeof(float), st>>>(g1, g2, act, y, y2, rows, c, partial);
+  const int grid = *nblocks;
+  const size_t smem = 256 * (y2 ? 24 : 16) * sizeof(float);
+#define DIRB_RED(MODE, G2, Y2) \
+  bn_bwd_reduce_kernel<MODE, G2, Y2><<<grid, 256, smem, st>>>(g1, g2, y, y2, scale, shift, mask, rows, c, partial)
+  if (!mask) DIRB_RED(MASK_FROM_Y, false, false);
+  else if (g2 && y2) DIRB_RED(MASK_BITS, true, true);
+  else if (g2) DIRB_RED(MASK_BITS, true, false);
+  else if (y2) DIRB_RED(MASK_BITS, false, true);
+  else DIRB_RED(MASK_BITS, false, false);
+#undef DIRB_RED
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
@@ -678,13 +810,26 @@ int bn_bwd_coeffs(const float* partial, int nblocks, int k, int gslot, int64_t r
   return DIRB200_OK;
 }
 
-int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* act, const __nv_bfloat16* y,
-                 const float* coef, const __nv_bfloat16* y2, const float* coef2, int64_t rows, int c,
-                 __nv_bfloat16* dy, __nv_bfloat16* dy2, __nv_bfloat16* dz_out, cudaStream_t st) {
+int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* y, const float* coef,
+                 const __nv_bfloat16* y2, const float* coef2, const float* scale, const float* shift,
+                 const uint8_t* mask, int64_t rows, int c, __nv_bfloat16* dy, __nv_bfloat16* dy2,
+                 __nv_bfloat16* dz_out, cudaStream_t st) {
   const int cgroups = c / 8;
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_bwd_apply: unsupported channel count %d", c);
-  bn_bwd_apply_kernel<<<stream_grid(rows, 256 / cgroups), 256, 0, st>>>(g1, g2, act, y, coef, y2, coef2, rows, c, dy,
-                                                                        dy2, dz_out);
+  DIRB_CHECK_ARG(mask || (scale && shift && !g2 && !y2 && !dz_out), "bn_bwd_apply: mask-from-y form takes one gradient, one BN");
+  DIRB_CHECK_ARG(!(y2 && dz_out), "bn_bwd_apply: a block has either a downsample branch or an identity path");
+  const int grid = stream_grid(rows, 256 / cgroups);
+#define DIRB_APP(MODE, G2, Y2, DZ)                                                                                   \
+  bn_bwd_apply_kernel<MODE, G2, Y2, DZ><<<grid, 256, 0, st>>>(g1, g2, y, coef, y2, coef2, scale, shift, mask, rows, c, \
+                                                             dy, dy2, dz_out)
+  if (!mask) DIRB_APP(MASK_FROM_Y, false, false, false);
+  else if (g2 && y2) DIRB_APP(MASK_BITS, true, true, false);
+  else if (g2 && dz_out) DIRB_APP(MASK_BITS, true, false, true);
+  else if (g2) DIRB_APP(MASK_BITS, true, false, false);
+  else if (y2) DIRB_APP(MASK_BITS, false, true, false);
+  else if (dz_out) DIRB_APP(MASK_BITS, false, false, true);
+  else DIRB_APP(MASK_BITS, false, false, false);
+#undef DIRB_APP
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
@@ -739,7 +884,7 @@ int dirb200_linear1_bwd(const float* grad_pred, const float* x, const float* w, 
 
 int dirb200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                       float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
-                      void* stream) {
+                      const float* clip_coef, void* stream) {
   DIRB_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad arguments");
   DIRB_CHECK_ARG((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
                   reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) % 16 == 0,
@@ -748,16 +893,36 @@ int dirb200_adam_step(float* params, const float* grads, float* exp_avg, float* 
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<grid1d(n / 4 + 1), 256, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                eps, weight_decay, (float)bc1, (float)sqrt(bc2),
-                                                               grad_scale);
+                                                               grad_scale, clip_coef);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
 
 int dirb200_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr, float momentum,
-                     float weight_decay, int first_step, float grad_scale, void* stream) {
+                     float weight_decay, int first_step, float grad_scale, const float* clip_coef, void* stream) {
   DIRB_CHECK_ARG(params && grads && n > 0 && (momentum == 0.f || momentum_buf), "sgd_step: bad arguments");
   sgd_kernel<<<grid1d(n), 256, 0, as_stream(stream)>>>(params, grads, momentum_buf, n, lr, momentum, weight_decay,
-                                                      first_step, grad_scale);
+                                                      first_step, grad_scale, clip_coef);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+size_t dirb200_grad_clip_workspace_bytes(void) { return sizeof(double) * kClipMaxGrid + 16; }
+
+/* The workspace must be zero-initialised once (its ticket word is reset by the kernel after every use). */
+int dirb200_grad_clip_coef(const float* grads, int64_t n, float grad_scale, float max_norm, void* workspace,
+                           size_t workspace_bytes, float* out, void* stream) {
+  DIRB_CHECK_ARG(grads && out && workspace && n > 0 && max_norm > 0.f, "grad_clip_coef: bad arguments");
+  DIRB_CHECK_ARG(reinterpret_cast<uintptr_t>(grads) % 16 == 0, "grad_clip_coef: gradient buffer must be 16-byte aligned");
+  if (workspace_bytes < dirb200_grad_clip_workspace_bytes()) {
+    set_error("grad_clip_coef: workspace too small");
+    return DIRB200_ERR_WORKSPACE;
+  }
+  double* partials = reinterpret_cast<double*>(workspace);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + kClipMaxGrid);
+  int grid = grid1d(n / 4 + 1, 256, 4);
+  if (grid > kClipMaxGrid) grid = kClipMaxGrid;
+  grad_clip_kernel<<<grid, 256, 0, as_stream(stream)>>>(grads, n, grad_scale, max_norm, partials, ticket, out);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }

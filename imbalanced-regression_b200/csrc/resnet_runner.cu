@@ -6,6 +6,7 @@
 // Parameters and their gradients live in ONE flat fp32 buffer each, laid out in the reference's
 // named_parameters() order (conv1.weight, bn1.weight, bn1.bias, layer1.0.conv1.weight, ...), which the
 // Python module (resnet.py) exposes as ordinary nn.Parameter views -> identical state_dict keys/shapes.
+#include <stdlib.h>
 #include <vector>
 #include "common.cuh"
 #include "conv.cuh"
@@ -36,6 +37,7 @@ struct Block {
   bool has_ds = false;
   const __nv_bfloat16* in = nullptr;
   __nv_bfloat16* out = nullptr;
+  uint8_t* mask = nullptr;     // ReLU mask of `out`, 1 bit per element ([rows][c/8] bytes), for the backward pass
 };
 
 }  // namespace dirb200
@@ -52,7 +54,9 @@ struct dirb200_net {
   int feat_c = 0, feat_hw = 0;
   __nv_bfloat16* scratch[8] = {};
   float* wgrad_ws = nullptr;
-  float* bn_partial = nullptr;   // per-CTA partial sums of the BN column reductions
+  float* bn_partial = nullptr;   // per-CTA partial sums of the BN column reductions (backward)
+  float* stat_partial = nullptr; // per-(CTA, epilogue warp) BN statistics written by the conv fprop epilogue; all-zero
+                                 // between uses (bn_finalize clears what it reads)
   PrepDesc* prep_descs = nullptr; // device table for the single weight re-layout launch
   int num_convs = 0;
   size_t param_count = 0, running_count = 0, activation_bytes = 0;
@@ -141,6 +145,7 @@ static bool build(dirb200_net* net, const int* blocks_per_stage, int num_stages)
       if (!setup_conv(net, B.c3, n, h2, w2, planes, planes * 4, 1, 1, 0, false, false)) return false;
       if (B.has_ds && !setup_conv(net, B.ds, n, h, w, inplanes, planes * 4, 1, stride, 0, false, false)) return false;
       NET_ALLOC(B.out, (size_t)B.c3.rows * planes * 4 * 2);
+      NET_ALLOC(B.mask, (size_t)B.c3.rows * planes * 4 / 8);
       max_act = std::max(max_act, (size_t)B.c1.rows * std::max(inplanes, planes));
       max_act = std::max(max_act, (size_t)B.c3.rows * planes * 4);
       cur = B.out;
@@ -160,6 +165,8 @@ static bool build(dirb200_net* net, const int* blocks_per_stage, int num_stages)
   }
   NET_ALLOC(net->wgrad_ws, ws);
   NET_ALLOC(net->bn_partial, sizeof(float) * bn_partial_floats(net->feat_c));
+  NET_ALLOC(net->stat_partial, sizeof(float) * bn_partial_floats(net->feat_c));
+  if (cudaMemset(net->stat_partial, 0, sizeof(float) * bn_partial_floats(net->feat_c)) != cudaSuccess) return false;
   std::vector<PrepDesc> descs;
   auto add = [&](const ConvLayer& cv) {
     descs.push_back(PrepDesc{cv.w_off, cv.s.cout, cv.stem ? 3 : cv.s.cin, cv.stem ? 7 : cv.s.kh, cv.stem ? 7 : cv.s.kw,
@@ -213,22 +220,35 @@ static inline void prof_end(dirb200_net* net, cudaStream_t st) {
     if (_rc) return _rc;          \
   } while (0)
 
+// DIRB200_FUSED_STATS=0: batch statistics by the separate bn_stats pass over y (A/B measurements) instead of the
+// conv epilogue.
+static bool fused_stats() {
+  static const bool on = [] {
+    const char* e = getenv("DIRB200_FUSED_STATS");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+
 static int conv_bn_forward(dirb200_net* net, ConvLayer& cv, const __nv_bfloat16* in, const float* params,
                            float* running, bool training, cudaStream_t st) {
-  RUNP(kFprop, conv_fprop(in, cv.wf, cv.y, cv.s, cv.stem, st));
   BNLayer& bn = cv.bn;
   if (training) {
+    // batch statistics come out of the conv epilogue (per-CTA column sums of the rounded outputs): y is not re-read
     int nblk = 0;
-    RUNP(kBnStats, bn_stats(cv.y, cv.rows, bn.c, net->bn_partial, &nblk, st));
-    RUNP(kBnStats, bn_finalize(net->bn_partial, nblk, cv.rows, bn.c, params + bn.gamma_off, params + bn.beta_off, 1e-5f, 0.1f,
-                    running ? running + bn.rm_off : nullptr, running ? running + bn.rv_off : nullptr, bn.mean,
-                    bn.invstd, bn.scale, bn.shift, st));
+    const bool fused = fused_stats();
+    RUNP(kFprop, conv_fprop(in, cv.wf, cv.y, cv.s, cv.stem, st, fused ? net->stat_partial : nullptr, &nblk));
+    if (!fused) RUNP(kBnStats, bn_stats(cv.y, cv.rows, bn.c, net->stat_partial, &nblk, st));
+    RUNP(kBnStats, bn_finalize(net->stat_partial, nblk, true, cv.rows, bn.c, params + bn.gamma_off, params + bn.beta_off, 1e-5f,
+                               0.1f, running ? running + bn.rm_off : nullptr, running ? running + bn.rv_off : nullptr,
+                               bn.mean, bn.invstd, bn.scale, bn.shift, st));
   } else {
+    RUNP(kFprop, conv_fprop(in, cv.wf, cv.y, cv.s, cv.stem, st));
     RUNP(kBnStats, bn_eval_coeffs(bn.c, params + bn.gamma_off, params + bn.beta_off, 1e-5f, running + bn.rm_off,
                                   running + bn.rv_off, bn.scale, bn.shift, st));
   }
   if (cv.a)
-    RUNP(kBnApply, bn_apply(cv.y, bn.scale, bn.shift, nullptr, nullptr, nullptr, nullptr, true, cv.rows, bn.c, cv.a, st));
+    RUNP(kBnApply, bn_apply(cv.y, bn.scale, bn.shift, nullptr, nullptr, nullptr, nullptr, true, cv.rows, bn.c, cv.a, nullptr, st));
   return DIRB200_OK;
 }
 
@@ -240,17 +260,18 @@ static int wgrad_step(dirb200_net* net, const __nv_bfloat16* x, const __nv_bfloa
   return DIRB200_OK;
 }
 
-// BN backward for a conv followed by BN+ReLU: g = d loss / d relu-output
+// BN backward for a conv followed by BN+ReLU: g = d loss / d relu-output.  The ReLU mask is re-derived from
+// (y, scale, shift): the activation cv.a is not read.
 static int conv_bn_backward(dirb200_net* net, ConvLayer& cv, const __nv_bfloat16* g, const float* params, float* grads,
                             __nv_bfloat16* dy, cudaStream_t st) {
   BNLayer& bn = cv.bn;
   int nblk = 0;
-  RUNP(kBnBwdReduce, bn_bwd_reduce(g, nullptr, cv.a, cv.y, bn.mean, bn.invstd, nullptr, nullptr, nullptr, cv.rows,
-                                   bn.c, net->bn_partial, &nblk, st));
+  RUNP(kBnBwdReduce, bn_bwd_reduce(g, nullptr, cv.y, nullptr, bn.scale, bn.shift, nullptr, cv.rows, bn.c,
+                                   net->bn_partial, &nblk, st));
   RUNP(kBnBwdApply, bn_bwd_coeffs(net->bn_partial, nblk, 2, 1, cv.rows, bn.c, bn.mean, bn.invstd,
                                   params + bn.gamma_off, grads + bn.gamma_off, grads + bn.beta_off, bn.coef, st));
-  RUNP(kBnBwdApply, bn_bwd_apply(g, nullptr, cv.a, cv.y, bn.coef, nullptr, nullptr, cv.rows, bn.c, dy, nullptr, nullptr,
-                                 st));
+  RUNP(kBnBwdApply, bn_bwd_apply(g, nullptr, cv.y, bn.coef, nullptr, nullptr, bn.scale, bn.shift, nullptr, cv.rows, bn.c,
+                                 dy, nullptr, nullptr, st));
   return DIRB200_OK;
 }
 
@@ -328,10 +349,10 @@ int dirb200_resnet_forward(dirb200_net* net, const float* x_nchw, const float* p
     if (B.has_ds) {
       RUN(conv_bn_forward(net, B.ds, B.in, params, bn_running, tr, st));
       RUNP(kBnApply, bn_apply(B.c3.y, B.c3.bn.scale, B.c3.bn.shift, nullptr, B.ds.y, B.ds.bn.scale, B.ds.bn.shift, true,
-                              B.c3.rows, B.c3.bn.c, B.out, st));
+                              B.c3.rows, B.c3.bn.c, B.out, tr ? B.mask : nullptr, st));
     } else {
       RUNP(kBnApply, bn_apply(B.c3.y, B.c3.bn.scale, B.c3.bn.shift, B.in, nullptr, nullptr, nullptr, true, B.c3.rows,
-                              B.c3.bn.c, B.out, st));
+                              B.c3.bn.c, B.out, tr ? B.mask : nullptr, st));
     }
   }
   RUNP(kPool, avgpool_fwd(net->blocks.back().out, net->n, net->feat_hw, net->feat_c, enc_out, st));
@@ -355,8 +376,7 @@ int dirb200_resnet_backward(dirb200_net* net, const float* d_enc, const float* p
     // ---- block output: out = relu(bn3(y3) + identity); dz = (gA + gB) * (out > 0)
     int nblk = 0;
     const int kparts = B.has_ds ? 3 : 2;
-    RUNP(kBnBwdReduce, bn_bwd_reduce(gA, gB, B.out, B.c3.y, b3.mean, b3.invstd, B.has_ds ? B.ds.y : nullptr,
-                                     B.has_ds ? B.ds.bn.mean : nullptr, B.has_ds ? B.ds.bn.invstd : nullptr, B.c3.rows,
+    RUNP(kBnBwdReduce, bn_bwd_reduce(gA, gB, B.c3.y, B.has_ds ? B.ds.y : nullptr, nullptr, nullptr, B.mask, B.c3.rows,
                                      b3.c, net->bn_partial, &nblk, st));
     if (B.has_ds) {
       BNLayer& bd = B.ds.bn;
@@ -365,9 +385,9 @@ int dirb200_resnet_backward(dirb200_net* net, const float* d_enc, const float* p
     }
     RUNP(kBnBwdApply, bn_bwd_coeffs(net->bn_partial, nblk, kparts, 1, B.c3.rows, b3.c, b3.mean, b3.invstd,
                                     params + b3.gamma_off, grads + b3.gamma_off, grads + b3.beta_off, b3.coef, st));
-    RUNP(kBnBwdApply, bn_bwd_apply(gA, gB, B.out, B.c3.y, b3.coef, B.has_ds ? B.ds.y : nullptr,
-                                   B.has_ds ? B.ds.bn.coef : nullptr, B.c3.rows, b3.c, t1, B.has_ds ? t2 : nullptr,
-                                   B.has_ds ? nullptr : nB, st));
+    RUNP(kBnBwdApply, bn_bwd_apply(gA, gB, B.c3.y, b3.coef, B.has_ds ? B.ds.y : nullptr,
+                                   B.has_ds ? B.ds.bn.coef : nullptr, nullptr, nullptr, B.mask, B.c3.rows, b3.c, t1,
+                                   B.has_ds ? t2 : nullptr, B.has_ds ? nullptr : nB, st));
     // ---- conv3
     RUN(wgrad_step(net, B.c2.a, t1, grads + B.c3.w_off, B.c3.s, false, st));
     RUNP(kDgrad, conv_dgrad(t1, B.c3.wd, t3, B.c3.s, st));

@@ -43,8 +43,10 @@ _lib.register({
     "dirb200_linear1_fwd": (c_int, [P, P, P, c_int64, c_int, P, P]),
     "dirb200_linear1_bwd": (c_int, [P, P, P, c_int64, c_int, P, P, P, P]),
     "dirb200_adam_step": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64,
-                                  c_float, P]),
-    "dirb200_sgd_step": (c_int, [P, P, P, c_int64, c_float, c_float, c_float, c_int, c_float, P]),
+                                  c_float, P, P]),
+    "dirb200_sgd_step": (c_int, [P, P, P, c_int64, c_float, c_float, c_float, c_int, c_float, P, P]),
+    "dirb200_grad_clip_workspace_bytes": (ctypes.c_size_t, []),
+    "dirb200_grad_clip_coef": (c_int, [P, c_int64, c_float, c_float, P, ctypes.c_size_t, P, P]),
 })
 
 
@@ -352,8 +354,9 @@ class ResNet(nn.Module):
         _lib.call("dirb200_resnet_read_profile", self._net(tuple(shape)), ms, cnt)
         return {k: (ms[i], cnt[i]) for i, k in enumerate(self.PROFILE_KINDS)}
 
-    def peek(self, shape, block, which):
-        """Test aid: copy of an internal NHWC bf16 activation of the runner for input `shape`, as fp32 NCHW."""
+    def peek(self, shape, block, which, copy=True):
+        """Test aid: an internal NHWC bf16 activation of the runner for input `shape`, as an fp32 NCHW copy
+        (copy=False: a zero-copy bf16 view with NCHW shape / channels-last strides, valid until the next forward)."""
         ptr, rows, ch = c_void_p(), c_int64(), c_int()
         _lib.call("dirb200_resnet_peek", self._net(tuple(shape)), block, which, ctypes.byref(ptr), ctypes.byref(rows),
                   ctypes.byref(ch))
@@ -364,6 +367,8 @@ class ResNet(nn.Module):
         flat = torch.as_tensor(_Arr(), device=self._flat["params"].device).view(torch.bfloat16)
         n = shape[0]
         side = int(round((rows.value // n) ** 0.5))
+        if not copy:
+            return flat.view(n, side, side, ch.value).permute(0, 3, 1, 2)
         return flat.float().view(n, side, side, ch.value).permute(0, 3, 1, 2).contiguous()
 
     # ---------------------------------------------------------------- forward

@@ -266,12 +266,20 @@ int dirb200_linear1_bwd(const float* grad_pred, const float* x, const float* w, 
 
 /* Fused optimizer steps over flat fp32 buffers (torch.optim.Adam / SGD semantics,
  * agedb-dir/train.py:163-164,262); grads are multiplied by grad_scale first
- * (1/world_size after a sum all-reduce). */
+ * (1/world_size after a sum all-reduce) and, when clip_coef != NULL, by the device scalar *clip_coef
+ * (dirb200_grad_clip_coef below: gradient-norm clipping without a host round trip). */
 int dirb200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                       float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
-                      void* stream);
+                      const float* clip_coef, void* stream);
 int dirb200_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr, float momentum,
-                     float weight_decay, int first_step, float grad_scale, void* stream);
+                     float weight_decay, int first_step, float grad_scale, const float* clip_coef, void* stream);
+
+/* torch.nn.utils.clip_grad_norm_ over one flat gradient buffer (sts-b-dir/trainer.py:147-149, --max_grad_norm):
+ * out[0] = min(1, max_norm / (||grad_scale * grads||_2 + 1e-6)), out[1] = that norm.  The gradients themselves are
+ * not rewritten -- the optimizer step applies out[0] while it reads them.  workspace: >= 8 KiB + 16 B, fp64 partials. */
+size_t dirb200_grad_clip_workspace_bytes(void);
+int dirb200_grad_clip_coef(const float* grads, int64_t n, float grad_scale, float max_norm, void* workspace,
+                           size_t workspace_bytes, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -202,6 +202,36 @@ def fds_batch_stats(features, labels, bucket_num, bucket_start):
     return cnt, mean, var
 
 
+def fds_stats_from_bins(features, bins, nb):
+    """Per-bin (count, mean, unbiased var [0 when n==1]) given the table row of every feature row (-1 = untouched):
+    the same quantities as fds_batch_stats / agedb-dir/fds.py:100-102, computed with one stable sort and segmented
+    float64 sums so that BASELINE-size inputs (2.46 M rows x 128, 5 749 rows x 12 000) finish in seconds.  Pinned to
+    the per-bin loop of fds_batch_stats by tests/test_oracle_golden.py."""
+    f = np.asarray(features)
+    bins = np.asarray(bins).reshape(-1)
+    keep = np.nonzero(bins >= 0)[0]
+    order = keep[np.argsort(bins[keep], kind="stable")]
+    sb = bins[order]
+    cnt = np.bincount(sb, minlength=nb).astype(np.int64)
+    mean = np.zeros((nb, f.shape[1]), dtype=np.float32)
+    var = np.zeros((nb, f.shape[1]), dtype=np.float32)
+    if order.size == 0:
+        return cnt, mean, var
+    starts = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+    present = np.nonzero(cnt)[0]
+    # column blocks bound the float64 scratch (rows x 512 x 8 B)
+    for c0 in range(0, f.shape[1], 512):
+        blk = f[order, c0:c0 + 512].astype(np.float64)
+        s1 = np.add.reduceat(blk, starts[present], axis=0)
+        m = s1 / cnt[present, None]
+        dev = blk - np.repeat(m, cnt[present], axis=0)
+        s2 = np.add.reduceat(dev * dev, starts[present], axis=0)
+        mean[present, c0:c0 + 512] = m
+        v = np.where(cnt[present, None] > 1, s2 / np.maximum(cnt[present, None] - 1, 1), 0.0)
+        var[present, c0:c0 + 512] = v
+    return cnt, mean, var
+
+
 class FDSState:
     """Numpy restatement of fds.FDS's buffers and state machine
     (agedb-dir/fds.py:16-35, 54-113), including the by-reference alias of

@@ -1,15 +1,15 @@
 """Standalone GPU check + per-layer timing of the conv GEMMs under the kernel's run-time switches (not collected
 by pytest; tests/test_gpu_conv_variants.py runs the parity half in subprocesses).
 
-    DIRB200_CTA2=1   python tests/cta2_check.py parity   # CTA pairs (cta_group::2), gather-fed A      [validated]
-    DIRB200_IM2COL=1 python tests/cta2_check.py parity   # im2col-mode TMA for the 3x3 / strided convs  [validated]
-    DIRB200_ATMA=0   python tests/cta2_check.py parity   # cp.async gather for every conv               [validated]
-    DIRB200_CTA2=2 [DIRB200_IM2COL=1] python tests/cta2_check.py parity   # pairs with TMA-fed A: NOT yet run on hardware
-    DIRB200_CTA2=3 ...                                   # mode 2 + wgrad pairs:  NOT yet run on hardware
-    <switches> python tests/cta2_check.py time           # per-layer fprop/dgrad times, batch-256 ResNet-50 shapes
-                                                          # (also written to gpurun_out/conv_layers_cta2_<mode>.json)
+    python tests/cta2_check.py parity                    # defaults: CTA pairs (256-wide, >= 4 k-blocks) + tiled / im2col TMA
+    DIRB200_CTA2=0   python tests/cta2_check.py parity   # single-CTA tiles only
+    DIRB200_IM2COL=0 python tests/cta2_check.py parity   # cp.async gather for the 3x3 / strided convs
+    DIRB200_ATMA=0   python tests/cta2_check.py parity   # cp.async gather for every conv
+    <switches> python tests/cta2_check.py time [substr]  # per-layer fprop/dgrad/wgrad times, batch-256 ResNet-50 shapes
+                                                          # (also written to gpurun_out/conv_layers_<tag>.json)
+    <switches> python tests/cta2_check.py one <substr> fprop|dgrad|wgrad   # a few launches of one layer (ncu target)
 
-The switches are read once per process, hence the separate invocations.  Round-1 results: profiles/r1_conv_layers.md.
+The switches are read once per process, hence the separate invocations.  Results: profiles/r2_conv_layers.md.
 """
 import json
 import os
@@ -36,6 +36,8 @@ PARITY = [
     (16, 28, 28, 128, 128, 3, 1, 1),    # BN=128 pair path, 98 m-tiles, 18 k-blocks
     (37, 14, 14, 256, 256, 3, 1, 1),    # odd number of m-tiles (57): last pair has an empty peer half
     (64, 14, 14, 256, 1024, 1, 1, 0),   # several tiles per cluster, accumulator double buffering
+    (75, 14, 14, 256, 256, 3, 1, 1),    # 115 m-tiles of a 3x3: pairs + im2col TMA, odd tile count
+    (64, 28, 28, 512, 256, 1, 1, 0),    # pairs + tiled TMA, 8 k-blocks
 ]
 
 # (name, n, h, w, cin, cout, k, stride, pad, count): every distinct non-stem conv of the batch-256 ResNet-50 step
@@ -83,7 +85,7 @@ def parity():
             except Exception:  # noqa: BLE001  (sticky CUDA error: nothing more can run in this process)
                 print("CUDA context lost; stopping", flush=True)
                 break
-    print(f"parity: {len(PARITY) - bad}/{len(PARITY)} ok (DIRB200_CTA2={os.environ.get('DIRB200_CTA2', '0')})")
+    print(f"parity: {len(PARITY) - bad}/{len(PARITY)} ok (switches: " + " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("DIRB200_")) + ")")
     return bad
 
 
@@ -145,10 +147,9 @@ def time_layers(reps=10, only=None):
     print("per-step totals (count-weighted, without the stem): " + ", ".join(f"{k} {v:.3f} ms" for k, v in total.items())
           + f", all {sum(total.values()):.3f} ms", flush=True)
     out["_total_ms"] = total
-    tag = os.environ.get("DIRB200_CTA2", "0") + ("i" if os.environ.get("DIRB200_IM2COL") == "1" else "") + \
-        os.environ.get("DIRB200_TAG", "")
+    tag = os.environ.get("DIRB200_TAG", "default")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"conv_layers_cta2_{tag}.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"conv_layers_{tag}.json"), "w"), indent=1)
 
 
 def one_layer(sub, which, reps=4):

@@ -1,5 +1,5 @@
 """GPU parity of the tcgen05 implicit-GEMM convolutions (fprop / dgrad / wgrad)
-against torch fp32 conv on the same bf16-rounded operands.  Tolerance: the
+against torch fp32 conv (TF32 off) on the same bf16-rounded operands.  Tolerance: the
 kernel accumulates in fp32 and rounds the result to bf16 once, so outputs must
 match the fp32 reference to bf16 precision (rel 2^-8 of the tensor scale);
 wgrad is fp32 end to end (1e-3 of scale for the long reductions)."""
@@ -10,6 +10,8 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+torch.backends.cudnn.allow_tf32 = False          # the reference convolutions must be true fp32
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def nhwc_bf16(t):      # NCHW fp32 -> NHWC bf16 contiguous
@@ -20,11 +22,12 @@ def to_nchw_f32(t):
     return t.float().permute(0, 3, 1, 2).contiguous()
 
 
-def run_conv(n, h, w, cin, cout, k, stride, pad, seed=0, check_dgrad=True):
+def run_conv(n, h, w, cin, cout, k, stride, pad, seed=0, check_dgrad=True, device_rng=False):
     import _lib, _convlib  # noqa: F401
-    g = torch.Generator(device="cpu").manual_seed(seed)
-    x = torch.randn(n, cin, h, w, generator=g).to(DEV)
-    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+    g = torch.Generator(device=DEV if device_rng else "cpu").manual_seed(seed)   # device_rng: full-size tensors
+    gdev = DEV if device_rng else "cpu"
+    x = torch.randn(n, cin, h, w, generator=g, device=gdev).to(DEV)
+    wt = (torch.randn(cout, cin, k, k, generator=g, device=gdev) / (cin * k * k) ** 0.5).to(DEV)
     xb = nhwc_bf16(x)
     xr = to_nchw_f32(xb)                                  # bf16-rounded x as fp32 NCHW
     wr = wt.to(torch.bfloat16).float()
@@ -43,9 +46,10 @@ def run_conv(n, h, w, cin, cout, k, stride, pad, seed=0, check_dgrad=True):
     scale = ref.abs().max().item()
     assert err <= 2 ** -7 * scale + 1e-6, f"fprop err {err} scale {scale}"
 
-    dy = torch.randn(n, cout, ho, wo, generator=g).to(DEV)
+    dy = torch.randn(n, cout, ho, wo, generator=g, device=gdev).to(DEV)
     dyb = nhwc_bf16(dy)
     dyr = to_nchw_f32(dyb)
+    del dy, x
     if check_dgrad:
         dx = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
         _lib.call("dirb200_conv_dgrad", _lib.ptr(dyb), _lib.ptr(wd), _lib.ptr(dx), *shape, st)
@@ -80,6 +84,9 @@ def run_conv(n, h, w, cin, cout, k, stride, pad, seed=0, check_dgrad=True):
     (1, 14, 14, 1024, 256, 1, 1, 0),   # 16 k-blocks > ring depth
     (4, 7, 7, 512, 2048, 1, 1, 0),     # 16 n-tiles
     (5, 9, 11, 64, 128, 3, 2, 1),      # odd sizes, non-square
+    (75, 14, 14, 256, 256, 3, 1, 1),   # CTA pairs + im2col TMA: 115 m-tiles (odd: last pair has an empty peer half)
+    (64, 28, 28, 512, 256, 1, 1, 0),   # CTA pairs + tiled TMA: 392 m-tiles, 8 k-blocks
+    (64, 14, 14, 256, 1024, 1, 1, 0),  # CTA pairs, 4 n-tiles per cluster walk, accumulator double buffering
 ])
 def test_conv_forms(cfg):
     run_conv(*cfg)

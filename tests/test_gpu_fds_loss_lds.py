@@ -331,3 +331,73 @@ def test_stsb_lds_weights_vs_reference_golden(tag, kw):
     assert w.is_cuda and w.dtype == torch.float32 and w.numel() == g["scores"].size
     assert_close(w.cpu().numpy(), g[f"w_{tag}"], rtol=2e-6, atol=0, what=tag)
     assert stsb_prepare_weights(g["scores"], "none") is None
+
+
+# ------------------------------------------------- BASELINE configs 4 and 5 at their own size
+def test_fds_depth_config4_full_size_vs_oracle():
+    """BASELINE config 4: the refinement input [32, 128, 240, 320] -> 2 457 600 pixel rows x 128 channels, depth bins
+    clamp(int(d*10), 7, 99).  Bins bit-exact, per-bin statistics within 1e-5 of the oracle, and the calibration of the
+    whole map (FDS.smooth, 1.26 GB in place) against the oracle on a strided sample of rows."""
+    import _lib
+    from fds_variants import FDSDepth
+    torch.manual_seed(4)
+    B, C, H, W = 32, 128, 240, 320
+    feats = torch.relu(torch.randn(B, C, H, W, device=DEV) + 0.4)
+    depth = torch.rand(B, 1, H, W, device=DEV) * 9.3 + 0.7
+    m = FDSDepth(C).to(DEV)
+    lab = depth.reshape(-1)
+    bins = torch.empty(lab.numel(), dtype=torch.int32, device=DEV)
+    flags = torch.zeros(2, dtype=torch.int32, device=DEV)
+    _lib.call("dirb200_fds_bin_rows", _lib.ptr(lab), lab.numel(), 100, 7, _lib.BIN_DEPTH10, _lib.ptr(flags), _lib.ptr(bins),
+              _lib.stream_ptr())
+    lab_np = lab.cpu().numpy()
+    want_bins = O.bin_index_depth10(lab_np, 100, 7)
+    assert np.array_equal(bins.cpu().numpy(), want_bins)
+    m.update_running_stats(feats, depth, 0)
+    rows = feats.permute(0, 2, 3, 1).reshape(-1, C).cpu().numpy()
+    cnt, mean, var = O.fds_stats_from_bins(rows, want_bins, 93)
+    assert np.array_equal(m.num_samples_tracked.cpu().numpy().astype(np.int64), cnt) and cnt.sum() == B * H * W
+    has = cnt > 0
+    assert_close(m.running_mean.cpu().numpy()[has], mean[has], rtol=1e-5, atol=1e-6, what="mean")
+    assert_close(m.running_var.cpu().numpy()[has], var[has], rtol=1e-5, atol=1e-6, what="var")
+    # second epoch: tables move, smoothing of the full map against the oracle on every 4 801st pixel row
+    m.update_last_epoch_stats(1)
+    m.update_running_stats(feats, depth, 1)
+    sel = np.arange(0, B * H * W, 4801)
+    before = rows[sel].copy()
+    out = m.smooth(feats, depth, 1)
+    got = out.permute(0, 2, 3, 1).reshape(-1, C)[torch.from_numpy(sel).to(DEV)].cpu().numpy()
+    tabs = [getattr(m, k).cpu().numpy() for k in ("running_mean_last_epoch", "running_var_last_epoch",
+                                                   "smoothed_mean_last_epoch", "smoothed_var_last_epoch")]
+    want = before.copy()
+    sb = want_bins[sel]
+    for b in np.unique(sb):
+        r = sb == b
+        want[r] = O.calibrate_mean_var_v2(before[r], tabs[0][b], tabs[1][b], tabs[2][b], tabs[3][b], 0.2, 5.0)
+    assert_close(got, want, rtol=1e-5, atol=1e-5, what="smooth")
+
+
+def test_fds_stsb_config5_full_size_vs_oracle():
+    """BASELINE config 5: feature_dim 12 000 (sts-b-dir/models.py:46-49), 50 score buckets over [0, 5], one epoch of
+    the STS-B training set (5 749 sentence pairs) + a batch-128 smooth: statistics, empty-bucket fill and calibration
+    against the oracle state machine."""
+    from fds_variants import FDSSTSB
+    rng = np.random.RandomState(9)
+    N, D, Bs = 5749, 12000, 128
+    feats = (rng.randn(N, D).astype(np.float32) * 0.5 + 0.3)
+    scores = np.round(rng.beta(2.0, 1.5, size=N) * 5 * 4) / 4          # quarter-point scores as in STS-B
+    scores = scores.astype(np.float32)
+    m = FDSSTSB(D).to(DEV)
+    ref = O.FDSVariantState("stsb", D, 50, 0)
+    for ep in (0, 1):
+        m.update_last_epoch_stats(ep)
+        ref.update_last_epoch_stats(ep)
+        m.update_running_stats(T(feats), T(scores), ep)
+        ref.update_running_stats(feats, scores, ep)
+        for k in ("running_mean", "running_var", "smoothed_mean_last_epoch", "smoothed_var_last_epoch",
+                  "num_samples_tracked"):
+            assert_close(getattr(m, k).cpu().numpy(), getattr(ref, k), rtol=1e-5, atol=1e-6, what=f"{k} e{ep}")
+    xb, lb = feats[:Bs].copy(), scores[:Bs]
+    got = m.smooth(T(xb), T(lb).reshape(-1, 1), 1).cpu().numpy()
+    want = ref.smooth(xb.copy(), lb, 1)
+    assert_close(got, want, rtol=1e-5, atol=1e-5, what="smooth")

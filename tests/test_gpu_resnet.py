@@ -11,6 +11,8 @@ from util import det_param
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+torch.backends.cudnn.allow_tf32 = False          # the oracle's convolutions are true fp32
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def make_model(fds=False, layers=(3, 4, 6, 3), **kw):
@@ -103,7 +105,7 @@ def test_forward_backward_vs_oracle_shallow():
     assert rel(m.flat_grads(), flat_ref) < 0.4, rel(m.flat_grads(), flat_ref)
 
 
-@pytest.mark.parametrize("n,hw", [(16, 64), (4, 224)])
+@pytest.mark.parametrize("n,hw", [(16, 64), (4, 224), (256, 224)], ids=["b16_64", "b4_224", "benchmark_b256_224"])
 def test_resnet50_layerwise_forward_teacher_forced(n, hw):
     """Every conv / BN+ReLU / residual stage of the full ResNet-50, each checked against the oracle op applied to
     the runner's OWN input of that stage (so errors cannot compound): relative L2 error <= 4e-3 (a bf16 ulp)."""
@@ -112,7 +114,9 @@ def test_resnet50_layerwise_forward_teacher_forced(n, hw):
     m = make_model()
     m.train()
     p = {k: v.detach() for k, v in m.named_parameters()}
-    x = det_param(f"x{n}", (n, 3, hw, hw), 1.0).to(DEV)
+    x = det_param(f"x{n}", (min(n, 16), 3, hw, hw), 1.0).to(DEV)
+    if n > 16:     # the benchmark batch: 16 generated images tiled with per-image gains (cheap to build, all distinct)
+        x = (x.repeat(n // 16, 1, 1, 1) * torch.linspace(0.5, 1.5, n, device=DEV).reshape(n, 1, 1, 1)).contiguous()
     m._run_forward(x, training=True)
     shape = tuple(x.shape)
     pk = lambda b, w: m.peek(shape, b, w)
@@ -153,7 +157,9 @@ def test_resnet50_layerwise_forward_teacher_forced(n, hw):
 TAPS = [("stem.y", -1, 0), ("stem.a", -1, 1), ("stem.pool", -1, 6)]
 
 
-@pytest.mark.parametrize("layers,n,hw", [((3, 4, 6, 3), 16, 64), ((3, 4, 6, 3), 4, 224), ((2, 2, 1, 1), 16, 64)])
+@pytest.mark.parametrize("layers,n,hw", [((3, 4, 6, 3), 16, 64), ((3, 4, 6, 3), 4, 224), ((2, 2, 1, 1), 16, 64),
+                                         ((3, 4, 6, 3), 256, 224)],
+                         ids=["r50_b16_64", "r50_b4_224", "shallow_b16_64", "r50_benchmark_b256_224"])
 def test_backward_vs_oracle_teacher_forced(layers, n, hw):
     """Backward parity at full depth: the oracle's forward is teacher-forced to the runner's stored activations
     (same ReLU masks, same BN inputs), its backward is torch autograd in fp32 with bf16 rounding at the points where
@@ -163,8 +169,10 @@ def test_backward_vs_oracle_teacher_forced(layers, n, hw):
     m = make_model(layers=layers)
     m.train()
     p = oracle_params(m)
-    x = det_param(f"x{n}", (n, 3, hw, hw), 1.0).to(DEV)
-    t = (torch.arange(n, dtype=torch.float32, device=DEV).reshape(n, 1) * 5 + 10)
+    x = det_param(f"x{n}", (min(n, 16), 3, hw, hw), 1.0).to(DEV)
+    if n > 16:     # the benchmark batch (BASELINE config 3 shape): tiled + per-image gains, see the forward test
+        x = (x.repeat(n // 16, 1, 1, 1) * torch.linspace(0.5, 1.5, n, device=DEV).reshape(n, 1, 1, 1)).contiguous()
+    t = (torch.arange(n, dtype=torch.float32, device=DEV).reshape(n, 1) * 5 + 10) % 101
     w = torch.linspace(0.5, 1.5, n, device=DEV).reshape(n, 1)
     pred = m(x, t, 0)
     L.weighted_l1_loss(pred, t, w).backward()
@@ -172,7 +180,7 @@ def test_backward_vs_oracle_teacher_forced(layers, n, hw):
     names = list(TAPS) + [(f"{b}.{k}", b, k) for b in range(sum(layers)) for k in range(7)]
     for name, b, k in names:
         try:
-            force[name] = m.peek(x.shape, b, k)
+            force[name] = m.peek(x.shape, b, k, copy=n <= 16)   # big batch: zero-copy bf16 views of the runner's buffers
         except Exception:
             pass                                   # blocks without a downsample branch
     assert len(force) == 3 + 6 * sum(layers) + 4
@@ -266,3 +274,52 @@ def test_fds_model_training_step_smooth_active():
     assert not torch.allclose(enc, raw)              # encoding returned is the smoothed one (in-place alias)
     L.weighted_l1_loss(pred, t, torch.ones_like(t)).backward()
     assert m.conv1.weight.grad.abs().sum() > 0 and torch.isfinite(m.flat_grads()).all()
+
+
+@pytest.mark.parametrize("clip", [None, 0.05], ids=["plain", "max_grad_norm"])
+def test_fused_sgd_matches_torch_sgd(clip):
+    """dirb200_sgd_step (agedb-dir/train.py:164: SGD, momentum 0.9, weight decay 1e-4) over the flat buffers against
+    torch.optim.SGD driven by the same gradients, 4 steps; with max_grad_norm also dirb200_grad_clip_coef against
+    torch.nn.utils.clip_grad_norm_ (sts-b-dir/trainer.py:147-149)."""
+    from optim import FusedSGD
+    m = make_model(layers=(1, 1, 1, 1))
+    m.train()
+    params = list(m.parameters())
+    opt = FusedSGD(params, lr=0.05, momentum=0.9, weight_decay=1e-4, max_grad_norm=clip)
+    shadow = [p.detach().clone().requires_grad_(True) for p in params]
+    ref_opt = torch.optim.SGD(shadow, lr=0.05, momentum=0.9, weight_decay=1e-4)
+    g = torch.Generator(device=DEV).manual_seed(11)
+    flat = m.flat_grads()
+    for step in range(4):
+        flat.copy_(torch.randn(flat.numel(), generator=g, device=DEV) * (1e-3 * (step + 1)))
+        for s, p in zip(shadow, params):
+            s.grad = p.grad.detach().clone()
+        if clip:
+            want_norm = torch.nn.utils.clip_grad_norm_(shadow, clip)
+        opt.step()
+        ref_opt.step()
+        if clip:
+            assert abs(float(opt.last_grad_norm()) - float(want_norm)) <= 1e-5 * float(want_norm)
+        for s, p in zip(shadow, params):
+            assert torch.allclose(s, p, rtol=2e-6, atol=1e-8), (step, (s - p).abs().max().item())
+
+
+def test_fused_adam_with_grad_clip_matches_torch():
+    from optim import FusedAdam
+    m = make_model(layers=(1, 1, 1, 1))
+    m.train()
+    params = list(m.parameters())
+    opt = FusedAdam(params, lr=1e-3, max_grad_norm=1.0)
+    shadow = [p.detach().clone().requires_grad_(True) for p in params]
+    ref_opt = torch.optim.Adam(shadow, lr=1e-3)
+    g = torch.Generator(device=DEV).manual_seed(12)
+    flat = m.flat_grads()
+    for step in range(3):
+        flat.copy_(torch.randn(flat.numel(), generator=g, device=DEV) * 0.01)
+        for s, p in zip(shadow, params):
+            s.grad = p.grad.detach().clone()
+        torch.nn.utils.clip_grad_norm_(shadow, 1.0)
+        opt.step()
+        ref_opt.step()
+        for s, p in zip(shadow, params):
+            assert torch.allclose(s, p, rtol=1e-5, atol=1e-7)

@@ -230,3 +230,16 @@ def test_stsb_host_mirror_from_oracle_bins(tag):
     w, hist = datasets.stsb_weights_from_bins(bins, **STSB_LDS[tag])
     assert np.array_equal(hist, g["hist"])
     assert_close(w, g[f"w_{tag}"], rtol=2e-6, atol=0, what=tag)
+
+
+def test_fds_stats_from_bins_equals_per_bin_loop():
+    """The vectorised statistics used by the BASELINE-size GPU tests == the per-bin loop restatement of fds.py:100-102."""
+    rng = np.random.RandomState(5)
+    for (bn, bs, n, d) in ((100, 3, 3000, 40), (101, 0, 500, 700), (50, 10, 64, 5)):
+        labels = rng.randint(0, 125, size=n).astype(np.float32)
+        feats = np.maximum(rng.randn(n, d).astype(np.float32) * 0.7 + 2.0, 0)
+        cnt, mean, var = O.fds_batch_stats(feats, labels, bn, bs)
+        cnt2, mean2, var2 = O.fds_stats_from_bins(feats, O.fds_bin_index(labels, bn, bs), bn - bs)
+        assert np.array_equal(cnt, cnt2)
+        np.testing.assert_allclose(mean2, mean, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(var2, var, rtol=1e-5, atol=1e-7)
