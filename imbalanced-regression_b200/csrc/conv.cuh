@@ -8,11 +8,19 @@ struct ConvShape {
   int n, h, w, cin, cout, kh, kw, stride, pad, ho, wo;
 };
 
+// Which rows of a per-CTA statistics buffer [rows][2][c] hold the partial sums of a channel: the CTAs (or CTA pairs,
+// group = 2) are dealt round-robin over the n_tiles column tiles of width bn, so channel ch lives in the rows
+// (j + k * n_tiles) * group + r   with j = ch / bn, k = 0 .. while the row index < rows, r = 0 .. group-1.
+// A plain column reduction over all rows is {rows, 1, c, 1}.
+struct StatLayout {
+  int rows, n_tiles, bn, group;
+};
+
 // stat_partial (optional): the epilogue also accumulates, per output channel, the sum and the sum of squares of the
-// stored outputs into stat_partial[row][2][cout] (row = (CTA, epilogue warp); *stat_rows rows are in use; the buffer
-// must be all-zero on entry outside what this launch writes) -- the BatchNorm batch statistics without re-reading y.
+// stored outputs into stat_partial[CTA][2][cout] (rows / columns as *layout describes; everything it names is
+// written, nothing else is touched) -- the BatchNorm batch statistics without re-reading y.
 int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, const ConvShape& s, bool stem,
-               cudaStream_t st, float* stat_partial = nullptr, int* stat_rows = nullptr);
+               cudaStream_t st, float* stat_partial = nullptr, StatLayout* layout = nullptr);
 int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* dx, const ConvShape& s,
                cudaStream_t st);
 int conv_wgrad_splits(const ConvShape& s);

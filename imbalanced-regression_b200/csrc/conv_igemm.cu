@@ -81,9 +81,9 @@ struct IgemmParams {
   int ldc;                   // output row stride in elements (Cout for fprop, Cin for dgrad, Cout for wgrad partials)
   void* out;                 // bf16 [pixels][ldc]   or   fp32 [splits][total_chunks*64][ldc]
   // fprop only, optional: per-column sum / sum of squares of the (bf16-rounded) output = the BatchNorm batch
-  // statistics of the layer, carried in the epilogue warps' registers over all tiles of the CTA and written once as
-  // stat_out[(blockIdx.x * 4 + epilogue warp)][2][ldc] (fp32; rows / columns a CTA does not own are left untouched:
-  // the buffer is kept all-zero between uses by its consumer, bn_finalize)
+  // statistics of the layer, carried in the epilogue warps' registers over all tiles of the CTA and written once per
+  // CTA as stat_out[blockIdx.x][2][ldc] (fp32), columns [n_tile * BN, n_tile * BN + BN) of the CTA's fixed n_tile only
+  // (see StatLayout for which rows hold which columns)
   float* stat_out;
 };
 
@@ -686,22 +686,24 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           }
           if (P.stat_out != nullptr) {
             // column sums over this warp's 32 rows: lane l owns columns 2l, 2l+1 of the pass (one bf16x2 word per
-            // row; rows past the end of the tensor hold zeros).  Word (36 r + l): conflict-free.
-            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            // row; rows past the end of the tensor hold zeros).  Word (36 r + l): conflict-free.  Plain (non-volatile)
+            // loads so that all 32 are in flight together, packed fp32 adds / FMAs (FADD2 / FFMA2), two chains.
+            const uint32_t* sp = reinterpret_cast<const uint32_t*>(smem_raw + (stage_base - smem_u32(smem_raw))) + lane;
+            float2 sa = make_float2(0.f, 0.f), qa = sa, sb = sa, qb = sa;
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              uint32_t w;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(stage_base + r * C::kStageRowBytes + lane * 4));
-              const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
-              s0 += lo;
-              s1 += hi;
-              q0 = fmaf(lo, lo, q0);
-              q1 = fmaf(hi, hi, q1);
+            for (int r = 0; r < 32; r += 2) {
+              const uint32_t w0 = sp[r * (C::kStageRowBytes / 4)], w1 = sp[(r + 1) * (C::kStageRowBytes / 4)];
+              const float2 v0 = make_float2(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xffff0000u));
+              const float2 v1 = make_float2(__uint_as_float(w1 << 16), __uint_as_float(w1 & 0xffff0000u));
+              sa = __fadd2_rn(sa, v0);
+              qa = __ffma2_rn(v0, v0, qa);
+              sb = __fadd2_rn(sb, v1);
+              qb = __ffma2_rn(v1, v1, qb);
             }
-            stat[cb][0] += s0;
-            stat[cb][1] += s1;
-            stat[cb][2] += q0;
-            stat[cb][3] += q1;
+            stat[cb][0] += sa.x + sb.x;
+            stat[cb][1] += sa.y + sb.y;
+            stat[cb][2] += qa.x + qb.x;
+            stat[cb][3] += qa.y + qb.y;
           }
           __syncwarp();                                         // staging tile is reused by the next pass / tile
         }
@@ -732,13 +734,28 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
       }
     }
     if constexpr (!WGRAD) {
-      if (P.stat_out != nullptr && tile_first < tile_end) {
-        // one flush per (CTA, epilogue warp): [row][0][c] = sums, [row][1][c] = sums of squares
-        float* dst = P.stat_out + (static_cast<size_t>(blockIdx.x) * 4 + quarter) * 2 * P.ldc + fixed_n * BN + 2 * lane;
+      if (P.stat_out != nullptr) {
+        // one flush per CTA: the four epilogue warps combine their column sums through their staging tiles (fixed
+        // order -> deterministic) and write stat_out[blockIdx.x][0][c] = sums, [1][c] = sums of squares for the BN
+        // columns of this CTA's n_tile.  Every CTA of the launch owns >= 1 tile (grid <= tiles), so every row of
+        // its n_tile's column range is written: the consumer (bn_finalize) reads exactly those, no zero-fill needed.
+        constexpr int NCB = BN / C::kEpiCols;
+        float* mine = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + C::kEpiOffset +
+                                               quarter * C::kEpiWarpBytes);
 #pragma unroll
-        for (int cb = 0; cb < BN / C::kEpiCols; ++cb) {
-          *reinterpret_cast<float2*>(dst + cb * C::kEpiCols) = make_float2(stat[cb][0], stat[cb][1]);
-          *reinterpret_cast<float2*>(dst + P.ldc + cb * C::kEpiCols) = make_float2(stat[cb][2], stat[cb][3]);
+        for (int cb = 0; cb < NCB; ++cb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mine[(cb * 4 + k) * 32 + lane] = stat[cb][k];
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
+        const float* all = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + C::kEpiOffset);
+        constexpr int kWarpFloats = C::kEpiWarpBytes / 4;
+        float* dst = P.stat_out + static_cast<size_t>(blockIdx.x) * 2 * P.ldc + fixed_n * BN;
+        for (int o = quarter * 32 + lane; o < 2 * BN; o += 128) {
+          const int k = o / BN, col = o - k * BN;
+          const int cb = col / C::kEpiCols, ln = (col % C::kEpiCols) >> 1, e = col & 1;
+          const int idx = (cb * 4 + k * 2 + e) * 32 + ln;
+          const float v = (all[idx] + all[kWarpFloats + idx]) + (all[2 * kWarpFloats + idx] + all[3 * kWarpFloats + idx]);
+          dst[static_cast<size_t>(k) * P.ldc + col] = v;
         }
       }
     }
@@ -836,7 +853,7 @@ int make_tmap_im2col_bf16(CUtensorMap* tm, const void* ptr, int c, int w, int h,
   return DIRB200_OK;
 }
 
-static thread_local int t_last_grid = 0;     // CTAs of the most recent igemm launch of this thread
+static thread_local StatLayout t_last_layout{};     // row layout of the statistics the most recent fprop launch wrote
 
 // Host-side completion of the launch parameters: reciprocal constants for every run-time divisor the kernel meets and
 // the per-tap tables (gather offset, im2col offsets) indexed by the position in tap_list.
@@ -881,7 +898,7 @@ static int launch_igemm_impl(const CUtensorMap& tm, const CUtensorMap& tma, cons
     configured = true;
   }
   const int grid = Q.num_tiles < num_sms() ? Q.num_tiles : num_sms();
-  t_last_grid = grid;
+  t_last_layout = StatLayout{grid, Q.n_tiles, BN, 1};
   igemm_kernel<BN, WGRAD, STEM, BSTAT, false, ATMA><<<grid, kThreads, C::kSmemBytes, st>>>(tm, tma, Q);
   DIRB_LAUNCHED();
   return DIRB200_OK;
@@ -924,7 +941,7 @@ static int launch_igemm_cta2(const CUtensorMap& tm, const CUtensorMap& tma, cons
   }
   const int pairs = Q.num_tiles < max_pairs ? Q.num_tiles : max_pairs;
   cfg.gridDim = dim3(2 * pairs, 1, 1);
-  t_last_grid = 2 * pairs;
+  t_last_layout = StatLayout{2 * pairs, Q.n_tiles, BN, 2};
   DIRB_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, tma, Q));
   DIRB_LAUNCHED();
   return DIRB200_OK;
@@ -1023,9 +1040,9 @@ static int conv_fprop_impl(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_
                            cudaStream_t st, float* stat_partial);
 
 int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, const ConvShape& s, bool stem,
-               cudaStream_t st, float* stat_partial, int* stat_rows) {
+               cudaStream_t st, float* stat_partial, StatLayout* layout) {
   const int rc = conv_fprop_impl(x, w, y, s, stem, st, stat_partial);
-  if (stat_rows) *stat_rows = 4 * t_last_grid;    // one partial row per (CTA, epilogue warp)
+  if (layout) *layout = t_last_layout;
   return rc;
 }
 

@@ -1,13 +1,14 @@
 // Internal (C++) interface of the HBM-bound ResNet layers (nn_kernels.cu).
 #pragma once
 #include "common.cuh"
+#include "conv.cuh"
 
 namespace dirb200 {
 
 int bn_partial_floats(int max_c);   // size of the per-CTA partial buffer shared by the column reductions
 int bn_stats(const __nv_bfloat16* y, int64_t rows, int c, float* partial, int* nblocks, cudaStream_t st);
-// clear: zero every partial once read (partials written by the conv fprop epilogue, see IgemmParams::stat_out)
-int bn_finalize(float* partial, int nblocks, bool clear, int64_t rows, int c, const float* gamma, const float* beta,
+// partial: [rows][2][c] column sums / sums of squares, rows per channel as `layout` says (conv.cuh)
+int bn_finalize(const float* partial, const StatLayout& layout, int64_t rows, int c, const float* gamma, const float* beta,
                 float eps, float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
                 float* scale, float* shift, cudaStream_t st);
 int bn_eval_coeffs(int c, const float* gamma, const float* beta, float eps, const float* running_mean,

@@ -4,6 +4,7 @@
 // Replaces nn.BatchNorm2d / nn.ReLU / nn.MaxPool2d / nn.AvgPool2d / nn.Linear of
 // agedb-dir/resnet.py:41-70,79-88,127-148 and torch.optim of agedb-dir/train.py:163-164.
 #include "common.cuh"
+#include "conv.cuh"
 #include "nn.cuh"
 
 namespace dirb200 {
@@ -71,32 +72,24 @@ __device__ __forceinline__ void column_reduce_finish(float (&acc)[K][8], int cg,
 // both slots are fetched in the same pass so that four independent loads are in flight per thread (these tiny
 // kernels sit on the critical path between two streaming kernels, 106 times per step: pure latency).
 // Valid in threads with threadIdx.y == 0 after the call.
-// CLEAR: every value is replaced by zero once read (the fprop epilogue only writes the rows / columns its CTAs own
-// and relies on the rest of the buffer being zero).
-template <bool CLEAR = false>
-__device__ __forceinline__ void sum_partials2(float* __restrict__ partial, int nblocks, int K, int s0, int s1,
+__device__ __forceinline__ void sum_partials2(const float* __restrict__ partial, int nblocks, int K, int s0, int s1,
                                               int c, int ch, double (*sh)[32], double& r0, double& r1) {
   double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
   if (ch < c) {
     int b = threadIdx.y;
     for (; b + 32 < nblocks; b += 64) {
-      float* p00 = partial + ((size_t)b * K + s0) * c + ch;
-      float* p01 = partial + ((size_t)b * K + s1) * c + ch;
-      float* p10 = partial + ((size_t)(b + 32) * K + s0) * c + ch;
-      float* p11 = partial + ((size_t)(b + 32) * K + s1) * c + ch;
-      const float x0 = *p00, y0 = *p01, x1 = *p10, y1 = *p11;
-      if (CLEAR) { *p00 = 0.f; *p01 = 0.f; *p10 = 0.f; *p11 = 0.f; }
+      const float x0 = partial[((size_t)b * K + s0) * c + ch];
+      const float y0 = partial[((size_t)b * K + s1) * c + ch];
+      const float x1 = partial[((size_t)(b + 32) * K + s0) * c + ch];
+      const float y1 = partial[((size_t)(b + 32) * K + s1) * c + ch];
       a0 += (double)x0;
       b0 += (double)y0;
       a1 += (double)x1;
       b1 += (double)y1;
     }
     if (b < nblocks) {
-      float* p00 = partial + ((size_t)b * K + s0) * c + ch;
-      float* p01 = partial + ((size_t)b * K + s1) * c + ch;
-      a0 += (double)*p00;
-      b0 += (double)*p01;
-      if (CLEAR) { *p00 = 0.f; *p01 = 0.f; }
+      a0 += (double)partial[((size_t)b * K + s0) * c + ch];
+      b0 += (double)partial[((size_t)b * K + s1) * c + ch];
     }
   }
   sh[threadIdx.y][threadIdx.x] = a0 + a1;
@@ -146,17 +139,43 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ y, int64_t rows, int c, float*
 
 // mean / invstd / scale / shift from the accumulated sums; running statistics as nn.BatchNorm2d (momentum 0.1,
 // unbiased running variance).
-template <bool CLEAR>
-__global__ void bn_finalize_kernel(float* __restrict__ partial, int nblocks, int64_t rows, int c,
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, StatLayout L, int64_t rows, int c,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                    float* __restrict__ scale, float* __restrict__ shift) {
-  __shared__ double sh[32][32];
+  __shared__ double sh[2][32][32];
   const int i = blockIdx.x * 32 + threadIdx.x;
-  double sx, sq;
-  sum_partials2<CLEAR>(partial, nblocks, 2, 0, 1, c, i, sh, sx, sq);
+  double a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
+  if (i < c) {
+    // rows that hold channel i (see StatLayout): CTA groups j, j + n_tiles, ...; `group` consecutive rows each
+    const int j = i / L.bn;
+    const int ngroups = L.rows / L.group;
+    const int nk = j < ngroups ? (ngroups - 1 - j) / L.n_tiles + 1 : 0;
+    const int nrows = nk * L.group;
+    int t = threadIdx.y;
+    for (; t + 32 < nrows; t += 64) {            // four independent loads in flight
+      const int r0 = (j + (t / L.group) * L.n_tiles) * L.group + t % L.group;
+      const int r1 = (j + ((t + 32) / L.group) * L.n_tiles) * L.group + (t + 32) % L.group;
+      const float x0 = partial[((size_t)r0 * 2) * c + i], y0 = partial[((size_t)r0 * 2 + 1) * c + i];
+      const float x1 = partial[((size_t)r1 * 2) * c + i], y1 = partial[((size_t)r1 * 2 + 1) * c + i];
+      a0 += (double)x0; b0 += (double)y0; a1 += (double)x1; b1 += (double)y1;
+    }
+    if (t < nrows) {
+      const int r0 = (j + (t / L.group) * L.n_tiles) * L.group + t % L.group;
+      a0 += (double)partial[((size_t)r0 * 2) * c + i];
+      b0 += (double)partial[((size_t)r0 * 2 + 1) * c + i];
+    }
+  }
+  sh[0][threadIdx.y][threadIdx.x] = a0 + a1;
+  sh[1][threadIdx.y][threadIdx.x] = b0 + b1;
+  __syncthreads();
   if (threadIdx.y != 0 || i >= c) return;
+  double sx = 0.0, sq = 0.0;
+  for (int w = 0; w < 32; ++w) {
+    sx += sh[0][w][threadIdx.x];
+    sq += sh[1][w][threadIdx.x];
+  }
   const double n = (double)rows;
   const double m = sx / n;
   double var = sq / n - m * m;
@@ -357,7 +376,7 @@ __global__ void bn_bwd_coeffs_kernel(const float* __restrict__ partial, int nblo
   __shared__ double sh[32][32];
   const int i = blockIdx.x * 32 + threadIdx.x;
   double db, s1;
-  sum_partials2<false>(const_cast<float*>(partial), nblocks, K, 0, gslot, c, i, sh, db, s1);
+  sum_partials2(partial, nblocks, K, 0, gslot, c, i, sh, db, s1);
   if (threadIdx.y != 0 || i >= c) return;
   const double n = (double)rows, is = (double)invstd[i], ga = (double)gamma[i], mu = (double)mean[i];
   const double dg = is * (s1 - mu * db);          // sum dz * xhat from the raw moments
@@ -729,10 +748,23 @@ static inline int stream_grid(int64_t rows, int lanes) {
 
 int bn_partial_floats(int max_c) { return kReduceCtasPerSm * num_sms() * 3 * max_c; }
 
-static inline int reduce_grid(int64_t rows, int lanes) {
+static inline int reduce_grid(int64_t rows, int lanes, int ctas_per_sm = kReduceCtasPerSm) {
   int64_t g = (rows + (int64_t)lanes * 16 - 1) / ((int64_t)lanes * 16);   // >= ~16 rows per thread
-  const int64_t cap = kReduceCtasPerSm * (int64_t)num_sms();
+  if (ctas_per_sm > kReduceCtasPerSm) ctas_per_sm = kReduceCtasPerSm;     // the partial buffer holds 4 rows per SM
+  const int64_t cap = ctas_per_sm * (int64_t)num_sms();
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// CTAs of `kernel` (256 threads, `smem` dynamic bytes) that fit on one SM: the row-walking kernels are launched with
+// exactly one resident wave (a grid of 4 x SMs on a kernel that fits 3 per SM runs a second, one-third-full wave).
+template <typename K>
+static int resident_ctas(K kernel, size_t smem) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem) != cudaSuccess || occ < 1) {
+    (void)cudaGetLastError();
+    occ = 2;
+  }
+  return occ;
 }
 
 // ------------------------------------------------------------- host wrappers
@@ -746,15 +778,14 @@ int bn_stats(const __nv_bfloat16* y, int64_t rows, int c, float* partial, int* n
   return DIRB200_OK;
 }
 
-int bn_finalize(float* partial, int nblocks, bool clear, int64_t rows, int c, const float* gamma, const float* beta,
-                float eps, float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
-                float* scale, float* shift, cudaStream_t st) {
-  if (clear)
-    bn_finalize_kernel<true><<<(c + 31) / 32, dim3(32, 32), 0, st>>>(partial, nblocks, rows, c, gamma, beta, eps, momentum,
-                                                                   running_mean, running_var, mean, invstd, scale, shift);
-  else
-    bn_finalize_kernel<false><<<(c + 31) / 32, dim3(32, 32), 0, st>>>(partial, nblocks, rows, c, gamma, beta, eps, momentum,
-                                                                    running_mean, running_var, mean, invstd, scale, shift);
+int bn_finalize(const float* partial, const StatLayout& layout, int64_t rows, int c, const float* gamma,
+                const float* beta, float eps, float momentum, float* running_mean, float* running_var, float* mean,
+                float* invstd, float* scale, float* shift, cudaStream_t st) {
+  DIRB_CHECK_ARG(layout.rows > 0 && layout.n_tiles > 0 && layout.bn > 0 && layout.group > 0 &&
+                     layout.n_tiles * layout.bn >= c,
+                 "bn_finalize: bad statistics layout");
+  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, st>>>(partial, layout, rows, c, gamma, beta, eps, momentum,
+                                                             running_mean, running_var, mean, invstd, scale, shift);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
@@ -786,11 +817,14 @@ int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_b
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_bwd_reduce: unsupported channel count %d", c);
   DIRB_CHECK_ARG(mask || (scale && shift && !g2 && !y2), "bn_bwd_reduce: mask-from-y form takes one gradient, one BN");
   const int lanes = 256 / cgroups;
-  *nblocks = reduce_grid(rows, lanes);
-  const int grid = *nblocks;
   const size_t smem = 256 * (y2 ? 24 : 16) * sizeof(float);
-#define DIRB_RED(MODE, G2, Y2) \
-  bn_bwd_reduce_kernel<MODE, G2, Y2><<<grid, 256, smem, st>>>(g1, g2, y, y2, scale, shift, mask, rows, c, partial)
+#define DIRB_RED(MODE, G2, Y2)                                                                            \
+  do {                                                                                                    \
+    static const int occ = resident_ctas(bn_bwd_reduce_kernel<MODE, G2, Y2>, 256 * 24 * sizeof(float));   \
+    *nblocks = reduce_grid(rows, lanes, occ);                                                             \
+    bn_bwd_reduce_kernel<MODE, G2, Y2><<<*nblocks, 256, smem, st>>>(g1, g2, y, y2, scale, shift, mask, rows, c, \
+                                                                    partial);                             \
+  } while (0)
   if (!mask) DIRB_RED(MASK_FROM_Y, false, false);
   else if (g2 && y2) DIRB_RED(MASK_BITS, true, true);
   else if (g2) DIRB_RED(MASK_BITS, true, false);
@@ -818,10 +852,14 @@ int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bf
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_bwd_apply: unsupported channel count %d", c);
   DIRB_CHECK_ARG(mask || (scale && shift && !g2 && !y2 && !dz_out), "bn_bwd_apply: mask-from-y form takes one gradient, one BN");
   DIRB_CHECK_ARG(!(y2 && dz_out), "bn_bwd_apply: a block has either a downsample branch or an identity path");
-  const int grid = stream_grid(rows, 256 / cgroups);
-#define DIRB_APP(MODE, G2, Y2, DZ)                                                                                   \
-  bn_bwd_apply_kernel<MODE, G2, Y2, DZ><<<grid, 256, 0, st>>>(g1, g2, y, coef, y2, coef2, scale, shift, mask, rows, c, \
-                                                             dy, dy2, dz_out)
+  const int want = stream_grid(rows, 256 / cgroups);
+#define DIRB_APP(MODE, G2, Y2, DZ)                                                                                     \
+  do {                                                                                                                 \
+    static const int occ = resident_ctas(bn_bwd_apply_kernel<MODE, G2, Y2, DZ>, 0);                                    \
+    const int grid = want < occ * num_sms() ? want : occ * num_sms();                                                  \
+    bn_bwd_apply_kernel<MODE, G2, Y2, DZ><<<grid, 256, 0, st>>>(g1, g2, y, coef, y2, coef2, scale, shift, mask, rows, c, \
+                                                               dy, dy2, dz_out);                                       \
+  } while (0)
   if (!mask) DIRB_APP(MASK_FROM_Y, false, false, false);
   else if (g2 && y2) DIRB_APP(MASK_BITS, true, true, false);
   else if (g2 && dz_out) DIRB_APP(MASK_BITS, true, false, true);

@@ -55,13 +55,17 @@ struct dirb200_net {
   __nv_bfloat16* scratch[8] = {};
   float* wgrad_ws = nullptr;
   float* bn_partial = nullptr;   // per-CTA partial sums of the BN column reductions (backward)
-  float* stat_partial = nullptr; // per-(CTA, epilogue warp) BN statistics written by the conv fprop epilogue; all-zero
-                                 // between uses (bn_finalize clears what it reads)
+  float* stat_partial = nullptr; // per-CTA BN statistics [CTA][2][c] written by the conv fprop epilogue (conv.cuh)
   PrepDesc* prep_descs = nullptr; // device table for the single weight re-layout launch
   int num_convs = 0;
   size_t param_count = 0, running_count = 0, activation_bytes = 0;
   std::vector<void*> allocs;
   bool forward_was_training = false;
+  // backward runs stage by stage (layer4 .. layer1, stem) so that the caller can start the gradient all-reduce of a
+  // finished stage while the earlier stages still compute; the incoming-gradient buffers live here between the calls
+  std::vector<int> stage_begin;          // first block of stage s (1-based stages; stage_begin[num_stages+1] = #blocks)
+  int bwd_next_stage = -1;               // stage the next dirb200_resnet_backward_stage call must name (-1: none pending)
+  __nv_bfloat16 *bw_gA = nullptr, *bw_gB = nullptr, *bw_nA = nullptr, *bw_nB = nullptr, *bw_spareB = nullptr;
   // optional per-kernel-class timing (CUDA events around every launch group)
   bool profiling = false;
   struct ProfRec { int kind; cudaEvent_t a, b; };
@@ -131,8 +135,10 @@ static bool build(dirb200_net* net, const int* blocks_per_stage, int num_stages)
   int inplanes = 64;
   const __nv_bfloat16* cur = net->pool_out;
   size_t max_act = (size_t)net->stem.rows * 64;
+  net->stage_begin.assign(1, 0);
   for (int st = 0; st < num_stages; ++st) {
     const int planes = 64 << st;
+    net->stage_begin.push_back((int)net->blocks.size());
     for (int b = 0; b < blocks_per_stage[st]; ++b) {
       const int stride = (b == 0 && st > 0) ? 2 : 1;
       net->blocks.emplace_back();
@@ -153,6 +159,7 @@ static bool build(dirb200_net* net, const int* blocks_per_stage, int num_stages)
       h = h2; w = w2;
     }
   }
+  net->stage_begin.push_back((int)net->blocks.size());
   net->feat_c = inplanes;
   net->feat_hw = h * w;
   for (int i = 0; i < 8; ++i) NET_ALLOC(net->scratch[i], max_act * 2);
@@ -166,7 +173,6 @@ static bool build(dirb200_net* net, const int* blocks_per_stage, int num_stages)
   NET_ALLOC(net->wgrad_ws, ws);
   NET_ALLOC(net->bn_partial, sizeof(float) * bn_partial_floats(net->feat_c));
   NET_ALLOC(net->stat_partial, sizeof(float) * bn_partial_floats(net->feat_c));
-  if (cudaMemset(net->stat_partial, 0, sizeof(float) * bn_partial_floats(net->feat_c)) != cudaSuccess) return false;
   std::vector<PrepDesc> descs;
   auto add = [&](const ConvLayer& cv) {
     descs.push_back(PrepDesc{cv.w_off, cv.s.cout, cv.stem ? 3 : cv.s.cin, cv.stem ? 7 : cv.s.kh, cv.stem ? 7 : cv.s.kw,
@@ -235,11 +241,15 @@ static int conv_bn_forward(dirb200_net* net, ConvLayer& cv, const __nv_bfloat16*
   BNLayer& bn = cv.bn;
   if (training) {
     // batch statistics come out of the conv epilogue (per-CTA column sums of the rounded outputs): y is not re-read
-    int nblk = 0;
+    StatLayout lay{};
     const bool fused = fused_stats();
-    RUNP(kFprop, conv_fprop(in, cv.wf, cv.y, cv.s, cv.stem, st, fused ? net->stat_partial : nullptr, &nblk));
-    if (!fused) RUNP(kBnStats, bn_stats(cv.y, cv.rows, bn.c, net->stat_partial, &nblk, st));
-    RUNP(kBnStats, bn_finalize(net->stat_partial, nblk, true, cv.rows, bn.c, params + bn.gamma_off, params + bn.beta_off, 1e-5f,
+    RUNP(kFprop, conv_fprop(in, cv.wf, cv.y, cv.s, cv.stem, st, fused ? net->stat_partial : nullptr, &lay));
+    if (!fused) {
+      int nblk = 0;
+      RUNP(kBnStats, bn_stats(cv.y, cv.rows, bn.c, net->stat_partial, &nblk, st));
+      lay = StatLayout{nblk, 1, bn.c, 1};
+    }
+    RUNP(kBnStats, bn_finalize(net->stat_partial, lay, cv.rows, bn.c, params + bn.gamma_off, params + bn.beta_off, 1e-5f,
                                0.1f, running ? running + bn.rm_off : nullptr, running ? running + bn.rv_off : nullptr,
                                bn.mean, bn.invstd, bn.scale, bn.shift, st));
   } else {
@@ -360,17 +370,15 @@ int dirb200_resnet_forward(dirb200_net* net, const float* x_nchw, const float* p
   return DIRB200_OK;
 }
 
-/* d_enc fp32 [n, feature_dim] -> ACCUMULATES d loss / d parameter into grads (flat fp32, same layout as params).
- * Must follow a training-mode forward on the same net. */
-int dirb200_resnet_backward(dirb200_net* net, const float* d_enc, const float* params, float* grads, void* stream) {
-  DIRB_CHECK_ARG(net && d_enc && params && grads, "resnet_backward: null pointer");
-  DIRB_CHECK_ARG(net->forward_was_training, "resnet_backward: needs a preceding training-mode forward");
-  cudaStream_t st = as_stream(stream);
-  __nv_bfloat16 *gA = net->scratch[0], *gB = nullptr, *nA = net->scratch[2], *nB = net->scratch[3];
+}  // extern "C"
+
+namespace dirb200 {
+
+// blocks [lo, hi) in reverse order; the incoming gradient pair is net->bw_gA / bw_gB
+static int backward_blocks(dirb200_net* net, int lo, int hi, const float* params, float* grads, cudaStream_t st) {
+  __nv_bfloat16 *gA = net->bw_gA, *gB = net->bw_gB, *nA = net->bw_nA, *nB = net->bw_nB, *spareB = net->bw_spareB;
   __nv_bfloat16 *t1 = net->scratch[4], *t2 = net->scratch[5], *t3 = net->scratch[6];
-  __nv_bfloat16* spareB = net->scratch[1];
-  RUNP(kPool, avgpool_bwd(d_enc, net->n, net->feat_hw, net->feat_c, gA, st));
-  for (int bi = (int)net->blocks.size() - 1; bi >= 0; --bi) {
+  for (int bi = hi - 1; bi >= lo; --bi) {
     Block& B = net->blocks[bi];
     BNLayer& b3 = B.c3.bn;
     // ---- block output: out = relu(bn3(y3) + identity); dz = (gA + gB) * (out > 0)
@@ -411,10 +419,71 @@ int dirb200_resnet_backward(dirb200_net* net, const float* d_enc, const float* p
     nA = oldA; nB = oldB;
     spareB = nullptr;
   }
-  // ---- stem: maxpool -> bn1+relu -> conv1 (no data gradient needed)
-  RUNP(kPool, maxpool_bwd(gA, gB, net->pool_idx, net->n, net->stem.s.ho, net->stem.s.wo, 64, t3, st));
-  RUN(conv_bn_backward(net, net->stem, t3, params, grads, t1, st));
-  RUN(wgrad_step(net, net->x_s2d, t1, grads + net->stem.w_off, net->stem.s, true, st));
+  net->bw_gA = gA; net->bw_gB = gB; net->bw_nA = nA; net->bw_nB = nB; net->bw_spareB = spareB;
+  return DIRB200_OK;
+}
+
+}  // namespace dirb200
+
+extern "C" {
+
+/* One stage of the backward pass: stage = number of stages (4 for ResNet-50) first -- average-pool backward of
+ * d_enc and the last layer group --, then stage-1 ... 1 (layer groups), finally 0 (max-pool, stem BN, conv1).  Calls
+ * must come in exactly that order after a training-mode forward; each ACCUMULATES the parameter gradients of its own
+ * stage into grads (flat fp32, same layout as params), whose range dirb200_resnet_stage_param_range reports -- a
+ * finished range can be all-reduced while the remaining stages run (agedb-dir/train.py:143,261: DataParallel's
+ * gradient reduction, here overlapped).  d_enc is only read by the first call. */
+int dirb200_resnet_backward_stage(dirb200_net* net, int stage, const float* d_enc, const float* params, float* grads,
+                                  void* stream) {
+  DIRB_CHECK_ARG(net && params && grads, "resnet_backward_stage: null pointer");
+  const int nst = (int)net->stage_begin.size() - 2;
+  DIRB_CHECK_ARG(stage >= 0 && stage <= nst, "resnet_backward_stage: bad stage %d", stage);
+  cudaStream_t st = as_stream(stream);
+  if (stage == nst) {
+    DIRB_CHECK_ARG(net->forward_was_training, "resnet_backward: needs a preceding training-mode forward");
+    DIRB_CHECK_ARG(d_enc, "resnet_backward_stage: the first stage needs d_enc");
+    net->bw_gA = net->scratch[0]; net->bw_gB = nullptr; net->bw_nA = net->scratch[2]; net->bw_nB = net->scratch[3];
+    net->bw_spareB = net->scratch[1];
+    RUNP(kPool, avgpool_bwd(d_enc, net->n, net->feat_hw, net->feat_c, net->bw_gA, st));
+  } else {
+    DIRB_CHECK_ARG(net->bwd_next_stage == stage, "resnet_backward_stage: stage %d out of order (expected %d)", stage,
+                   net->bwd_next_stage);
+  }
+  net->bwd_next_stage = -1;
+  if (stage >= 1) {
+    RUN(backward_blocks(net, net->stage_begin[stage], net->stage_begin[stage + 1], params, grads, st));
+  } else {
+    // ---- stem: maxpool -> bn1+relu -> conv1 (no data gradient needed)
+    __nv_bfloat16 *t1 = net->scratch[4], *t3 = net->scratch[6];
+    RUNP(kPool, maxpool_bwd(net->bw_gA, net->bw_gB, net->pool_idx, net->n, net->stem.s.ho, net->stem.s.wo, 64, t3, st));
+    RUN(conv_bn_backward(net, net->stem, t3, params, grads, t1, st));
+    RUN(wgrad_step(net, net->x_s2d, t1, grads + net->stem.w_off, net->stem.s, true, st));
+  }
+  net->bwd_next_stage = stage - 1;          // -1 after the stem: nothing pending
+  return DIRB200_OK;
+}
+
+/* Parameters of stage `stage` (0 = stem conv1 + bn1, s = layer group s) occupy [*lo, *hi) of the flat buffers. */
+int dirb200_resnet_stage_param_range(const dirb200_net* net, int stage, int64_t* lo, int64_t* hi) {
+  DIRB_CHECK_ARG(net && lo && hi, "resnet_stage_param_range: null pointer");
+  const int nst = (int)net->stage_begin.size() - 2;
+  DIRB_CHECK_ARG(stage >= 0 && stage <= nst, "resnet_stage_param_range: bad stage %d", stage);
+  auto first = [&](int s) -> int64_t {
+    return s > nst ? (int64_t)net->param_count : (int64_t)net->blocks[net->stage_begin[s]].c1.w_off;
+  };
+  *lo = stage == 0 ? 0 : first(stage);
+  *hi = first(stage + 1);
+  return DIRB200_OK;
+}
+
+int dirb200_resnet_num_stages(const dirb200_net* net) { return net ? (int)net->stage_begin.size() - 2 : -1; }
+
+/* d_enc fp32 [n, feature_dim] -> ACCUMULATES d loss / d parameter into grads (flat fp32, same layout as params): all
+ * stages back to back.  Must follow a training-mode forward on the same net. */
+int dirb200_resnet_backward(dirb200_net* net, const float* d_enc, const float* params, float* grads, void* stream) {
+  DIRB_CHECK_ARG(net && d_enc && params && grads, "resnet_backward: null pointer");
+  for (int stage = (int)net->stage_begin.size() - 2; stage >= 0; --stage)
+    RUN(dirb200_resnet_backward_stage(net, stage, d_enc, params, grads, stream));
   return DIRB200_OK;
 }
 

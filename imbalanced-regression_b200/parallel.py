@@ -3,9 +3,12 @@ the single-process torch.nn.DataParallel of agedb-dir/train.py:143.
 
 `DataParallel(model)` keeps the reference's call shape (`model.module.FDS`,
 `model(inputs, targets, epoch)`), but each rank owns the whole replica and its
-shard of the mini-batch; after backward the flat fp32 gradient buffer is
-all-reduced (sum) over NCCL / NVLink in one collective and the optimizer
-applies 1/world_size (`grad_scale`).  BN statistics stay per rank (reference
+shard of the mini-batch.  The flat fp32 gradient buffer is all-reduced (sum)
+over NCCL / NVLink in buckets that follow the backward pass: as soon as a layer
+group (layer4, layer3, layer2, layer1) has produced its gradients, its slice is
+all-reduced asynchronously while the earlier layer groups still compute; the
+stem / regressor slices and the wait happen in `reduce_gradients()`.  The
+optimizer applies 1/world_size (`grad_scale`).  BN statistics stay per rank (reference
 behaviour under DataParallel); FDS per-bin statistics are all-reduced per
 epoch inside fds.FDS.
 """
@@ -55,9 +58,19 @@ class ShardSampler(Sampler):
 
 
 class DataParallel(nn.Module):
-    def __init__(self, module):
+    def __init__(self, module, overlap=True):
         super().__init__()
         self.module = module
+        self._works, self._done = [], []          # pending async all-reduces, flat ranges they cover
+        if overlap and is_distributed() and hasattr(module, "_grad_bucket_hook"):
+            module._grad_bucket_hook = self._reduce_bucket
+
+    def _reduce_bucket(self, lo, hi):
+        """Backward has finished the flat-gradient range [lo, hi): start its all-reduce (NCCL's stream waits for the
+        kernels enqueued so far on the compute stream, then runs beside the rest of the backward pass)."""
+        flat = self.module._flat["grads"] if hasattr(self.module, "_flat") else self.module.flat_grads()
+        self._works.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+        self._done.append((lo, hi))
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
@@ -67,7 +80,23 @@ class DataParallel(nn.Module):
         grads = self.module.flat_grads()     # also (re)attaches every .grad to its view of the flat buffer
         if not is_distributed():
             return None
-        return dist.all_reduce(grads, op=dist.ReduceOp.SUM, async_op=async_op)
+        # whatever the bucket hook has not covered yet (the stem and the regressor; everything without the hook)
+        covered, self._done = sorted(self._done), []
+        pos, rest = 0, []
+        for lo, hi in covered:
+            if lo > pos:
+                rest.append((pos, lo))
+            pos = max(pos, hi)
+        if pos < grads.numel():
+            rest.append((pos, grads.numel()))
+        for lo, hi in rest:
+            self._works.append(dist.all_reduce(grads[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+        works, self._works = self._works, []
+        if async_op:
+            return works
+        for w in works:
+            w.wait()                           # the compute stream waits; the host does not block
+        return None
 
     def broadcast_parameters(self, src=0):
         if is_distributed():

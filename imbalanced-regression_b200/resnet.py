@@ -37,6 +37,9 @@ _lib.register({
     "dirb200_resnet_device_bytes": (c_int64, [P]),
     "dirb200_resnet_forward": (c_int, [P, P, P, P, c_int, P, P]),
     "dirb200_resnet_backward": (c_int, [P, P, P, P, P]),
+    "dirb200_resnet_num_stages": (c_int, [P]),
+    "dirb200_resnet_backward_stage": (c_int, [P, c_int, P, P, P, P]),
+    "dirb200_resnet_stage_param_range": (c_int, [P, c_int, P, P]),
     "dirb200_resnet_set_profiling": (c_int, [P, c_int]),
     "dirb200_resnet_read_profile": (c_int, [P, P, P]),
     "dirb200_resnet_peek": (c_int, [P, c_int, c_int, P, P, P]),
@@ -185,6 +188,7 @@ class ResNet(nn.Module):
                 m.bias.data.zero_()
 
         self._nets = {}
+        self._grad_bucket_hook = None          # callable(lo, hi) on the flat gradient, see _run_backward
         self._anchor = torch.zeros(1, requires_grad=True)
         self._flat = None
         self._flatten()
@@ -337,8 +341,21 @@ class ResNet(nn.Module):
                                     "pass) was evicted -- more than MAX_NETS shapes ran between forward and backward")
         self._ensure_grads()
         g = g.detach().to(torch.float32).contiguous()
-        _lib.call("dirb200_resnet_backward", self._net(shape), _lib.ptr(g), _lib.ptr(self._flat["params"]),
-                  _lib.ptr(self._flat["grads"]), _lib.stream_ptr())
+        net = self._net(shape)
+        hook = self._grad_bucket_hook
+        if hook is None:
+            _lib.call("dirb200_resnet_backward", net, _lib.ptr(g), _lib.ptr(self._flat["params"]),
+                      _lib.ptr(self._flat["grads"]), _lib.stream_ptr())
+            return
+        # stage by stage (layer4 ... layer1, stem); after each layer group its slice of the flat gradient is final and
+        # is handed to the hook (parallel.DataParallel: an asynchronous NCCL all-reduce that overlaps the rest)
+        for stage in range(_lib.raw("dirb200_resnet_num_stages")(net), -1, -1):
+            _lib.call("dirb200_resnet_backward_stage", net, stage, _lib.ptr(g), _lib.ptr(self._flat["params"]),
+                      _lib.ptr(self._flat["grads"]), _lib.stream_ptr())
+            if stage >= 1:
+                lo, hi = c_int64(), c_int64()
+                _lib.call("dirb200_resnet_stage_param_range", net, stage, ctypes.byref(lo), ctypes.byref(hi))
+                hook(lo.value, hi.value)
 
     PROFILE_KINDS = ("prep", "conv_fprop", "conv_dgrad", "conv_wgrad", "wgrad_reduce", "bn_stats", "bn_apply",
                      "bn_bwd_reduce", "bn_bwd_apply", "pool")

@@ -245,6 +245,16 @@ int dirb200_resnet_forward(dirb200_net* net, const float* x_nchw, const float* p
 /* Backward of the above: d_enc fp32 [n, feature_dim]; ACCUMULATES into grads. */
 int dirb200_resnet_backward(dirb200_net* net, const float* d_enc, const float* params, float* grads, void* stream);
 
+/* The same backward, one stage per call, so that the caller can overlap the gradient all-reduce of a finished stage
+ * (agedb-dir/train.py:143 DataParallel's reduction) with the stages still running:
+ * stage = dirb200_resnet_num_stages() (avg-pool backward + last layer group; reads d_enc), then stage-1 ... 1, then 0
+ * (max-pool, stem).  In exactly that order after a training-mode forward.  dirb200_resnet_stage_param_range: the
+ * [lo, hi) float range of the flat parameter / gradient buffers that stage owns (0 = conv1 + bn1). */
+int dirb200_resnet_num_stages(const dirb200_net* net);
+int dirb200_resnet_backward_stage(dirb200_net* net, int stage, const float* d_enc, const float* params, float* grads,
+                                  void* stream);
+int dirb200_resnet_stage_param_range(const dirb200_net* net, int stage, int64_t* lo, int64_t* hi);
+
 /* Per-kernel-class device timing of forward/backward (CUDA events around every launch group).  Classes:
  * 0 prep (weight re-layout, s2d), 1 conv fprop, 2 conv dgrad, 3 conv wgrad GEMM, 4 wgrad split-K reduce,
  * 5 BN statistics, 6 BN apply, 7 BN backward reduce, 8 BN backward apply, 9 pooling.

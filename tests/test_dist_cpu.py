@@ -76,6 +76,26 @@ def _worker(rank, world, port, tmp):
     dp = DataParallel(Dummy())
     dp.reduce_gradients()
     assert torch.allclose(dp.module.flat_grads() * dp.grad_scale, torch.full((10,), (1 + 2) / 2.0))
+    # ---- bucketed / overlapped reduction: ranges handed over during backward + the remainder in reduce_gradients
+    # cover every element exactly once (each ends up as the sum over ranks, never twice)
+    class Staged(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self._g = torch.arange(100, dtype=torch.float32) * (rank + 1)
+            self._grad_bucket_hook = None
+
+        def flat_grads(self):
+            return self._g
+
+        def flat_parameters(self):
+            return torch.zeros(100)
+    dp2 = DataParallel(Staged())
+    assert dp2.module._grad_bucket_hook is not None
+    dp2.module._grad_bucket_hook(60, 100)          # "layer4" finished first
+    dp2.module._grad_bucket_hook(30, 60)           # then "layer3"
+    dp2.reduce_gradients()                         # stem part [0, 30) + wait
+    assert torch.equal(dp2.module.flat_grads(), torch.arange(100, dtype=torch.float32) * 3)
+    assert not dp2._works and not dp2._done
     open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     dist.destroy_process_group()
 

@@ -57,12 +57,16 @@ def test_train_loop_fds_refresh_matches_reference_order(cfg):
     bucket_num, bucket_start, start_update, start_smooth = cfg
     train, args, net, model, loader, opt, ref = _setup(*cfg)
     fds = net.FDS
-    raw, fed = [], []
-    run_forward, accumulate = net._run_forward, fds.accumulate_batch
+    raw, fed, state = [], [], {"collecting": False}
+    run_forward, accumulate, begin = net._run_forward, fds.accumulate_batch, fds.begin_epoch_stats
+
+    def rec_begin(all_labels):                           # the collection pass starts here (train.py:269-272) ...
+        state["collecting"] = True
+        return begin(all_labels)
 
     def rec_forward(x, training):
         enc = run_forward(x, training)
-        if not torch.is_grad_enabled():
+        if state["collecting"]:
             raw.append(enc.detach().clone())             # before FDS.smooth touches it in place
         return enc
 
@@ -70,10 +74,11 @@ def test_train_loop_fds_refresh_matches_reference_order(cfg):
         fed.append((features.detach().clone(), labels.detach().clone().reshape(-1)))
         return accumulate(features, labels)
 
-    net._run_forward, fds.accumulate_batch = rec_forward, rec_accumulate
+    net._run_forward, fds.accumulate_batch, fds.begin_epoch_stats = rec_forward, rec_accumulate, rec_begin
     for epoch in range(start_update + 3):
         raw.clear()
         fed.clear()
+        state["collecting"] = False                      # ... and ends with train()
         loss = train.train(loader, model, opt, epoch, args)
         assert np.isfinite(loss)
         if epoch < start_update:
