@@ -31,6 +31,12 @@ int wgrad_reduce(const float* workspace, int splits, float* dw, const ConvShape&
                  cudaStream_t st);
 int conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* workspace, const ConvShape& s,
                bool stem, bool accumulate, cudaStream_t st);
+struct WgradReduceDesc {        // one conv layer's split-K reduction job (see wgrad_reduce_all)
+  const float* partial;         // [splits][cout][kh*kw*cin] (stem: [splits][cout][256]) from conv_wgrad_partials
+  size_t w_off;                 // dW (+)= ... at grads + w_off, fp32 [Cout][Cin][KH][KW]
+  int splits, cout, cin, kh, kw, stem;
+};
+int wgrad_reduce_all(const WgradReduceDesc* descs_dev, int nlayers, float* grads, cudaStream_t st);
 struct PrepDesc {               // one conv layer's weight re-layout job (see prep_weights_all)
   size_t w_off;                 // fp32 [Cout][Cin][KH][KW] at params + w_off
   int cout, cin, kh, kw, stem;

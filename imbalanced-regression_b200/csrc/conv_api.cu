@@ -97,6 +97,53 @@ __global__ void wgrad_reduce_stem_kernel(const float* __restrict__ partial, int 
   }
 }
 
+// Split-K reduction of SEVERAL layers in one launch (blockIdx.y selects the layer, the CTAs of a row stride over its
+// weights): the runner keeps one partial buffer per conv and reduces a whole backward stage at once -- 5 launches per
+// step instead of 53 latency-bound ones.  Always accumulates into grads (+=), like the per-layer form the runner used.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_all_kernel(const WgradReduceDesc* __restrict__ descs, float* __restrict__ grads) {
+  const WgradReduceDesc d = descs[blockIdx.y];
+  float* dw = grads + d.w_off;
+  if (d.stem) {
+    const int total = 256 * d.cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int co = i >> 8, k = i & 255;
+      const int rp = k >> 6, sp_ = (k >> 4) & 3, ph = (k >> 3) & 1, pw = (k >> 2) & 1, c = k & 3;
+      const int r = 2 * rp + ph - 1, s = 2 * sp_ + pw - 1;
+      if (c >= 3 || r < 0 || s < 0) continue;
+      float acc = 0.f;
+      for (int sp = 0; sp < d.splits; ++sp) acc += d.partial[(int64_t)sp * total + i];
+      dw[((co * 3 + c) * 7 + r) * 7 + s] += acc;
+    }
+    return;
+  }
+  const int64_t ktot = (int64_t)d.kh * d.kw * d.cin;
+  const int64_t total = ktot * d.cout;
+  const int taps = d.kh * d.kw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float* p = d.partial + i;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four independent chains: the loads of a thread overlap
+    int sp = 0;
+    for (; sp + 4 <= d.splits; sp += 4) {
+      a0 += p[(int64_t)sp * total];
+      a1 += p[(int64_t)(sp + 1) * total];
+      a2 += p[(int64_t)(sp + 2) * total];
+      a3 += p[(int64_t)(sp + 3) * total];
+    }
+    for (; sp < d.splits; ++sp) a0 += p[(int64_t)sp * total];
+    const int64_t co = i / ktot, k = i - co * ktot;
+    const int c = (int)(k % d.cin), t = (int)(k / d.cin);
+    dw[(co * d.cin + c) * taps + t] += (a0 + a1) + (a2 + a3);
+  }
+}
+
+int wgrad_reduce_all(const WgradReduceDesc* descs_dev, int nlayers, float* grads, cudaStream_t st) {
+  if (nlayers <= 0) return DIRB200_OK;
+  wgrad_reduce_all_kernel<<<dim3(2 * num_sms(), nlayers), 256, 0, st>>>(descs_dev, grads);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
 // All conv weights of a network in ONE launch: blockIdx.y selects the layer.
 __global__ void prep_weights_all_kernel(const float* __restrict__ params, const PrepDesc* __restrict__ descs) {
   const PrepDesc d = descs[blockIdx.y];

@@ -26,6 +26,7 @@ struct ConvLayer {
   bool stem = false;
   size_t w_off = 0;
   __nv_bfloat16 *wf = nullptr, *wd = nullptr;  // GEMM operands (fprop / dgrad layouts)
+  float* wpart = nullptr;                      // split-K partials of this layer's weight gradient
   __nv_bfloat16* y = nullptr;                  // raw conv output [rows][cout]
   __nv_bfloat16* a = nullptr;                  // relu(bn(y)) when this conv is followed by BN+ReLU
   int64_t rows = 0;                            // n*ho*wo
@@ -53,7 +54,8 @@ struct dirb200_net {
   int pool_h = 0, pool_w = 0;
   int feat_c = 0, feat_hw = 0;
   __nv_bfloat16* scratch[8] = {};
-  float* wgrad_ws = nullptr;
+  WgradReduceDesc* reduce_descs = nullptr;     // device table, conv layers in backward-stage order
+  std::vector<int> reduce_begin;               // first table entry of stage s (0 = stem, 1.. = layer groups); +1 sentinel
   float* bn_partial = nullptr;   // per-CTA partial sums of the BN column reductions (backward)
   float* stat_partial = nullptr; // per-CTA BN statistics [CTA][2][c] written by the conv fprop epilogue (conv.cuh)
   PrepDesc* prep_descs = nullptr; // device table for the single weight re-layout launch
@@ -116,6 +118,7 @@ static bool setup_conv(dirb200_net* net, ConvLayer& cv, int n, int h, int w, int
   const size_t welems = stem ? (size_t)cout * 256 : (size_t)cout * cin * k * k;
   NET_ALLOC(cv.wf, welems * 2);
   if (!stem) NET_ALLOC(cv.wd, welems * 2);
+  NET_ALLOC(cv.wpart, conv_wgrad_workspace_bytes(cv.s));
   NET_ALLOC(cv.y, (size_t)cv.rows * cout * 2);
   if (with_act) NET_ALLOC(cv.a, (size_t)cv.rows * cout * 2);
   return setup_bn(net, cv.bn, cout);
@@ -163,14 +166,29 @@ static bool build(dirb200_net* net, const int* blocks_per_stage, int num_stages)
   net->feat_c = inplanes;
   net->feat_hw = h * w;
   for (int i = 0; i < 8; ++i) NET_ALLOC(net->scratch[i], max_act * 2);
-  size_t ws = conv_wgrad_workspace_bytes(net->stem.s);
-  for (Block& B : net->blocks) {
-    ws = std::max(ws, conv_wgrad_workspace_bytes(B.c1.s));
-    ws = std::max(ws, conv_wgrad_workspace_bytes(B.c2.s));
-    ws = std::max(ws, conv_wgrad_workspace_bytes(B.c3.s));
-    if (B.has_ds) ws = std::max(ws, conv_wgrad_workspace_bytes(B.ds.s));
+  {
+    // split-K reduction jobs: every conv owns its partial buffer; one launch reduces a whole backward stage
+    std::vector<WgradReduceDesc> rd;
+    auto addr = [&](const ConvLayer& cv) {
+      rd.push_back(WgradReduceDesc{cv.wpart, cv.w_off, conv_wgrad_splits(cv.s), cv.s.cout, cv.stem ? 3 : cv.s.cin,
+                                   cv.stem ? 7 : cv.s.kh, cv.stem ? 7 : cv.s.kw, cv.stem ? 1 : 0});
+    };
+    net->reduce_begin.clear();
+    net->reduce_begin.push_back(0);
+    addr(net->stem);
+    for (int stg = 1; stg <= num_stages; ++stg) {
+      net->reduce_begin.push_back((int)rd.size());
+      for (int bi = net->stage_begin[stg]; bi < net->stage_begin[stg + 1]; ++bi) {
+        Block& B = net->blocks[bi];
+        addr(B.c1); addr(B.c2); addr(B.c3);
+        if (B.has_ds) addr(B.ds);
+      }
+    }
+    net->reduce_begin.push_back((int)rd.size());
+    NET_ALLOC(net->reduce_descs, sizeof(WgradReduceDesc) * rd.size());
+    if (cudaMemcpy(net->reduce_descs, rd.data(), sizeof(WgradReduceDesc) * rd.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+      return false;
   }
-  NET_ALLOC(net->wgrad_ws, ws);
   NET_ALLOC(net->bn_partial, sizeof(float) * bn_partial_floats(net->feat_c));
   NET_ALLOC(net->stat_partial, sizeof(float) * bn_partial_floats(net->feat_c));
   std::vector<PrepDesc> descs;
@@ -262,11 +280,17 @@ static int conv_bn_forward(dirb200_net* net, ConvLayer& cv, const __nv_bfloat16*
   return DIRB200_OK;
 }
 
-static int wgrad_step(dirb200_net* net, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, const ConvShape& s,
-                      bool stem, cudaStream_t st) {
+// weight-gradient GEMM of one conv into its own split-K partial buffer; the reduction into the flat gradient happens
+// once per backward stage (wgrad_reduce_stage)
+static int wgrad_step(dirb200_net* net, const __nv_bfloat16* x, const __nv_bfloat16* dy, ConvLayer& cv, cudaStream_t st) {
   int splits = 1;
-  RUNP(kWgrad, conv_wgrad_partials(x, dy, net->wgrad_ws, s, stem, &splits, st));
-  RUNP(kWgradReduce, wgrad_reduce(net->wgrad_ws, splits, dw, s, stem, true, st));
+  RUNP(kWgrad, conv_wgrad_partials(x, dy, cv.wpart, cv.s, cv.stem, &splits, st));
+  return DIRB200_OK;
+}
+
+static int wgrad_reduce_stage(dirb200_net* net, int stage, float* grads, cudaStream_t st) {
+  const int lo = net->reduce_begin[stage], hi = net->reduce_begin[stage + 1];
+  RUNP(kWgradReduce, wgrad_reduce_all(net->reduce_descs + lo, hi - lo, grads, st));
   return DIRB200_OK;
 }
 
@@ -397,19 +421,19 @@ static int backward_blocks(dirb200_net* net, int lo, int hi, const float* params
                                    B.has_ds ? B.ds.bn.coef : nullptr, nullptr, nullptr, B.mask, B.c3.rows, b3.c, t1,
                                    B.has_ds ? t2 : nullptr, B.has_ds ? nullptr : nB, st));
     // ---- conv3
-    RUN(wgrad_step(net, B.c2.a, t1, grads + B.c3.w_off, B.c3.s, false, st));
+    RUN(wgrad_step(net, B.c2.a, t1, B.c3, st));
     RUNP(kDgrad, conv_dgrad(t1, B.c3.wd, t3, B.c3.s, st));
     // ---- bn2 + conv2
     RUN(conv_bn_backward(net, B.c2, t3, params, grads, t1, st));
-    RUN(wgrad_step(net, B.c1.a, t1, grads + B.c2.w_off, B.c2.s, false, st));
+    RUN(wgrad_step(net, B.c1.a, t1, B.c2, st));
     RUNP(kDgrad, conv_dgrad(t1, B.c2.wd, t3, B.c2.s, st));
     // ---- bn1 + conv1
     RUN(conv_bn_backward(net, B.c1, t3, params, grads, t1, st));
-    RUN(wgrad_step(net, B.in, t1, grads + B.c1.w_off, B.c1.s, false, st));
+    RUN(wgrad_step(net, B.in, t1, B.c1, st));
     RUNP(kDgrad, conv_dgrad(t1, B.c1.wd, nA, B.c1.s, st));
     // ---- downsample branch
     if (B.has_ds) {
-      RUN(wgrad_step(net, B.in, t2, grads + B.ds.w_off, B.ds.s, false, st));
+      RUN(wgrad_step(net, B.in, t2, B.ds, st));
       RUNP(kDgrad, conv_dgrad(t2, B.ds.wd, nB, B.ds.s, st));
     }
     // the two gradients w.r.t. this block's input become the next (earlier) block's incoming pair
@@ -457,8 +481,9 @@ int dirb200_resnet_backward_stage(dirb200_net* net, int stage, const float* d_en
     __nv_bfloat16 *t1 = net->scratch[4], *t3 = net->scratch[6];
     RUNP(kPool, maxpool_bwd(net->bw_gA, net->bw_gB, net->pool_idx, net->n, net->stem.s.ho, net->stem.s.wo, 64, t3, st));
     RUN(conv_bn_backward(net, net->stem, t3, params, grads, t1, st));
-    RUN(wgrad_step(net, net->x_s2d, t1, grads + net->stem.w_off, net->stem.s, true, st));
+    RUN(wgrad_step(net, net->x_s2d, t1, net->stem, st));
   }
+  RUN(wgrad_reduce_stage(net, stage, grads, st));
   net->bwd_next_stage = stage - 1;          // -1 after the stem: nothing pending
   return DIRB200_OK;
 }
