@@ -1,18 +1,10 @@
 // Library-wide plumbing of libdirb200: error string, version, launch counter.
 #include "common.cuh"
 #include <stdarg.h>
-#include <stdlib.h>
 
 namespace dirb200 {
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
-bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("DIRB200_PDL");
-    return !(e != nullptr && e[0] == '0');
-  }();
-  return on;
-}
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -23,6 +15,6 @@ void set_error(const char* fmt, ...) {
 
 extern "C" {
 const char* dirb200_last_error(void) { return dirb200::g_err; }
-int dirb200_version(void) { return 200; }
+int dirb200_version(void) { return 100; }
 int64_t dirb200_launch_count(void) { return dirb200::g_launches.load(); }
 }

@@ -59,36 +59,6 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Programmatic dependent launch (PDL).  Every kernel of the training step starts with pdl_prologue(): it lets the NEXT
-// kernel of the stream be scheduled early (its CTAs start as SM resources free up, during this kernel's tail) and
-// then waits until the PREVIOUS kernel of the stream has completed and its memory is visible -- no global memory is
-// touched before the wait, so the semantics are exactly those of an ordinary in-stream launch; what overlaps is the
-// launch / scheduling latency between the ~440 dependent kernels of a step.  Kernels are launched through
-// launch_pdl() (cudaLaunchKernelEx + cudaLaunchAttributeProgrammaticStreamSerialization).  DIRB200_PDL=0 disables
-// the attribute (the device-side instructions are then no-ops).
-__device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-
-bool pdl_enabled();
-
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                              Args&&... args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
 // streaming 128-bit global load that does not allocate in L1
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   float4 r;

@@ -40,7 +40,6 @@ __global__ void prep_stem_weights_kernel(const float* __restrict__ w, int cout, 
 
 // x fp32 NCHW [n,3,h,w] -> bf16 [n, h/2, w/2, 16], channel = (ph*2 + pw)*4 + c (c == 3 is zero padding)
 __global__ void input_to_s2d_kernel(const float* __restrict__ x, int n, int h, int w, __nv_bfloat16* __restrict__ out) {
-  pdl_prologue();
   const int h2 = h / 2, w2 = w / 2;
   const int64_t total = (int64_t)n * h2 * w2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -103,7 +102,6 @@ __global__ void wgrad_reduce_stem_kernel(const float* __restrict__ partial, int 
 // step instead of 53 latency-bound ones.  Always accumulates into grads (+=), like the per-layer form the runner used.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_all_kernel(const WgradReduceDesc* __restrict__ descs, float* __restrict__ grads) {
-  pdl_prologue();
   const WgradReduceDesc d = descs[blockIdx.y];
   float* dw = grads + d.w_off;
   if (d.stem) {
@@ -141,14 +139,13 @@ wgrad_reduce_all_kernel(const WgradReduceDesc* __restrict__ descs, float* __rest
 
 int wgrad_reduce_all(const WgradReduceDesc* descs_dev, int nlayers, float* grads, cudaStream_t st) {
   if (nlayers <= 0) return DIRB200_OK;
-  DIRB_CUDA(launch_pdl(wgrad_reduce_all_kernel, dim3(2 * num_sms(), nlayers), dim3(256), 0, st, descs_dev, grads));
+  wgrad_reduce_all_kernel<<<dim3(2 * num_sms(), nlayers), 256, 0, st>>>(descs_dev, grads);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
 
 // All conv weights of a network in ONE launch: blockIdx.y selects the layer.
 __global__ void prep_weights_all_kernel(const float* __restrict__ params, const PrepDesc* __restrict__ descs) {
-  pdl_prologue();
   const PrepDesc d = descs[blockIdx.y];
   const float* w = params + d.w_off;
   if (d.stem) {
@@ -177,7 +174,7 @@ __global__ void prep_weights_all_kernel(const float* __restrict__ params, const 
 }
 
 int prep_weights_all(const float* params, const PrepDesc* descs_dev, int nlayers, cudaStream_t st) {
-  DIRB_CUDA(launch_pdl(prep_weights_all_kernel, dim3(96, nlayers), dim3(256), 0, st, params, descs_dev));
+  prep_weights_all_kernel<<<dim3(96, nlayers), 256, 0, st>>>(params, descs_dev);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
@@ -200,7 +197,7 @@ int prep_weights(const float* w, int cout, int cin, int kh, int kw, bool stem, _
 }
 
 int input_to_s2d(const float* x, int n, int h, int w, __nv_bfloat16* out, cudaStream_t st) {
-  DIRB_CUDA(launch_pdl(input_to_s2d_kernel, dim3(grid1d((int64_t)n * (h / 2) * (w / 2))), dim3(256), 0, st, x, n, h, w, out));
+  input_to_s2d_kernel<<<grid1d((int64_t)n * (h / 2) * (w / 2)), 256, 0, st>>>(x, n, h, w, out);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }

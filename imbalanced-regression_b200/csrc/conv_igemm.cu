@@ -199,7 +199,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
   static_assert(!(CTA2 && WGRAD && ATMA), "wgrad pairs: gather-fed A only so far");
   static_assert(!ATMA || (!STEM && !BSTAT), "TMA-fed A operand: not for the stem / B-stationary forms");
   extern __shared__ uint8_t smem_raw[];
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // PDL, see common.cuh
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + C::kBarOffset;
   // BSTAT layout: [kStages x A (16 KB)] [B: num_kblocks x kBBytes] ; else [kStages x (A | B)]
@@ -285,8 +284,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_holder));
-  // the on-chip setup above overlapped the previous kernel's tail; from here on global memory is read / written
-  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp < 4) {
     if constexpr (!ATMA) {
@@ -902,8 +899,7 @@ static int launch_igemm_impl(const CUtensorMap& tm, const CUtensorMap& tma, cons
   }
   const int grid = Q.num_tiles < num_sms() ? Q.num_tiles : num_sms();
   t_last_layout = StatLayout{grid, Q.n_tiles, BN, 1};
-  DIRB_CUDA(launch_pdl(igemm_kernel<BN, WGRAD, STEM, BSTAT, false, ATMA>, dim3(grid), dim3(kThreads), C::kSmemBytes, st, tm, tma,
-                       Q));
+  igemm_kernel<BN, WGRAD, STEM, BSTAT, false, ATMA><<<grid, kThreads, C::kSmemBytes, st>>>(tm, tma, Q);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
@@ -924,13 +920,11 @@ static int launch_igemm_cta2(const CUtensorMap& tm, const CUtensorMap& tma, cons
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // PDL, see common.cuh
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // the persistent tile walk assumes every cluster of the grid is resident at once: cap the grid at the number of
@@ -947,7 +941,6 @@ static int launch_igemm_cta2(const CUtensorMap& tm, const CUtensorMap& tma, cons
   }
   const int pairs = Q.num_tiles < max_pairs ? Q.num_tiles : max_pairs;
   cfg.gridDim = dim3(2 * pairs, 1, 1);
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   t_last_layout = StatLayout{2 * pairs, Q.n_tiles, BN, 2};
   DIRB_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, tma, Q));
   DIRB_LAUNCHED();

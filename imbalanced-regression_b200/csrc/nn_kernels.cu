@@ -108,7 +108,6 @@ __device__ __forceinline__ void sum_partials2(const float* __restrict__ partial,
 
 __global__ void __launch_bounds__(256, 4)
 bn_stats_kernel(const __nv_bfloat16* __restrict__ y, int64_t rows, int c, float* __restrict__ partial) {
-  pdl_prologue();
   const int cgroups = c / 8;
   const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
   float acc[2][8] = {};
@@ -145,7 +144,6 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, StatLayout
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                    float* __restrict__ scale, float* __restrict__ shift) {
-  pdl_prologue();
   __shared__ double sh[2][32][32];
   const int i = blockIdx.x * 32 + threadIdx.x;
   double a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
@@ -199,7 +197,6 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, StatLayout
 __global__ void bn_eval_coeffs_kernel(int c, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                       const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                       float* __restrict__ scale, float* __restrict__ shift) {
-  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c) return;
   const float sc = gamma[i] * rsqrtf(running_var[i] + eps);
@@ -222,7 +219,6 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
                 const __nv_bfloat16* __restrict__ res, const __nv_bfloat16* __restrict__ res_y,
                 const float* __restrict__ res_scale, const float* __restrict__ res_shift, int relu, int64_t rows,
                 int c, __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ mask_out) {
-  pdl_prologue();
   const int cgroups = c / 8;
   const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
   const V8 sc = loadf8(scale + cg * 8), sh = loadf8(shift + cg * 8);
@@ -310,7 +306,6 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
                      const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ y2,
                      const float* __restrict__ scale, const float* __restrict__ shift,
                      const uint8_t* __restrict__ mask, int64_t rows, int c, float* __restrict__ partial) {
-  pdl_prologue();
   const int cgroups = c / 8;
   const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
   constexpr int K = HAS_Y2 ? 3 : 2;
@@ -378,7 +373,6 @@ __global__ void bn_bwd_coeffs_kernel(const float* __restrict__ partial, int nblo
                                      int c, const float* __restrict__ mean, const float* __restrict__ invstd,
                                      const float* __restrict__ gamma, float* __restrict__ grad_gamma,
                                      float* __restrict__ grad_beta, float* __restrict__ coef /* [3][c] */) {
-  pdl_prologue();
   __shared__ double sh[32][32];
   const int i = blockIdx.x * 32 + threadIdx.x;
   double db, s1;
@@ -403,7 +397,6 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
                     const float* __restrict__ scale, const float* __restrict__ shift,
                     const uint8_t* __restrict__ mask, int64_t rows, int c, __nv_bfloat16* __restrict__ dy,
                     __nv_bfloat16* __restrict__ dy2, __nv_bfloat16* __restrict__ dz_out) {
-  pdl_prologue();
   const int cgroups = c / 8;
   const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
   const V8 A = loadf8(coef + cg * 8), B = loadf8(coef + c + cg * 8), C = loadf8(coef + 2 * c + cg * 8);
@@ -468,7 +461,6 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
 // 3x3 / stride 2 / pad 1 max pool; idx = r*3+s of the first maximum (PyTorch's tie rule)
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c,
                                    __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx) {
-  pdl_prologue();
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1, cg = c / 8;
   const int64_t total = (int64_t)n * ho * wo * cg;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -509,7 +501,6 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, i
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                    const uint8_t* __restrict__ idx, int n, int h, int w, int c, __nv_bfloat16* __restrict__ dx) {
-  pdl_prologue();
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1, cg = c / 8;
   const int64_t total = (int64_t)n * h * w * cg;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -570,7 +561,6 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __
 
 // enc[b, c] = mean over hw pixels (fp32)            (nn.AvgPool2d(7) on a 7x7 map + view, resnet.py:137-138)
 __global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, int hw, int c, float* __restrict__ enc) {
-  pdl_prologue();
   const int cg = c / 8;
   const int64_t total = (int64_t)n * cg;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -589,7 +579,6 @@ __global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, i
 }
 
 __global__ void avgpool_bwd_kernel(const float* __restrict__ genc, int n, int hw, int c, __nv_bfloat16* __restrict__ dx) {
-  pdl_prologue();
   const int cg = c / 8;
   const int64_t total = (int64_t)n * hw * cg;
   const float inv = 1.f / (float)hw;
@@ -647,7 +636,6 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
             float grad_scale, const float* __restrict__ clip_coef) {
-  pdl_prologue();
   if (clip_coef) grad_scale *= clip_coef[0];
   const int64_t n4 = n / 4;
   const float step_size = lr / bc1;
@@ -785,7 +773,7 @@ int bn_stats(const __nv_bfloat16* y, int64_t rows, int c, float* partial, int* n
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_stats: unsupported channel count %d", c);
   const int lanes = 256 / cgroups;
   *nblocks = reduce_grid(rows, lanes);
-  DIRB_CUDA(launch_pdl(bn_stats_kernel, dim3(*nblocks), dim3(256), 256 * 16 * sizeof(float), st, y, rows, c, partial));
+  bn_stats_kernel<<<*nblocks, 256, 256 * 16 * sizeof(float), st>>>(y, rows, c, partial);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
@@ -796,15 +784,15 @@ int bn_finalize(const float* partial, const StatLayout& layout, int64_t rows, in
   DIRB_CHECK_ARG(layout.rows > 0 && layout.n_tiles > 0 && layout.bn > 0 && layout.group > 0 &&
                      layout.n_tiles * layout.bn >= c,
                  "bn_finalize: bad statistics layout");
-  DIRB_CUDA(launch_pdl(bn_finalize_kernel, dim3((c + 31) / 32), dim3(32, 32), 0, st, partial, layout, rows, c, gamma, beta,
-                       eps, momentum, running_mean, running_var, mean, invstd, scale, shift));
+  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, st>>>(partial, layout, rows, c, gamma, beta, eps, momentum,
+                                                             running_mean, running_var, mean, invstd, scale, shift);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
 
 int bn_eval_coeffs(int c, const float* gamma, const float* beta, float eps, const float* running_mean,
                    const float* running_var, float* scale, float* shift, cudaStream_t st) {
-  DIRB_CUDA(launch_pdl(bn_eval_coeffs_kernel, dim3((c + 127) / 128), dim3(128), 0, st, c, gamma, beta, eps, running_mean, running_var, scale, shift));
+  bn_eval_coeffs_kernel<<<(c + 127) / 128, 128, 0, st>>>(c, gamma, beta, eps, running_mean, running_var, scale, shift);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
@@ -814,8 +802,8 @@ int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, con
              __nv_bfloat16* out, uint8_t* mask_out, cudaStream_t st) {
   const int cgroups = c / 8;
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_apply: unsupported channel count %d", c);
-  DIRB_CUDA(launch_pdl(bn_apply_kernel, dim3(stream_grid(rows, 256 / cgroups)), dim3(256), 0, st, y, scale, shift, res, res_y,
-                       res_scale, res_shift, relu ? 1 : 0, rows, c, out, mask_out));
+  bn_apply_kernel<<<stream_grid(rows, 256 / cgroups), 256, 0, st>>>(y, scale, shift, res, res_y, res_scale, res_shift,
+                                                                    relu ? 1 : 0, rows, c, out, mask_out);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
@@ -834,8 +822,8 @@ int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_b
   do {                                                                                                    \
     static const int occ = resident_ctas(bn_bwd_reduce_kernel<MODE, G2, Y2>, 256 * 24 * sizeof(float));   \
     *nblocks = reduce_grid(rows, lanes, occ);                                                             \
-    DIRB_CUDA(launch_pdl(bn_bwd_reduce_kernel<MODE, G2, Y2>, dim3(*nblocks), dim3(256), smem, st, g1, g2, y, y2, scale,   \
-                         shift, mask, rows, c, partial));                                                 \
+    bn_bwd_reduce_kernel<MODE, G2, Y2><<<*nblocks, 256, smem, st>>>(g1, g2, y, y2, scale, shift, mask, rows, c, \
+                                                                    partial);                             \
   } while (0)
   if (!mask) DIRB_RED(MASK_FROM_Y, false, false);
   else if (g2 && y2) DIRB_RED(MASK_BITS, true, true);
@@ -850,8 +838,8 @@ int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_b
 int bn_bwd_coeffs(const float* partial, int nblocks, int k, int gslot, int64_t rows, int c, const float* mean,
                   const float* invstd, const float* gamma, float* grad_gamma, float* grad_beta, float* coef,
                   cudaStream_t st) {
-  DIRB_CUDA(launch_pdl(bn_bwd_coeffs_kernel, dim3((c + 31) / 32), dim3(32, 32), 0, st, partial, nblocks, k, gslot, rows, c,
-                       mean, invstd, gamma, grad_gamma, grad_beta, coef));
+  bn_bwd_coeffs_kernel<<<(c + 31) / 32, dim3(32, 32), 0, st>>>(partial, nblocks, k, gslot, rows, c, mean, invstd, gamma,
+                                                      grad_gamma, grad_beta, coef);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
@@ -869,8 +857,8 @@ int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bf
   do {                                                                                                                 \
     static const int occ = resident_ctas(bn_bwd_apply_kernel<MODE, G2, Y2, DZ>, 0);                                    \
     const int grid = want < occ * num_sms() ? want : occ * num_sms();                                                  \
-    DIRB_CUDA(launch_pdl(bn_bwd_apply_kernel<MODE, G2, Y2, DZ>, dim3(grid), dim3(256), 0, st, g1, g2, y, coef, y2, coef2,    \
-                         scale, shift, mask, rows, c, dy, dy2, dz_out));                                               \
+    bn_bwd_apply_kernel<MODE, G2, Y2, DZ><<<grid, 256, 0, st>>>(g1, g2, y, coef, y2, coef2, scale, shift, mask, rows, c, \
+                                                               dy, dy2, dz_out);                                       \
   } while (0)
   if (!mask) DIRB_APP(MASK_FROM_Y, false, false, false);
   else if (g2 && y2) DIRB_APP(MASK_BITS, true, true, false);
@@ -886,26 +874,26 @@ int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bf
 
 int maxpool_fwd(const __nv_bfloat16* x, int n, int h, int w, int c, __nv_bfloat16* out, uint8_t* idx, cudaStream_t st) {
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
-  DIRB_CUDA(launch_pdl(maxpool_fwd_kernel, dim3(grid1d((int64_t)n * ho * wo * c / 8)), dim3(256), 0, st, x, n, h, w, c, out, idx));
+  maxpool_fwd_kernel<<<grid1d((int64_t)n * ho * wo * c / 8), 256, 0, st>>>(x, n, h, w, c, out, idx);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
 
 int maxpool_bwd(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const uint8_t* idx, int n, int h, int w, int c,
                 __nv_bfloat16* dx, cudaStream_t st) {
-  DIRB_CUDA(launch_pdl(maxpool_bwd_kernel, dim3(grid1d((int64_t)n * h * w * c / 8)), dim3(256), 0, st, g1, g2, idx, n, h, w, c, dx));
+  maxpool_bwd_kernel<<<grid1d((int64_t)n * h * w * c / 8), 256, 0, st>>>(g1, g2, idx, n, h, w, c, dx);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
 
 int avgpool_fwd(const __nv_bfloat16* x, int n, int hw, int c, float* enc, cudaStream_t st) {
-  DIRB_CUDA(launch_pdl(avgpool_fwd_kernel, dim3(grid1d((int64_t)n * c / 8, 128)), dim3(128), 0, st, x, n, hw, c, enc));
+  avgpool_fwd_kernel<<<grid1d((int64_t)n * c / 8, 128), 128, 0, st>>>(x, n, hw, c, enc);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
 
 int avgpool_bwd(const float* genc, int n, int hw, int c, __nv_bfloat16* dx, cudaStream_t st) {
-  DIRB_CUDA(launch_pdl(avgpool_bwd_kernel, dim3(grid1d((int64_t)n * hw * c / 8)), dim3(256), 0, st, genc, n, hw, c, dx));
+  avgpool_bwd_kernel<<<grid1d((int64_t)n * hw * c / 8), 256, 0, st>>>(genc, n, hw, c, dx);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
@@ -941,9 +929,9 @@ int dirb200_adam_step(float* params, const float* grads, float* exp_avg, float* 
                  "adam_step: buffers must be 16-byte aligned");
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  DIRB_CUDA(launch_pdl(adam_kernel, dim3(grid1d(n / 4 + 1)), dim3(256), 0, as_stream(stream), params, grads, exp_avg,
-                       exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale,
-                       clip_coef));
+  adam_kernel<<<grid1d(n / 4 + 1), 256, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                               eps, weight_decay, (float)bc1, (float)sqrt(bc2),
+                                                               grad_scale, clip_coef);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
