@@ -106,7 +106,12 @@ struct Cfg {
   static constexpr int kStageRowBytes = kEpiCols * 2 + 16;      // +16 B: conflict-free 16-byte column writes
   static constexpr int kEpiWarpBytes = 32 * kStageRowBytes;
   static constexpr int kEpiOffset = kBarOffset + 256;           // after the mbarriers ((2*kStages + 6) * 8 <= 176 B)
-  static constexpr int kSmemBytes = kEpiOffset + (STAGED_EPI ? 4 * kEpiWarpBytes : 0) + 1024;
+  // per epilogue warp: [BN / kEpiCols passes][4 (sum c0, sum c1, sumsq c0, sumsq c1)][32 lanes] fp32 running column sums
+  // of the BN statistics (kept in smem, not registers, so that the column-pass loop stays rolled: unrolled four-fold
+  // the epilogue outgrew the instruction cache and the epilogue-bound 1x1 layers lost 25 %)
+  static constexpr int kStatWarpBytes = (BN / kEpiCols) * 4 * 32 * 4;
+  static constexpr int kStatOffset = kEpiOffset + (STAGED_EPI ? 4 * kEpiWarpBytes : 0);
+  static constexpr int kSmemBytes = kStatOffset + (STAGED_EPI ? 4 * kStatWarpBytes : 0) + 1024;
   // B-stationary layout: nstages (<= kStages) A slots, then the whole B matrix; barriers stay at kBarOffset
   static constexpr int kTmemCols = 2 * BN;  // two accumulators (epilogue of tile i overlaps the MMAs of tile i+1)
 };
@@ -620,7 +625,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32)
     const int row = quarter * 32 + lane;
     uint32_t tcount = 0;
-    float stat[WGRAD ? 1 : BN / C::kEpiCols][4] = {};   // BN statistics of this warp's rows (fprop with stat_out)
+    // BN statistics of this warp's rows (fprop with stat_out): running column sums in this warp's smem slots
+    float* stat_sm = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + C::kStatOffset) +
+                     (WGRAD ? 0 : quarter * (C::kStatWarpBytes / 4)) + lane;
+    if constexpr (!WGRAD) {
+      if (P.stat_out != nullptr)
+        for (int i = 0; i < (BN / C::kEpiCols) * 4; ++i) stat_sm[i * 32] = 0.f;
+    }
     for (int t = tile_first; t < tile_end; t += tile_step, ++tcount) {
       int split, m_tile, n_tile, kb_begin, nk;
       decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
@@ -652,7 +663,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           }
           orow8[i] = orow;
         }
-#pragma unroll
+#pragma unroll 1
         for (int cb = 0; cb < BN / C::kEpiCols; ++cb) {
 #pragma unroll
           for (int c = 0; c < C::kEpiCols / 32; ++c) {
@@ -700,10 +711,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
               sb = __fadd2_rn(sb, v1);
               qb = __ffma2_rn(v1, v1, qb);
             }
-            stat[cb][0] += sa.x + sb.x;
-            stat[cb][1] += sa.y + sb.y;
-            stat[cb][2] += qa.x + qb.x;
-            stat[cb][3] += qa.y + qb.y;
+            float* acc = stat_sm + cb * 4 * 32;
+            acc[0] += sa.x + sb.x;
+            acc[32] += sa.y + sb.y;
+            acc[64] += qa.x + qb.x;
+            acc[96] += qa.y + qb.y;
           }
           __syncwarp();                                         // staging tile is reused by the next pass / tile
         }
@@ -735,20 +747,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
     }
     if constexpr (!WGRAD) {
       if (P.stat_out != nullptr) {
-        // one flush per CTA: the four epilogue warps combine their column sums through their staging tiles (fixed
-        // order -> deterministic) and write stat_out[blockIdx.x][0][c] = sums, [1][c] = sums of squares for the BN
+        // one flush per CTA: the four epilogue warps' smem column sums are combined (fixed order -> deterministic)
+        // and written as stat_out[blockIdx.x][0][c] = sums, [1][c] = sums of squares for the BN
         // columns of this CTA's n_tile.  Every CTA of the launch owns >= 1 tile (grid <= tiles), so every row of
         // its n_tile's column range is written: the consumer (bn_finalize) reads exactly those, no zero-fill needed.
-        constexpr int NCB = BN / C::kEpiCols;
-        float* mine = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + C::kEpiOffset +
-                                               quarter * C::kEpiWarpBytes);
-#pragma unroll
-        for (int cb = 0; cb < NCB; ++cb)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) mine[(cb * 4 + k) * 32 + lane] = stat[cb][k];
+        __syncwarp();
         asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
-        const float* all = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + C::kEpiOffset);
-        constexpr int kWarpFloats = C::kEpiWarpBytes / 4;
+        const float* all = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + C::kStatOffset);
+        constexpr int kWarpFloats = C::kStatWarpBytes / 4;
         float* dst = P.stat_out + static_cast<size_t>(blockIdx.x) * 2 * P.ldc + fixed_n * BN;
         for (int o = quarter * 32 + lane; o < 2 * BN; o += 128) {
           const int k = o / BN, col = o - k * BN;

@@ -43,7 +43,8 @@ def main():
     n, d, bn, bs = 5000, 256, 100, 3
     feats = np.maximum(rng.randn(n, d).astype(np.float32) * 0.7 + 1.0, 0)
     labels = rng.randint(0, 115, size=n).astype(np.float32)
-    labels[rank] = 3.0 if rank == 0 else labels[rank]            # the low edge value occurs on rank 0's shard only
+    labels[labels == 3.0] = 4.0
+    labels[0] = 3.0                     # the low edge value occurs in rank 0's shard only: the flag must be MAX-reduced
     m = FDS(d, bn, bs).to(dev)
     ref = O.FDSState(d, bn, bs)
     for ep in (0, 1):
