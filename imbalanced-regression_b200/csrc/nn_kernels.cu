@@ -397,6 +397,10 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
                     const float* __restrict__ scale, const float* __restrict__ shift,
                     const uint8_t* __restrict__ mask, int64_t rows, int c, __nv_bfloat16* __restrict__ dy,
                     __nv_bfloat16* __restrict__ dy2, __nv_bfloat16* __restrict__ dz_out) {
+  // rows per iteration: every load of all of them is issued before the first use.  Two CTAs of 8 warps fit per SM
+  // (register-limited), so the plain two-input form needs four rows (8 x 16 B per thread) in flight to cover the HBM
+  // latency -- with two it ran at 4.4 TB/s (ncu, profiles/r2_bn_full.md); the forms with more inputs keep two.
+  constexpr int R = (HAS_G2 || HAS_Y2) ? 2 : 4;
   const int cgroups = c / 8;
   const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
   const V8 A = loadf8(coef + cg * 8), B = loadf8(coef + c + cg * 8), C = loadf8(coef + 2 * c + cg * 8);
@@ -409,24 +413,29 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
   MaskSrc<MODE> ms;
   ms.init(scale, shift, mask, cgroups, cg);
   const int64_t stride = (int64_t)gridDim.x * lanes;
-  for (int64_t r0 = blockIdx.x * (int64_t)lanes + lane; r0 < rows; r0 += 2 * stride) {
-    const int64_t r1 = r0 + stride;
-    const bool two = r1 < rows;
-    const int64_t offs[2] = {r0 * c + cg * 8, (two ? r1 : r0) * c + cg * 8};
-    uint4 G[2], Y[2], G2[2], Y2[2];
-    uint32_t M[2];
+  for (int64_t r0 = blockIdx.x * (int64_t)lanes + lane; r0 < rows; r0 += R * stride) {
+    int64_t rr[R], offs[R];
+    bool live[R];
+    uint4 G[R], Y[R], G2[R], Y2[R];
+    uint32_t M[R];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < R; ++u) {
+      rr[u] = r0 + u * stride;
+      live[u] = rr[u] < rows;
+      if (!live[u]) rr[u] = r0;
+      offs[u] = rr[u] * c + cg * 8;
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
       G[u] = *reinterpret_cast<const uint4*>(g1 + offs[u]);
       Y[u] = *reinterpret_cast<const uint4*>(y + offs[u]);
       if (HAS_G2) G2[u] = *reinterpret_cast<const uint4*>(g2 + offs[u]);
       if (HAS_Y2) Y2[u] = *reinterpret_cast<const uint4*>(y2 + offs[u]);
+      M[u] = ms.load(rr[u]);
     }
-    M[0] = ms.load(r0);
-    M[1] = ms.load(two ? r1 : r0);
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u == 1 && !two) break;
+    for (int u = 0; u < R; ++u) {
+      if (!live[u]) continue;
       const uint32_t gw[4] = {G[u].x, G[u].y, G[u].z, G[u].w}, yw[4] = {Y[u].x, Y[u].y, Y[u].z, Y[u].w};
       uint32_t o1[4], o2[4], oz[4];
 #pragma unroll
@@ -496,66 +505,69 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, i
 }
 
 // dx[h,w] = sum over the (<= 4) windows containing (h,w) whose argmax is this position of (g1 [+ g2]).
-// All candidate loads are issued before any is consumed (the dependent-load chain made the first version 6x slower
-// than its DRAM traffic).
+// A thread owns a 2x2 block of input pixels (2a+py, 2b+px) x 8 channels: exactly the four windows (a+dy, b+dx) reach
+// it, so each window's (gradient, argmax) is loaded once per block instead of once per covered pixel (2.25 loads per
+// pixel on average before) and all four loads are issued before any is consumed.  Pixel (py, px) sits at filter
+// position ((py + 1 - 2 dy), (px + 1 - 2 dx)) of window (dy, dx) -- inside the 3x3 only if (dy == 0 || py == 1) and
+// (dx == 0 || px == 1).  H, W even (the runner's stem output always is).
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                    const uint8_t* __restrict__ idx, int n, int h, int w, int c, __nv_bfloat16* __restrict__ dx) {
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1, cg = c / 8;
-  const int64_t total = (int64_t)n * h * w * cg;
+  const int hb = h / 2, wb = w / 2;
+  const int64_t total = (int64_t)n * hb * wb * cg;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(i % cg);
     int64_t t = i / cg;
-    const int xi = (int)(t % w); t /= w;
-    const int yi = (int)(t % h);
-    const int b = (int)(t / h);
-    // windows (yo, xo) with 2*yo - 1 <= yi <= 2*yo + 1: yo in {yi/2, (yi+1)/2}
-    int64_t off[4];
-    int pos[4];
-    int cnt = 0;
-    const int y0 = yi / 2, y1 = (yi + 1) / 2, x0 = xi / 2, x1 = (xi + 1) / 2;
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const int yo = a ? y1 : y0;
-      if ((a && y1 == y0) || yo >= ho) continue;
-#pragma unroll
-      for (int bb = 0; bb < 2; ++bb) {
-        const int xo = bb ? x1 : x0;
-        if ((bb && x1 == x0) || xo >= wo) continue;
-        off[cnt] = (((int64_t)b * ho + yo) * wo + xo) * c + g * 8;
-        pos[cnt] = (yi - (2 * yo - 1)) * 3 + (xi - (2 * xo - 1));
-        ++cnt;
-      }
-    }
+    const int xb = (int)(t % wb); t /= wb;
+    const int ya = (int)(t % hb);
+    const int b = (int)(t / hb);
     uint4 gv[4], g2v[4];
     uint2 iv[4];
+    bool ok[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (k < cnt) {
-        gv[k] = *reinterpret_cast<const uint4*>(g1 + off[k]);
-        if (g2) g2v[k] = *reinterpret_cast<const uint4*>(g2 + off[k]);
-        iv[k] = *reinterpret_cast<const uint2*>(idx + off[k]);
-      }
-    V8 acc{};
+    for (int k = 0; k < 4; ++k) {
+      const int yo = ya + (k >> 1), xo = xb + (k & 1);
+      ok[k] = yo < ho && xo < wo;
+      const int64_t off = (((int64_t)b * ho + (ok[k] ? yo : 0)) * wo + (ok[k] ? xo : 0)) * c + g * 8;
+      gv[k] = *reinterpret_cast<const uint4*>(g1 + off);
+      g2v[k] = g2 ? *reinterpret_cast<const uint4*>(g2 + off) : make_uint4(0, 0, 0, 0);
+      iv[k] = *reinterpret_cast<const uint2*>(idx + off);
+    }
+    V8 acc[4] = {};                       // [py * 2 + px]
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (k < cnt) {
-        const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&gv[k]);
-        const __nv_bfloat162* hg2 = reinterpret_cast<const __nv_bfloat162*>(&g2v[k]);
-        const uint8_t* ib = reinterpret_cast<const uint8_t*>(&iv[k]);
+    for (int k = 0; k < 4; ++k) {
+      if (!ok[k]) continue;
+      const int dy = k >> 1, dxw = k & 1;
+      const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&gv[k]);
+      const __nv_bfloat162* hg2 = reinterpret_cast<const __nv_bfloat162*>(&g2v[k]);
+      const uint8_t* ib = reinterpret_cast<const uint8_t*>(&iv[k]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float2 f = __bfloat1622float2(hg[j]);
-          if (g2) {
-            const float2 f2 = __bfloat1622float2(hg2[j]);
-            f.x += f2.x;
-            f.y += f2.y;
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __bfloat1622float2(hg[j]);
+        if (g2) {
+          const float2 f2 = __bfloat1622float2(hg2[j]);
+          f.x += f2.x;
+          f.y += f2.y;
+        }
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+          if (dy == 1 && py == 0) continue;
+#pragma unroll
+          for (int px = 0; px < 2; ++px) {
+            if (dxw == 1 && px == 0) continue;
+            const int pos = (py + 1 - 2 * dy) * 3 + (px + 1 - 2 * dxw);
+            if (ib[2 * j] == pos) acc[py * 2 + px].v[2 * j] += f.x;
+            if (ib[2 * j + 1] == pos) acc[py * 2 + px].v[2 * j + 1] += f.y;
           }
-          if (ib[2 * j] == pos[k]) acc.v[2 * j] += f.x;
-          if (ib[2 * j + 1] == pos[k]) acc.v[2 * j + 1] += f.y;
         }
       }
-    store8(dx + i * 8, acc);
+    }
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px)
+        store8(dx + ((((int64_t)b * h + 2 * ya + py) * w + 2 * xb + px) * c + g * 8), acc[py * 2 + px]);
   }
 }
 
@@ -881,7 +893,8 @@ int maxpool_fwd(const __nv_bfloat16* x, int n, int h, int w, int c, __nv_bfloat1
 
 int maxpool_bwd(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const uint8_t* idx, int n, int h, int w, int c,
                 __nv_bfloat16* dx, cudaStream_t st) {
-  maxpool_bwd_kernel<<<grid1d((int64_t)n * h * w * c / 8), 256, 0, st>>>(g1, g2, idx, n, h, w, c, dx);
+  DIRB_CHECK_ARG(h % 2 == 0 && w % 2 == 0, "maxpool_bwd: H and W must be even");
+  maxpool_bwd_kernel<<<grid1d((int64_t)n * (h / 2) * (w / 2) * c / 8), 256, 0, st>>>(g1, g2, idx, n, h, w, c, dx);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
