@@ -21,9 +21,8 @@ struct StatLayout {
 // written, nothing else is touched) -- the BatchNorm batch statistics without re-reading y.
 int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, const ConvShape& s, bool stem,
                cudaStream_t st, float* stat_partial = nullptr, StatLayout* layout = nullptr);
-// residual (optional, stride-1 convs): dx = bf16(dgrad) + residual (same layout as dx; may be dx itself)
 int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* dx, const ConvShape& s,
-               cudaStream_t st, const __nv_bfloat16* residual = nullptr);
+               cudaStream_t st);
 int conv_wgrad_splits(const ConvShape& s);
 size_t conv_wgrad_workspace_bytes(const ConvShape& s);
 int conv_wgrad_partials(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* partial, const ConvShape& s, bool stem,

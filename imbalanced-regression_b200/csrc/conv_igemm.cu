@@ -85,10 +85,6 @@ struct IgemmParams {
   // CTA as stat_out[blockIdx.x][2][ldc] (fp32), columns [n_tile * BN, n_tile * BN + BN) of the CTA's fixed n_tile only
   // (see StatLayout for which rows hold which columns)
   float* stat_out;
-  // dgrad only, optional: a bf16 tensor with the layout of `out` that is ADDED to the result before it is stored
-  // (out = bf16(acc) + residual, one bf16 rounding of the sum; may alias `out`): the runner folds the shortcut-branch
-  // gradient of a bottleneck block into the conv1 dgrad this way instead of carrying two gradient tensors
-  const __nv_bfloat16* residual;
 };
 
 // CTA2: the tile is computed by a CTA pair (cta_group::2, UMMA M = 256): this CTA owns 128 of the 256 rows and stages
@@ -669,14 +665,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
         }
 #pragma unroll 1
         for (int cb = 0; cb < BN / C::kEpiCols; ++cb) {
-          // residual rows of this pass: loaded first, consumed after the accumulator has been staged
-          uint4 resv[kIters];
-          if (P.residual != nullptr) {
-            const __nv_bfloat16* res_cols = P.residual + n0 + cb * C::kEpiCols + col16 * 8;
-#pragma unroll
-            for (int i = 0; i < kIters; ++i)
-              resv[i] = orow8[i] >= 0 ? *reinterpret_cast<const uint4*>(res_cols + orow8[i] * P.ldc) : make_uint4(0, 0, 0, 0);
-          }
 #pragma unroll
           for (int c = 0; c < C::kEpiCols / 32; ++c) {
             uint32_t v[32];
@@ -704,12 +692,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                            : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
                            : "r"(stage_base + (i * kRowsPerIter + sub) * C::kStageRowBytes + col16 * 16));
-              if (P.residual != nullptr) {
-                __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&val);
-                const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&resv[i]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) a[e] = __hadd2(a[e], b[e]);
-              }
               *reinterpret_cast<uint4*>(out_cols + orow8[i] * P.ldc) = val;
             }
           }
@@ -1111,9 +1093,8 @@ static int conv_fprop_impl(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_
 
 // dX[n,h,w,cin] = conv_transpose(dY[n,ho,wo,cout], Wt[cin][kh][kw][cout])
 int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* dx, const ConvShape& s,
-               cudaStream_t st, const __nv_bfloat16* residual) {
+               cudaStream_t st) {
   if (int rc = check_shape(s, false, "conv_dgrad")) return rc;
-  DIRB_CHECK_ARG(residual == nullptr || s.stride == 1, "conv_dgrad: the residual form is for stride-1 convs");
   DIRB_CHECK_ARG(s.stride == 1 || s.stride == 2, "conv_dgrad: stride must be 1 or 2 (got %d)", s.stride);
   DIRB_CHECK_ARG(s.kh * s.kw <= 9, "conv_dgrad: at most 9 filter taps (got %dx%d)", s.kh, s.kw);
   const int ktot = s.kh * s.kw * s.cout;
@@ -1122,7 +1103,6 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
   P.kh = s.kh; P.kw = s.kw; P.stride = s.stride; P.pad = s.pad; P.transposed = 1;
   P.cpb = s.cout / 64;
   P.ldc = s.cin; P.out = dx;
-  P.residual = residual;
   CUtensorMap tm;
   if (s.stride == 1) {
     P.pixels = static_cast<long long>(s.n) * s.h * s.w;

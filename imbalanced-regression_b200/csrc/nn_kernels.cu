@@ -265,7 +265,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
   }
 }
 
-// ---- backward.  dz = g * relu_mask.  The mask is never read from an activation tensor:
+// ---- backward.  dz = (g1 [+ g2]) * relu_mask.  The mask is never read from an activation tensor:
 //   MASK_FROM_Y  (conv -> BN -> ReLU):       mask = (y*scale + shift > 0), the same fmaf the forward evaluated, so the
 //                                            activation `a` is not touched by the backward pass at all;
 //   MASK_BITS    (block output, BN + residual + ReLU):  the 1-bit-per-element mask bn_apply stored.
@@ -300,9 +300,9 @@ struct MaskSrc {
   }
 };
 
-template <int MODE, bool HAS_Y2>
+template <int MODE, bool HAS_G2, bool HAS_Y2>
 __global__ void __launch_bounds__(256, 3)
-bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1,
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                      const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ y2,
                      const float* __restrict__ scale, const float* __restrict__ shift,
                      const uint8_t* __restrict__ mask, int64_t rows, int c, float* __restrict__ partial) {
@@ -318,12 +318,16 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1,
     const int64_t r1 = r0 + stride;
     const bool two = r1 < rows;
     const int64_t o0 = r0 * c + cg * 8, o1 = (two ? r1 : r0) * c + cg * 8;
-    uint4 G[2], Y[2], Y2[2];
+    uint4 G[2], Y[2], G2[2], Y2[2];
     uint32_t M[2];
     G[0] = *reinterpret_cast<const uint4*>(g1 + o0);
     G[1] = *reinterpret_cast<const uint4*>(g1 + o1);
     Y[0] = *reinterpret_cast<const uint4*>(y + o0);
     Y[1] = *reinterpret_cast<const uint4*>(y + o1);
+    if (HAS_G2) {
+      G2[0] = *reinterpret_cast<const uint4*>(g2 + o0);
+      G2[1] = *reinterpret_cast<const uint4*>(g2 + o1);
+    }
     if (HAS_Y2) {
       Y2[0] = *reinterpret_cast<const uint4*>(y2 + o0);
       Y2[1] = *reinterpret_cast<const uint4*>(y2 + o1);
@@ -337,6 +341,12 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1,
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         float2 g = bf2_to_f2(gw[w]);
+        if (HAS_G2) {
+          const uint32_t g2w[4] = {G2[u].x, G2[u].y, G2[u].z, G2[u].w};
+          const float2 t = bf2_to_f2(g2w[w]);
+          g.x += t.x;
+          g.y += t.y;
+        }
         const float2 yv = bf2_to_f2(yw[w]);
         ms.apply(M[u], w, yv, g);
         acc[0][2 * w] += g.x;
@@ -377,11 +387,11 @@ __global__ void bn_bwd_coeffs_kernel(const float* __restrict__ partial, int nblo
   grad_beta[i] += (float)db;
 }
 
-// dz = g * mask;  dy = A*dz + B*y + C  (and the same for the second BN);  optionally writes dz.
+// dz = (g1 [+ g2]) * mask;  dy = A*dz + B*y + C  (and the same for the second BN);  optionally writes dz.
 // Same (channel group, row lane) mapping as bn_apply: coefficients live in registers.
-template <int MODE, bool HAS_Y2, bool WRITE_DZ>
+template <int MODE, bool HAS_G2, bool HAS_Y2, bool WRITE_DZ>
 __global__ void __launch_bounds__(256, 2)
-bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1,
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ coef,
                     const __nv_bfloat16* __restrict__ y2, const float* __restrict__ coef2,
                     const float* __restrict__ scale, const float* __restrict__ shift,
@@ -389,8 +399,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1,
                     __nv_bfloat16* __restrict__ dy2, __nv_bfloat16* __restrict__ dz_out) {
   // rows per iteration: every load of all of them is issued before the first use.  Two CTAs of 8 warps fit per SM
   // (register-limited), so the plain two-input form needs four rows (8 x 16 B per thread) in flight to cover the HBM
-  // latency -- with two it ran at 4.4 TB/s (ncu, profiles/r2_bn_full.md); the two-BN form keeps two.
-  constexpr int R = HAS_Y2 ? 2 : 4;
+  // latency -- with two it ran at 4.4 TB/s (ncu, profiles/r2_bn_full.md); the forms with more inputs keep two.
+  constexpr int R = (HAS_G2 || HAS_Y2) ? 2 : 4;
   const int cgroups = c / 8;
   const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
   const V8 A = loadf8(coef + cg * 8), B = loadf8(coef + c + cg * 8), C = loadf8(coef + 2 * c + cg * 8);
@@ -406,7 +416,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1,
   for (int64_t r0 = blockIdx.x * (int64_t)lanes + lane; r0 < rows; r0 += R * stride) {
     int64_t rr[R], offs[R];
     bool live[R];
-    uint4 G[R], Y[R], Y2[R];
+    uint4 G[R], Y[R], G2[R], Y2[R];
     uint32_t M[R];
 #pragma unroll
     for (int u = 0; u < R; ++u) {
@@ -419,6 +429,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1,
     for (int u = 0; u < R; ++u) {
       G[u] = *reinterpret_cast<const uint4*>(g1 + offs[u]);
       Y[u] = *reinterpret_cast<const uint4*>(y + offs[u]);
+      if (HAS_G2) G2[u] = *reinterpret_cast<const uint4*>(g2 + offs[u]);
       if (HAS_Y2) Y2[u] = *reinterpret_cast<const uint4*>(y2 + offs[u]);
       M[u] = ms.load(rr[u]);
     }
@@ -430,6 +441,12 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1,
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         float2 g = bf2_to_f2(gw[w]);
+        if (HAS_G2) {
+          const uint32_t g2w[4] = {G2[u].x, G2[u].y, G2[u].z, G2[u].w};
+          const float2 t = bf2_to_f2(g2w[w]);
+          g.x += t.x;
+          g.y += t.y;
+        }
         const float2 yv = bf2_to_f2(yw[w]);
         ms.apply(M[u], w, yv, g);
         if (WRITE_DZ) oz[w] = f2_to_bf2(g.x, g.y);
@@ -804,24 +821,27 @@ int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, con
 }
 
 // mask == nullptr: conv -> BN -> ReLU layer, the ReLU mask is re-derived from y with (scale, shift);
-// mask != nullptr: block output, the bit mask bn_apply stored (y2: the downsample branch's raw output, if any).
-int bn_bwd_reduce(const __nv_bfloat16* g, const __nv_bfloat16* y, const __nv_bfloat16* y2, const float* scale,
-                  const float* shift, const uint8_t* mask, int64_t rows, int c, float* partial, int* nblocks,
-                  cudaStream_t st) {
+// mask != nullptr: block output, the bit mask bn_apply stored (g2 / y2: second incoming gradient / downsample branch).
+int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* y, const __nv_bfloat16* y2,
+                  const float* scale, const float* shift, const uint8_t* mask, int64_t rows, int c, float* partial,
+                  int* nblocks, cudaStream_t st) {
   const int cgroups = c / 8;
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_bwd_reduce: unsupported channel count %d", c);
-  DIRB_CHECK_ARG(mask || (scale && shift && !y2), "bn_bwd_reduce: the mask-from-y form takes one BN");
+  DIRB_CHECK_ARG(mask || (scale && shift && !g2 && !y2), "bn_bwd_reduce: mask-from-y form takes one gradient, one BN");
   const int lanes = 256 / cgroups;
   const size_t smem = 256 * (y2 ? 24 : 16) * sizeof(float);
-#define DIRB_RED(MODE, Y2)                                                                                \
+#define DIRB_RED(MODE, G2, Y2)                                                                            \
   do {                                                                                                    \
-    static const int occ = resident_ctas(bn_bwd_reduce_kernel<MODE, Y2>, 256 * 24 * sizeof(float));       \
+    static const int occ = resident_ctas(bn_bwd_reduce_kernel<MODE, G2, Y2>, 256 * 24 * sizeof(float));   \
     *nblocks = reduce_grid(rows, lanes, occ);                                                             \
-    bn_bwd_reduce_kernel<MODE, Y2><<<*nblocks, 256, smem, st>>>(g, y, y2, scale, shift, mask, rows, c, partial); \
+    bn_bwd_reduce_kernel<MODE, G2, Y2><<<*nblocks, 256, smem, st>>>(g1, g2, y, y2, scale, shift, mask, rows, c, \
+                                                                    partial);                             \
   } while (0)
-  if (!mask) DIRB_RED(MASK_FROM_Y, false);
-  else if (y2) DIRB_RED(MASK_BITS, true);
-  else DIRB_RED(MASK_BITS, false);
+  if (!mask) DIRB_RED(MASK_FROM_Y, false, false);
+  else if (g2 && y2) DIRB_RED(MASK_BITS, true, true);
+  else if (g2) DIRB_RED(MASK_BITS, true, false);
+  else if (y2) DIRB_RED(MASK_BITS, false, true);
+  else DIRB_RED(MASK_BITS, false, false);
 #undef DIRB_RED
   DIRB_LAUNCHED();
   return DIRB200_OK;
@@ -836,25 +856,29 @@ int bn_bwd_coeffs(const float* partial, int nblocks, int k, int gslot, int64_t r
   return DIRB200_OK;
 }
 
-int bn_bwd_apply(const __nv_bfloat16* g, const __nv_bfloat16* y, const float* coef, const __nv_bfloat16* y2,
-                 const float* coef2, const float* scale, const float* shift, const uint8_t* mask, int64_t rows, int c,
-                 __nv_bfloat16* dy, __nv_bfloat16* dy2, __nv_bfloat16* dz_out, cudaStream_t st) {
+int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* y, const float* coef,
+                 const __nv_bfloat16* y2, const float* coef2, const float* scale, const float* shift,
+                 const uint8_t* mask, int64_t rows, int c, __nv_bfloat16* dy, __nv_bfloat16* dy2,
+                 __nv_bfloat16* dz_out, cudaStream_t st) {
   const int cgroups = c / 8;
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_bwd_apply: unsupported channel count %d", c);
-  DIRB_CHECK_ARG(mask || (scale && shift && !y2 && !dz_out), "bn_bwd_apply: the mask-from-y form takes one BN");
+  DIRB_CHECK_ARG(mask || (scale && shift && !g2 && !y2 && !dz_out), "bn_bwd_apply: mask-from-y form takes one gradient, one BN");
   DIRB_CHECK_ARG(!(y2 && dz_out), "bn_bwd_apply: a block has either a downsample branch or an identity path");
   const int want = stream_grid(rows, 256 / cgroups);
-#define DIRB_APP(MODE, Y2, DZ)                                                                                    \
-  do {                                                                                                            \
-    static const int occ = resident_ctas(bn_bwd_apply_kernel<MODE, Y2, DZ>, 0);                                   \
-    const int grid = want < occ * num_sms() ? want : occ * num_sms();                                             \
-    bn_bwd_apply_kernel<MODE, Y2, DZ><<<grid, 256, 0, st>>>(g, y, coef, y2, coef2, scale, shift, mask, rows, c, dy, \
-                                                           dy2, dz_out);                                          \
+#define DIRB_APP(MODE, G2, Y2, DZ)                                                                                     \
+  do {                                                                                                                 \
+    static const int occ = resident_ctas(bn_bwd_apply_kernel<MODE, G2, Y2, DZ>, 0);                                    \
+    const int grid = want < occ * num_sms() ? want : occ * num_sms();                                                  \
+    bn_bwd_apply_kernel<MODE, G2, Y2, DZ><<<grid, 256, 0, st>>>(g1, g2, y, coef, y2, coef2, scale, shift, mask, rows, c, \
+                                                               dy, dy2, dz_out);                                       \
   } while (0)
-  if (!mask) DIRB_APP(MASK_FROM_Y, false, false);
-  else if (y2) DIRB_APP(MASK_BITS, true, false);
-  else if (dz_out) DIRB_APP(MASK_BITS, false, true);
-  else DIRB_APP(MASK_BITS, false, false);
+  if (!mask) DIRB_APP(MASK_FROM_Y, false, false, false);
+  else if (g2 && y2) DIRB_APP(MASK_BITS, true, true, false);
+  else if (g2 && dz_out) DIRB_APP(MASK_BITS, true, false, true);
+  else if (g2) DIRB_APP(MASK_BITS, true, false, false);
+  else if (y2) DIRB_APP(MASK_BITS, false, true, false);
+  else if (dz_out) DIRB_APP(MASK_BITS, false, false, true);
+  else DIRB_APP(MASK_BITS, false, false, false);
 #undef DIRB_APP
   DIRB_LAUNCHED();
   return DIRB200_OK;

@@ -67,7 +67,7 @@ struct dirb200_net {
   // finished stage while the earlier stages still compute; the incoming-gradient buffers live here between the calls
   std::vector<int> stage_begin;          // first block of stage s (1-based stages; stage_begin[num_stages+1] = #blocks)
   int bwd_next_stage = -1;               // stage the next dirb200_resnet_backward_stage call must name (-1: none pending)
-  __nv_bfloat16 *bw_gA = nullptr, *bw_nA = nullptr;    // gradient w.r.t. the next block output to process / spare
+  __nv_bfloat16 *bw_gA = nullptr, *bw_gB = nullptr, *bw_nA = nullptr, *bw_nB = nullptr, *bw_spareB = nullptr;
   // optional per-kernel-class timing (CUDA events around every launch group)
   bool profiling = false;
   struct ProfRec { int kind; cudaEvent_t a, b; };
@@ -165,7 +165,7 @@ static bool build(dirb200_net* net, const int* blocks_per_stage, int num_stages)
   net->stage_begin.push_back((int)net->blocks.size());
   net->feat_c = inplanes;
   net->feat_hw = h * w;
-  for (int i : {0, 1, 4, 5, 6}) NET_ALLOC(net->scratch[i], max_act * 2);   // g / next g, dy, dy (downsample), dgrad out
+  for (int i = 0; i < 8; ++i) NET_ALLOC(net->scratch[i], max_act * 2);
   {
     // split-K reduction jobs: every conv owns its partial buffer; one launch reduces a whole backward stage
     std::vector<WgradReduceDesc> rd;
@@ -300,12 +300,12 @@ static int conv_bn_backward(dirb200_net* net, ConvLayer& cv, const __nv_bfloat16
                             __nv_bfloat16* dy, cudaStream_t st) {
   BNLayer& bn = cv.bn;
   int nblk = 0;
-  RUNP(kBnBwdReduce, bn_bwd_reduce(g, cv.y, nullptr, bn.scale, bn.shift, nullptr, cv.rows, bn.c, net->bn_partial, &nblk,
-                                   st));
+  RUNP(kBnBwdReduce, bn_bwd_reduce(g, nullptr, cv.y, nullptr, bn.scale, bn.shift, nullptr, cv.rows, bn.c,
+                                   net->bn_partial, &nblk, st));
   RUNP(kBnBwdApply, bn_bwd_coeffs(net->bn_partial, nblk, 2, 1, cv.rows, bn.c, bn.mean, bn.invstd,
                                   params + bn.gamma_off, grads + bn.gamma_off, grads + bn.beta_off, bn.coef, st));
-  RUNP(kBnBwdApply, bn_bwd_apply(g, cv.y, bn.coef, nullptr, nullptr, bn.scale, bn.shift, nullptr, cv.rows, bn.c, dy,
-                                 nullptr, nullptr, st));
+  RUNP(kBnBwdApply, bn_bwd_apply(g, nullptr, cv.y, bn.coef, nullptr, nullptr, bn.scale, bn.shift, nullptr, cv.rows, bn.c,
+                                 dy, nullptr, nullptr, st));
   return DIRB200_OK;
 }
 
@@ -398,21 +398,18 @@ int dirb200_resnet_forward(dirb200_net* net, const float* x_nchw, const float* p
 
 namespace dirb200 {
 
-// blocks [lo, hi) in reverse order; net->bw_gA holds the gradient w.r.t. the last block's output.  ONE gradient tensor
-// flows between blocks: the shortcut branch's contribution (dz of an identity shortcut, the downsample conv's dgrad
-// otherwise) is folded into the conv1 dgrad's epilogue (conv_dgrad's `residual`), so the block-output BN backward
-// reads one incoming gradient instead of two.
+// blocks [lo, hi) in reverse order; the incoming gradient pair is net->bw_gA / bw_gB
 static int backward_blocks(dirb200_net* net, int lo, int hi, const float* params, float* grads, cudaStream_t st) {
-  __nv_bfloat16 *g = net->bw_gA, *nxt = net->bw_nA;
+  __nv_bfloat16 *gA = net->bw_gA, *gB = net->bw_gB, *nA = net->bw_nA, *nB = net->bw_nB, *spareB = net->bw_spareB;
   __nv_bfloat16 *t1 = net->scratch[4], *t2 = net->scratch[5], *t3 = net->scratch[6];
   for (int bi = hi - 1; bi >= lo; --bi) {
     Block& B = net->blocks[bi];
     BNLayer& b3 = B.c3.bn;
-    // ---- block output: out = relu(bn3(y3) + shortcut); dz = g * (out > 0)  (1-bit mask stored by the forward)
+    // ---- block output: out = relu(bn3(y3) + identity); dz = (gA + gB) * (out > 0)
     int nblk = 0;
     const int kparts = B.has_ds ? 3 : 2;
-    RUNP(kBnBwdReduce, bn_bwd_reduce(g, B.c3.y, B.has_ds ? B.ds.y : nullptr, nullptr, nullptr, B.mask, B.c3.rows, b3.c,
-                                     net->bn_partial, &nblk, st));
+    RUNP(kBnBwdReduce, bn_bwd_reduce(gA, gB, B.c3.y, B.has_ds ? B.ds.y : nullptr, nullptr, nullptr, B.mask, B.c3.rows,
+                                     b3.c, net->bn_partial, &nblk, st));
     if (B.has_ds) {
       BNLayer& bd = B.ds.bn;
       RUNP(kBnBwdApply, bn_bwd_coeffs(net->bn_partial, nblk, kparts, 2, B.c3.rows, b3.c, bd.mean, bd.invstd,
@@ -420,10 +417,9 @@ static int backward_blocks(dirb200_net* net, int lo, int hi, const float* params
     }
     RUNP(kBnBwdApply, bn_bwd_coeffs(net->bn_partial, nblk, kparts, 1, B.c3.rows, b3.c, b3.mean, b3.invstd,
                                     params + b3.gamma_off, grads + b3.gamma_off, grads + b3.beta_off, b3.coef, st));
-    // identity shortcut: dz goes straight into `nxt`, where conv1's dgrad adds its result on top
-    RUNP(kBnBwdApply, bn_bwd_apply(g, B.c3.y, b3.coef, B.has_ds ? B.ds.y : nullptr, B.has_ds ? B.ds.bn.coef : nullptr,
-                                   nullptr, nullptr, B.mask, B.c3.rows, b3.c, t1, B.has_ds ? t2 : nullptr,
-                                   B.has_ds ? nullptr : nxt, st));
+    RUNP(kBnBwdApply, bn_bwd_apply(gA, gB, B.c3.y, b3.coef, B.has_ds ? B.ds.y : nullptr,
+                                   B.has_ds ? B.ds.bn.coef : nullptr, nullptr, nullptr, B.mask, B.c3.rows, b3.c, t1,
+                                   B.has_ds ? t2 : nullptr, B.has_ds ? nullptr : nB, st));
     // ---- conv3
     RUN(wgrad_step(net, B.c2.a, t1, B.c3, st));
     RUNP(kDgrad, conv_dgrad(t1, B.c3.wd, t3, B.c3.s, st));
@@ -431,21 +427,23 @@ static int backward_blocks(dirb200_net* net, int lo, int hi, const float* params
     RUN(conv_bn_backward(net, B.c2, t3, params, grads, t1, st));
     RUN(wgrad_step(net, B.c1.a, t1, B.c2, st));
     RUNP(kDgrad, conv_dgrad(t1, B.c2.wd, t3, B.c2.s, st));
-    // ---- bn1
+    // ---- bn1 + conv1
     RUN(conv_bn_backward(net, B.c1, t3, params, grads, t1, st));
-    // ---- downsample branch first (its dgrad fills `nxt`), then conv1's dgrad accumulates onto the shortcut gradient
+    RUN(wgrad_step(net, B.in, t1, B.c1, st));
+    RUNP(kDgrad, conv_dgrad(t1, B.c1.wd, nA, B.c1.s, st));
+    // ---- downsample branch
     if (B.has_ds) {
       RUN(wgrad_step(net, B.in, t2, B.ds, st));
-      RUNP(kDgrad, conv_dgrad(t2, B.ds.wd, nxt, B.ds.s, st));
+      RUNP(kDgrad, conv_dgrad(t2, B.ds.wd, nB, B.ds.s, st));
     }
-    RUN(wgrad_step(net, B.in, t1, B.c1, st));
-    RUNP(kDgrad, conv_dgrad(t1, B.c1.wd, nxt, B.c1.s, st, nxt));
-    __nv_bfloat16* tmp = g;
-    g = nxt;
-    nxt = tmp;
+    // the two gradients w.r.t. this block's input become the next (earlier) block's incoming pair
+    __nv_bfloat16* oldA = gA;
+    __nv_bfloat16* oldB = gB ? gB : spareB;
+    gA = nA; gB = nB;
+    nA = oldA; nB = oldB;
+    spareB = nullptr;
   }
-  net->bw_gA = g;
-  net->bw_nA = nxt;
+  net->bw_gA = gA; net->bw_gB = gB; net->bw_nA = nA; net->bw_nB = nB; net->bw_spareB = spareB;
   return DIRB200_OK;
 }
 
@@ -468,8 +466,8 @@ int dirb200_resnet_backward_stage(dirb200_net* net, int stage, const float* d_en
   if (stage == nst) {
     DIRB_CHECK_ARG(net->forward_was_training, "resnet_backward: needs a preceding training-mode forward");
     DIRB_CHECK_ARG(d_enc, "resnet_backward_stage: the first stage needs d_enc");
-    net->bw_gA = net->scratch[0];
-    net->bw_nA = net->scratch[1];
+    net->bw_gA = net->scratch[0]; net->bw_gB = nullptr; net->bw_nA = net->scratch[2]; net->bw_nB = net->scratch[3];
+    net->bw_spareB = net->scratch[1];
     RUNP(kPool, avgpool_bwd(d_enc, net->n, net->feat_hw, net->feat_c, net->bw_gA, st));
   } else {
     DIRB_CHECK_ARG(net->bwd_next_stage == stage, "resnet_backward_stage: stage %d out of order (expected %d)", stage,
@@ -481,7 +479,7 @@ int dirb200_resnet_backward_stage(dirb200_net* net, int stage, const float* d_en
   } else {
     // ---- stem: maxpool -> bn1+relu -> conv1 (no data gradient needed)
     __nv_bfloat16 *t1 = net->scratch[4], *t3 = net->scratch[6];
-    RUNP(kPool, maxpool_bwd(net->bw_gA, nullptr, net->pool_idx, net->n, net->stem.s.ho, net->stem.s.wo, 64, t3, st));
+    RUNP(kPool, maxpool_bwd(net->bw_gA, net->bw_gB, net->pool_idx, net->n, net->stem.s.ho, net->stem.s.wo, 64, t3, st));
     RUN(conv_bn_backward(net, net->stem, t3, params, grads, t1, st));
     RUN(wgrad_step(net, net->x_s2d, t1, net->stem, st));
   }
