@@ -29,28 +29,6 @@ constexpr int kProducerThreads = 128;   // warps 0-3
 constexpr int kTmaWarp = 4, kMmaWarp = 5; // warps 6-9: epilogue (warp & 3 = TMEM lane quarter)
 constexpr int kThreads = 320;
 
-// Division by a run-time constant as multiply-high + shift (n < 2^31, d >= 1): the k-loops of the producer / TMA
-// warps used to spend most of their time in the ~35-instruction SASS sequences of `/` by cpb, kw, hw, wm
-// (ncu source page, profiles/r2_conv_stalls.md) -- that, not the memory system, was the "gather rate".
-struct FastDiv {
-  uint32_t mul, shr, d;
-  __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : (__umulhi(n, mul) >> shr); }
-  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
-    q = div(n);
-    r = n - q * d;
-  }
-};
-static FastDiv make_fastdiv(uint32_t d) {
-  FastDiv f{0u, 0u, d < 1 ? 1u : d};
-  if (f.d == 1) return f;
-  uint32_t lg = 0;
-  while ((1ull << lg) < f.d) ++lg;
-  const uint32_t p = 31 + lg;
-  f.mul = static_cast<uint32_t>(((1ull << p) + f.d - 1) / f.d);
-  f.shr = p - 32;
-  return f;
-}
-
 struct IgemmParams {
   const __nv_bfloat16* src;  // gathered tensor, NHWC
   int n, hs, ws, cs;         // its shape

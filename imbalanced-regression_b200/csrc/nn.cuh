@@ -18,16 +18,20 @@ int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, con
              const __nv_bfloat16* res_y, const float* res_scale, const float* res_shift, bool relu, int64_t rows, int c,
              __nv_bfloat16* out, uint8_t* mask_out, cudaStream_t st);
 // BN backward, ReLU mask from (y, scale, shift) when mask == nullptr, else from the stored bit mask
+// g2_h, g2_w > 0: g2 is the COMPACT [n, g2_h/2, g2_w/2, c] gradient of a stride-2 1x1 downsample conv (added at even y, x)
 int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* y, const __nv_bfloat16* y2,
                   const float* scale, const float* shift, const uint8_t* mask, int64_t rows, int c, float* partial,
-                  int* nblocks, cudaStream_t st);
+                  int* nblocks, cudaStream_t st, int g2_h = 0, int g2_w = 0);
 int bn_bwd_coeffs(const float* partial, int nblocks, int k, int gslot, int64_t rows, int c, const float* mean,
                   const float* invstd, const float* gamma, float* grad_gamma, float* grad_beta, float* coef,
                   cudaStream_t st);
 int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* y, const float* coef,
                  const __nv_bfloat16* y2, const float* coef2, const float* scale, const float* shift,
                  const uint8_t* mask, int64_t rows, int c, __nv_bfloat16* dy, __nv_bfloat16* dy2,
-                 __nv_bfloat16* dz_out, cudaStream_t st);
+                 __nv_bfloat16* dz_out, cudaStream_t st, int g2_h = 0, int g2_w = 0);
+// stem: relu(bn(y)) + 3x3/2 max pool in one pass (the activation itself is not materialised)
+int bn_relu_maxpool_fwd(const __nv_bfloat16* y, const float* scale, const float* shift, int n, int h, int w, int c,
+                        __nv_bfloat16* out, uint8_t* idx, cudaStream_t st);
 int maxpool_fwd(const __nv_bfloat16* x, int n, int h, int w, int c, __nv_bfloat16* out, uint8_t* idx, cudaStream_t st);
 int maxpool_bwd(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const uint8_t* idx, int n, int h, int w, int c,
                 __nv_bfloat16* dx, cudaStream_t st);

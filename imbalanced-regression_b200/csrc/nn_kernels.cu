@@ -300,12 +300,29 @@ struct MaskSrc {
   }
 };
 
-template <int MODE, bool HAS_G2, bool HAS_Y2>
+// Second incoming gradient of a block output: absent, a dense tensor, or -- behind a stride-2 1x1 downsample conv --
+// the COMPACT tensor [n, h/2, w/2, c] of that conv's dgrad, which contributes only at even (y, x) (the dense form
+// would be a memset of the full map plus a scattered GEMM plus two dense re-reads of mostly zeros).
+enum { G2_NONE = 0, G2_DENSE = 1, G2_COMPACT = 2 };
+struct CompactG2 {
+  FastDiv hw, w;          // full-resolution pixel grid of the rows
+  int h2, w2;             // compact grid
+  __device__ __forceinline__ bool locate(int64_t r, int64_t& r2) const {
+    uint32_t n, rem, yy, xx;
+    hw.divmod(static_cast<uint32_t>(r), n, rem);
+    w.divmod(rem, yy, xx);
+    r2 = (static_cast<int64_t>(n) * h2 + (yy >> 1)) * w2 + (xx >> 1);
+    return ((yy | xx) & 1u) == 0u;
+  }
+};
+
+template <int MODE, int G2M, bool HAS_Y2>
 __global__ void __launch_bounds__(256, 3)
-bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2, CompactG2 cg2,
                      const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ y2,
                      const float* __restrict__ scale, const float* __restrict__ shift,
                      const uint8_t* __restrict__ mask, int64_t rows, int c, float* __restrict__ partial) {
+  constexpr bool HAS_G2 = G2M != G2_NONE;
   const int cgroups = c / 8;
   const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
   constexpr int K = HAS_Y2 ? 3 : 2;
@@ -324,9 +341,14 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
     G[1] = *reinterpret_cast<const uint4*>(g1 + o1);
     Y[0] = *reinterpret_cast<const uint4*>(y + o0);
     Y[1] = *reinterpret_cast<const uint4*>(y + o1);
-    if (HAS_G2) {
+    if (G2M == G2_DENSE) {
       G2[0] = *reinterpret_cast<const uint4*>(g2 + o0);
       G2[1] = *reinterpret_cast<const uint4*>(g2 + o1);
+    } else if (G2M == G2_COMPACT) {
+      int64_t q0, q1;
+      const bool v0 = cg2.locate(r0, q0), v1 = cg2.locate(two ? r1 : r0, q1);
+      G2[0] = v0 ? *reinterpret_cast<const uint4*>(g2 + q0 * c + cg * 8) : make_uint4(0, 0, 0, 0);
+      G2[1] = v1 ? *reinterpret_cast<const uint4*>(g2 + q1 * c + cg * 8) : make_uint4(0, 0, 0, 0);
     }
     if (HAS_Y2) {
       Y2[0] = *reinterpret_cast<const uint4*>(y2 + o0);
@@ -389,9 +411,9 @@ __global__ void bn_bwd_coeffs_kernel(const float* __restrict__ partial, int nblo
 
 // dz = (g1 [+ g2]) * mask;  dy = A*dz + B*y + C  (and the same for the second BN);  optionally writes dz.
 // Same (channel group, row lane) mapping as bn_apply: coefficients live in registers.
-template <int MODE, bool HAS_G2, bool HAS_Y2, bool WRITE_DZ>
+template <int MODE, int G2M, bool HAS_Y2, bool WRITE_DZ>
 __global__ void __launch_bounds__(256, 2)
-bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2, CompactG2 cg2,
                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ coef,
                     const __nv_bfloat16* __restrict__ y2, const float* __restrict__ coef2,
                     const float* __restrict__ scale, const float* __restrict__ shift,
@@ -400,6 +422,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
   // rows per iteration: every load of all of them is issued before the first use.  Two CTAs of 8 warps fit per SM
   // (register-limited), so the plain two-input form needs four rows (8 x 16 B per thread) in flight to cover the HBM
   // latency -- with two it ran at 4.4 TB/s (ncu, profiles/r2_bn_full.md); the forms with more inputs keep two.
+  constexpr bool HAS_G2 = G2M != G2_NONE;
   constexpr int R = (HAS_G2 || HAS_Y2) ? 2 : 4;
   const int cgroups = c / 8;
   const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
@@ -429,7 +452,13 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* _
     for (int u = 0; u < R; ++u) {
       G[u] = *reinterpret_cast<const uint4*>(g1 + offs[u]);
       Y[u] = *reinterpret_cast<const uint4*>(y + offs[u]);
-      if (HAS_G2) G2[u] = *reinterpret_cast<const uint4*>(g2 + offs[u]);
+      if (G2M == G2_DENSE) {
+        G2[u] = *reinterpret_cast<const uint4*>(g2 + offs[u]);
+      } else if (G2M == G2_COMPACT) {
+        int64_t q;
+        const bool v = cg2.locate(rr[u], q);
+        G2[u] = v ? *reinterpret_cast<const uint4*>(g2 + q * c + cg * 8) : make_uint4(0, 0, 0, 0);
+      }
       if (HAS_Y2) Y2[u] = *reinterpret_cast<const uint4*>(y2 + offs[u]);
       M[u] = ms.load(rr[u]);
     }
@@ -492,6 +521,62 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, i
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (v.v[j] > best[j]) { best[j] = v.v[j]; bi[j] = r * 3 + s; }
+      }
+    }
+    V8 o;
+    __align__(8) uint8_t ib[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o.v[j] = best[j]; ib[j] = (uint8_t)bi[j]; }
+    const int64_t off = (((int64_t)b * ho + yo) * wo + xo) * c + g * 8;
+    store8(out + off, o);
+    *reinterpret_cast<uint2*>(idx + off) = *reinterpret_cast<uint2*>(ib);
+  }
+}
+
+// Stem: relu(bn(y)) and the 3x3 / stride 2 / pad 1 max pool in one pass (resnet.py:128-131: bn1 -> relu -> maxpool).
+// The activation is never written: the backward re-derives the ReLU mask from (y, scale, shift) and routes gradients by
+// the stored argmax, so nothing downstream reads it (saves 411 MB written + read at batch 256).  Values are rounded to
+// bf16 before they are compared, i.e. exactly what pooling the stored activation gave; idx = r*3+s of the first maximum.
+__global__ void __launch_bounds__(256)
+bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                           const float* __restrict__ shift, int n, int h, int w, int c,
+                           __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx) {
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1, cg = c / 8;
+  const int64_t total = (int64_t)n * ho * wo * cg;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    int64_t t = i / cg;
+    const int xo = (int)(t % wo); t /= wo;
+    const int yo = (int)(t % ho);
+    const int b = (int)(t / ho);
+    const V8 sc = loadf8(scale + g * 8), sh = loadf8(shift + g * 8);
+    // the (up to) nine loads first
+    uint4 v[9];
+    bool ok[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int yi = 2 * yo - 1 + r, xi = 2 * xo - 1 + q;
+        ok[r * 3 + q] = yi >= 0 && yi < h && xi >= 0 && xi < w;
+        v[r * 3 + q] = ok[r * 3 + q] ? *reinterpret_cast<const uint4*>(y + (((int64_t)b * h + yi) * w + xi) * c + g * 8)
+                                     : make_uint4(0, 0, 0, 0);
+      }
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      if (!ok[k]) continue;
+      const uint32_t yw[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float2 yv = bf2_to_f2(yw[p]);
+        const float2 a = bf2_to_f2(f2_to_bf2(fmaxf(fmaf(yv.x, sc.v[2 * p], sh.v[2 * p]), 0.f),
+                                             fmaxf(fmaf(yv.y, sc.v[2 * p + 1], sh.v[2 * p + 1]), 0.f)));
+        if (a.x > best[2 * p]) { best[2 * p] = a.x; bi[2 * p] = k; }
+        if (a.y > best[2 * p + 1]) { best[2 * p + 1] = a.y; bi[2 * p + 1] = k; }
       }
     }
     V8 o;
@@ -822,9 +907,24 @@ int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, con
 
 // mask == nullptr: conv -> BN -> ReLU layer, the ReLU mask is re-derived from y with (scale, shift);
 // mask != nullptr: block output, the bit mask bn_apply stored (g2 / y2: second incoming gradient / downsample branch).
+static CompactG2 make_compact(int g2_h, int g2_w) {
+  CompactG2 cg{};
+  if (g2_h > 0 && g2_w > 0) {
+    cg.hw = make_fastdiv(static_cast<uint32_t>(g2_h) * g2_w);
+    cg.w = make_fastdiv(static_cast<uint32_t>(g2_w));
+    cg.h2 = g2_h / 2;
+    cg.w2 = g2_w / 2;
+  }
+  return cg;
+}
+
+// g2_h, g2_w > 0: g2 is the compact [n, g2_h/2, g2_w/2, c] tensor (rows are the pixels of the g2_h x g2_w maps)
 int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* y, const __nv_bfloat16* y2,
                   const float* scale, const float* shift, const uint8_t* mask, int64_t rows, int c, float* partial,
-                  int* nblocks, cudaStream_t st) {
+                  int* nblocks, cudaStream_t st, int g2_h, int g2_w) {
+  const CompactG2 cg2 = make_compact(g2_h, g2_w);
+  DIRB_CHECK_ARG(g2_h == 0 || (g2 && mask && !y2 && g2_h % 2 == 0 && g2_w % 2 == 0 && rows % ((int64_t)g2_h * g2_w) == 0),
+                 "bn_bwd_reduce: bad compact second gradient");
   const int cgroups = c / 8;
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_bwd_reduce: unsupported channel count %d", c);
   DIRB_CHECK_ARG(mask || (scale && shift && !g2 && !y2), "bn_bwd_reduce: mask-from-y form takes one gradient, one BN");
@@ -834,14 +934,15 @@ int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_b
   do {                                                                                                    \
     static const int occ = resident_ctas(bn_bwd_reduce_kernel<MODE, G2, Y2>, 256 * 24 * sizeof(float));   \
     *nblocks = reduce_grid(rows, lanes, occ);                                                             \
-    bn_bwd_reduce_kernel<MODE, G2, Y2><<<*nblocks, 256, smem, st>>>(g1, g2, y, y2, scale, shift, mask, rows, c, \
+    bn_bwd_reduce_kernel<MODE, G2, Y2><<<*nblocks, 256, smem, st>>>(g1, g2, cg2, y, y2, scale, shift, mask, rows, c, \
                                                                     partial);                             \
   } while (0)
-  if (!mask) DIRB_RED(MASK_FROM_Y, false, false);
-  else if (g2 && y2) DIRB_RED(MASK_BITS, true, true);
-  else if (g2) DIRB_RED(MASK_BITS, true, false);
-  else if (y2) DIRB_RED(MASK_BITS, false, true);
-  else DIRB_RED(MASK_BITS, false, false);
+  if (!mask) DIRB_RED(MASK_FROM_Y, G2_NONE, false);
+  else if (g2_h) DIRB_RED(MASK_BITS, G2_COMPACT, false);
+  else if (g2 && y2) DIRB_RED(MASK_BITS, G2_DENSE, true);
+  else if (g2) DIRB_RED(MASK_BITS, G2_DENSE, false);
+  else if (y2) DIRB_RED(MASK_BITS, G2_NONE, true);
+  else DIRB_RED(MASK_BITS, G2_NONE, false);
 #undef DIRB_RED
   DIRB_LAUNCHED();
   return DIRB200_OK;
@@ -859,7 +960,9 @@ int bn_bwd_coeffs(const float* partial, int nblocks, int k, int gslot, int64_t r
 int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* y, const float* coef,
                  const __nv_bfloat16* y2, const float* coef2, const float* scale, const float* shift,
                  const uint8_t* mask, int64_t rows, int c, __nv_bfloat16* dy, __nv_bfloat16* dy2,
-                 __nv_bfloat16* dz_out, cudaStream_t st) {
+                 __nv_bfloat16* dz_out, cudaStream_t st, int g2_h, int g2_w) {
+  const CompactG2 cg2 = make_compact(g2_h, g2_w);
+  DIRB_CHECK_ARG(g2_h == 0 || (g2 && mask && !y2 && dz_out), "bn_bwd_apply: bad compact second gradient");
   const int cgroups = c / 8;
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_bwd_apply: unsupported channel count %d", c);
   DIRB_CHECK_ARG(mask || (scale && shift && !g2 && !y2 && !dz_out), "bn_bwd_apply: mask-from-y form takes one gradient, one BN");
@@ -869,16 +972,17 @@ int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bf
   do {                                                                                                                 \
     static const int occ = resident_ctas(bn_bwd_apply_kernel<MODE, G2, Y2, DZ>, 0);                                    \
     const int grid = want < occ * num_sms() ? want : occ * num_sms();                                                  \
-    bn_bwd_apply_kernel<MODE, G2, Y2, DZ><<<grid, 256, 0, st>>>(g1, g2, y, coef, y2, coef2, scale, shift, mask, rows, c, \
-                                                               dy, dy2, dz_out);                                       \
+    bn_bwd_apply_kernel<MODE, G2, Y2, DZ><<<grid, 256, 0, st>>>(g1, g2, cg2, y, coef, y2, coef2, scale, shift, mask, rows, \
+                                                               c, dy, dy2, dz_out);                                    \
   } while (0)
-  if (!mask) DIRB_APP(MASK_FROM_Y, false, false, false);
-  else if (g2 && y2) DIRB_APP(MASK_BITS, true, true, false);
-  else if (g2 && dz_out) DIRB_APP(MASK_BITS, true, false, true);
-  else if (g2) DIRB_APP(MASK_BITS, true, false, false);
-  else if (y2) DIRB_APP(MASK_BITS, false, true, false);
-  else if (dz_out) DIRB_APP(MASK_BITS, false, false, true);
-  else DIRB_APP(MASK_BITS, false, false, false);
+  if (!mask) DIRB_APP(MASK_FROM_Y, G2_NONE, false, false);
+  else if (g2_h) DIRB_APP(MASK_BITS, G2_COMPACT, false, true);
+  else if (g2 && y2) DIRB_APP(MASK_BITS, G2_DENSE, true, false);
+  else if (g2 && dz_out) DIRB_APP(MASK_BITS, G2_DENSE, false, true);
+  else if (g2) DIRB_APP(MASK_BITS, G2_DENSE, false, false);
+  else if (y2) DIRB_APP(MASK_BITS, G2_NONE, true, false);
+  else if (dz_out) DIRB_APP(MASK_BITS, G2_NONE, false, true);
+  else DIRB_APP(MASK_BITS, G2_NONE, false, false);
 #undef DIRB_APP
   DIRB_LAUNCHED();
   return DIRB200_OK;
@@ -887,6 +991,14 @@ int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bf
 int maxpool_fwd(const __nv_bfloat16* x, int n, int h, int w, int c, __nv_bfloat16* out, uint8_t* idx, cudaStream_t st) {
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
   maxpool_fwd_kernel<<<grid1d((int64_t)n * ho * wo * c / 8), 256, 0, st>>>(x, n, h, w, c, out, idx);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
+int bn_relu_maxpool_fwd(const __nv_bfloat16* y, const float* scale, const float* shift, int n, int h, int w, int c,
+                        __nv_bfloat16* out, uint8_t* idx, cudaStream_t st) {
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  bn_relu_maxpool_fwd_kernel<<<grid1d((int64_t)n * ho * wo * c / 8), 256, 0, st>>>(y, scale, shift, n, h, w, c, out, idx);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }

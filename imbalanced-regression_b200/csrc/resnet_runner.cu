@@ -68,6 +68,7 @@ struct dirb200_net {
   std::vector<int> stage_begin;          // first block of stage s (1-based stages; stage_begin[num_stages+1] = #blocks)
   int bwd_next_stage = -1;               // stage the next dirb200_resnet_backward_stage call must name (-1: none pending)
   __nv_bfloat16 *bw_gA = nullptr, *bw_gB = nullptr, *bw_nA = nullptr, *bw_nB = nullptr, *bw_spareB = nullptr;
+  int bw_gB_h = 0, bw_gB_w = 0;          // > 0: bw_gB is the compact [n, h/2, w/2, c] gradient of a stride-2 1x1 downsample
   // optional per-kernel-class timing (CUDA events around every launch group)
   bool profiling = false;
   struct ProfRec { int kind; cudaEvent_t a, b; };
@@ -126,7 +127,8 @@ static bool setup_conv(dirb200_net* net, ConvLayer& cv, int n, int h, int w, int
 
 static bool build(dirb200_net* net, const int* blocks_per_stage, int num_stages) {
   const int n = net->n;
-  if (!setup_conv(net, net->stem, n, net->h, net->w, 3, 64, 7, 2, 3, true, true)) return false;
+  // the stem's activation is never materialised: BN + ReLU are fused into the max pool (bn_relu_maxpool_fwd)
+  if (!setup_conv(net, net->stem, n, net->h, net->w, 3, 64, 7, 2, 3, true, false)) return false;
   int h = net->h / 2, w = net->w / 2;
   NET_ALLOC(net->x_s2d, (size_t)n * h * w * 16 * 2);
   net->pool_h = (h - 1) / 2 + 1;
@@ -374,8 +376,9 @@ int dirb200_resnet_forward(dirb200_net* net, const float* x_nchw, const float* p
   const bool tr = training != 0;
   RUNP(kPrep, prep_weights_all(params, net->prep_descs, net->num_convs, st));
   RUNP(kPrep, input_to_s2d(x_nchw, net->n, net->h, net->w, net->x_s2d, st));
-  RUN(conv_bn_forward(net, net->stem, net->x_s2d, params, bn_running, tr, st));
-  RUNP(kPool, maxpool_fwd(net->stem.a, net->n, net->stem.s.ho, net->stem.s.wo, 64, net->pool_out, net->pool_idx, st));
+  RUN(conv_bn_forward(net, net->stem, net->x_s2d, params, bn_running, tr, st));       // stem.a == nullptr: no bn_apply
+  RUNP(kPool, bn_relu_maxpool_fwd(net->stem.y, net->stem.bn.scale, net->stem.bn.shift, net->n, net->stem.s.ho,
+                                  net->stem.s.wo, 64, net->pool_out, net->pool_idx, st));
   for (Block& B : net->blocks) {
     RUN(conv_bn_forward(net, B.c1, B.in, params, bn_running, tr, st));
     RUN(conv_bn_forward(net, B.c2, B.c1.a, params, bn_running, tr, st));
@@ -402,6 +405,7 @@ namespace dirb200 {
 static int backward_blocks(dirb200_net* net, int lo, int hi, const float* params, float* grads, cudaStream_t st) {
   __nv_bfloat16 *gA = net->bw_gA, *gB = net->bw_gB, *nA = net->bw_nA, *nB = net->bw_nB, *spareB = net->bw_spareB;
   __nv_bfloat16 *t1 = net->scratch[4], *t2 = net->scratch[5], *t3 = net->scratch[6];
+  int gB_h = net->bw_gB_h, gB_w = net->bw_gB_w;
   for (int bi = hi - 1; bi >= lo; --bi) {
     Block& B = net->blocks[bi];
     BNLayer& b3 = B.c3.bn;
@@ -409,7 +413,7 @@ static int backward_blocks(dirb200_net* net, int lo, int hi, const float* params
     int nblk = 0;
     const int kparts = B.has_ds ? 3 : 2;
     RUNP(kBnBwdReduce, bn_bwd_reduce(gA, gB, B.c3.y, B.has_ds ? B.ds.y : nullptr, nullptr, nullptr, B.mask, B.c3.rows,
-                                     b3.c, net->bn_partial, &nblk, st));
+                                     b3.c, net->bn_partial, &nblk, st, gB_h, gB_w));
     if (B.has_ds) {
       BNLayer& bd = B.ds.bn;
       RUNP(kBnBwdApply, bn_bwd_coeffs(net->bn_partial, nblk, kparts, 2, B.c3.rows, b3.c, bd.mean, bd.invstd,
@@ -419,7 +423,8 @@ static int backward_blocks(dirb200_net* net, int lo, int hi, const float* params
                                     params + b3.gamma_off, grads + b3.gamma_off, grads + b3.beta_off, b3.coef, st));
     RUNP(kBnBwdApply, bn_bwd_apply(gA, gB, B.c3.y, b3.coef, B.has_ds ? B.ds.y : nullptr,
                                    B.has_ds ? B.ds.bn.coef : nullptr, nullptr, nullptr, B.mask, B.c3.rows, b3.c, t1,
-                                   B.has_ds ? t2 : nullptr, B.has_ds ? nullptr : nB, st));
+                                   B.has_ds ? t2 : nullptr, B.has_ds ? nullptr : nB, st, gB_h, gB_w));
+    gB_h = gB_w = 0;
     // ---- conv3
     RUN(wgrad_step(net, B.c2.a, t1, B.c3, st));
     RUNP(kDgrad, conv_dgrad(t1, B.c3.wd, t3, B.c3.s, st));
@@ -434,7 +439,19 @@ static int backward_blocks(dirb200_net* net, int lo, int hi, const float* params
     // ---- downsample branch
     if (B.has_ds) {
       RUN(wgrad_step(net, B.in, t2, B.ds, st));
-      RUNP(kDgrad, conv_dgrad(t2, B.ds.wd, nB, B.ds.s, st));
+      const ConvShape& d = B.ds.s;
+      if (d.stride == 2 && d.kh == 1 && d.kw == 1 && d.pad == 0 && d.h % 2 == 0 && d.w % 2 == 0 && bi > 0 &&
+          !net->blocks[bi - 1].has_ds) {
+        // stride-2 1x1 downsample: its input gradient is non-zero at the even pixels only -> keep it COMPACT
+        // ([n, h/2, w/2, cin], a plain GEMM over the strided grid); the previous block's output BN backward adds it at
+        // the even positions (no memset of the full map, no scattered store, no dense re-reads of zeros)
+        const ConvShape cs{d.n, d.ho, d.wo, d.cin, d.cout, 1, 1, 1, 0, d.ho, d.wo};
+        RUNP(kDgrad, conv_dgrad(t2, B.ds.wd, nB, cs, st));
+        gB_h = d.h;
+        gB_w = d.w;
+      } else {
+        RUNP(kDgrad, conv_dgrad(t2, B.ds.wd, nB, B.ds.s, st));
+      }
     }
     // the two gradients w.r.t. this block's input become the next (earlier) block's incoming pair
     __nv_bfloat16* oldA = gA;
@@ -444,6 +461,7 @@ static int backward_blocks(dirb200_net* net, int lo, int hi, const float* params
     spareB = nullptr;
   }
   net->bw_gA = gA; net->bw_gB = gB; net->bw_nA = nA; net->bw_nB = nB; net->bw_spareB = spareB;
+  net->bw_gB_h = gB_h; net->bw_gB_w = gB_w;
   return DIRB200_OK;
 }
 
@@ -468,6 +486,7 @@ int dirb200_resnet_backward_stage(dirb200_net* net, int stage, const float* d_en
     DIRB_CHECK_ARG(d_enc, "resnet_backward_stage: the first stage needs d_enc");
     net->bw_gA = net->scratch[0]; net->bw_gB = nullptr; net->bw_nA = net->scratch[2]; net->bw_nB = net->scratch[3];
     net->bw_spareB = net->scratch[1];
+    net->bw_gB_h = net->bw_gB_w = 0;
     RUNP(kPool, avgpool_bwd(d_enc, net->n, net->feat_hw, net->feat_c, net->bw_gA, st));
   } else {
     DIRB_CHECK_ARG(net->bwd_next_stage == stage, "resnet_backward_stage: stage %d out of order (expected %d)", stage,

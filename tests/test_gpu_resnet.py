@@ -131,8 +131,8 @@ def test_resnet50_layerwise_forward_teacher_forced(n, hw):
 
     with torch.no_grad():
         check("stem.y", pk(-1, 0), R._conv(q(x), p["conv1.weight"], 2, 3, True))
-        check("stem.a", pk(-1, 1), q(F.relu(R._bn(pk(-1, 0), p, "bn1.", None, True))))
-        check("stem.pool", pk(-1, 6), F.max_pool2d(pk(-1, 1), 3, 2, 1))
+        # relu(bn1(.)) is fused into the max pool and never stored: checked through the pooled tensor
+        check("stem.pool", pk(-1, 6), F.max_pool2d(q(F.relu(R._bn(pk(-1, 0), p, "bn1.", None, True))), 3, 2, 1))
         bi = 0
         for li, nblocks in enumerate((3, 4, 6, 3)):
             for b in range(nblocks):
@@ -156,7 +156,7 @@ def test_resnet50_layerwise_forward_teacher_forced(n, hw):
         check("avgpool", enc, pk(15, 6).mean(dim=(2, 3)))
 
 
-TAPS = [("stem.y", -1, 0), ("stem.a", -1, 1), ("stem.pool", -1, 6)]
+TAPS = [("stem.y", -1, 0), ("stem.pool", -1, 6)]      # the stem's activation is not materialised by the runner
 
 
 @pytest.mark.parametrize("layers,n,hw", [((3, 4, 6, 3), 16, 64), ((3, 4, 6, 3), 4, 224), ((2, 2, 1, 1), 16, 64),
@@ -185,7 +185,7 @@ def test_backward_vs_oracle_teacher_forced(layers, n, hw):
             force[name] = m.peek(x.shape, b, k, copy=n <= 16)   # big batch: zero-copy bf16 views of the runner's buffers
         except Exception:
             pass                                   # blocks without a downsample branch
-    assert len(force) == 3 + 6 * sum(layers) + 4
+    assert len(force) == 2 + 6 * sum(layers) + 4
     rpred, renc = R.forward(p, x, layers=layers, quant=True, force=force)
     ((rpred - t).abs() * w).mean().backward()
     assert rel(pred.detach(), rpred.detach()) < 2e-3
