@@ -41,7 +41,16 @@ struct PrepDesc {               // one conv layer's weight re-layout job (see pr
   size_t w_off;                 // fp32 [Cout][Cin][KH][KW] at params + w_off
   int cout, cin, kh, kw, stem;
   __nv_bfloat16 *wf, *wd;       // outputs (wd may be null)
+  FastDiv fd_cin, fd_cout, fd_taps;   // reciprocals of cin, cout, kh*kw (make_prep_desc)
 };
+inline PrepDesc make_prep_desc(size_t w_off, int cout, int cin, int kh, int kw, int stem, __nv_bfloat16* wf,
+                               __nv_bfloat16* wd) {
+  PrepDesc d{w_off, cout, cin, kh, kw, stem, wf, wd, {}, {}, {}};
+  d.fd_cin = make_fastdiv((uint32_t)cin);
+  d.fd_cout = make_fastdiv((uint32_t)cout);
+  d.fd_taps = make_fastdiv((uint32_t)(kh * kw));
+  return d;
+}
 int prep_weights_all(const float* params, const PrepDesc* descs_dev, int nlayers, cudaStream_t st);
 int prep_weights(const float* w, int cout, int cin, int kh, int kw, bool stem, __nv_bfloat16* wf, __nv_bfloat16* wd,
                  cudaStream_t st);

@@ -160,16 +160,26 @@ __global__ void prep_weights_all_kernel(const float* __restrict__ params, const 
     }
     return;
   }
-  const int64_t total = (int64_t)d.cout * d.cin * d.kh * d.kw;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % d.cin);
-    int64_t t = i / d.cin;
-    int s = (int)(t % d.kw); t /= d.kw;
-    int r = (int)(t % d.kh);
-    int co = (int)(t / d.kh);
-    const __nv_bfloat16 b = __float2bfloat16_rn(w[(((int64_t)co * d.cin + c) * d.kh + r) * d.kw + s]);
-    d.wf[i] = b;
-    if (d.wd) d.wd[(((int64_t)c * d.kh + r) * d.kw + s) * d.cout + co] = b;
+  // Two coalesced-store passes (one thread per OUTPUT element; the fp32 source is gathered, its 32-byte sectors are
+  // shared by neighbouring threads through L1/L2) instead of one pass with 2-byte scattered stores into the transposed
+  // copy; index arithmetic by multiply-high reciprocals filled in on the host.
+  const uint32_t taps = (uint32_t)(d.kh * d.kw);
+  const uint32_t total = (uint32_t)d.cout * (uint32_t)d.cin * taps;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  // fprop operand [co][tap][c]
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    uint32_t t, c, co, tap;
+    d.fd_cin.divmod(i, t, c);
+    d.fd_taps.divmod(t, co, tap);
+    d.wf[i] = __float2bfloat16_rn(w[((size_t)co * d.cin + c) * taps + tap]);
+  }
+  if (!d.wd) return;
+  // dgrad operand [c][tap][co]
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    uint32_t t, c, co, tap;
+    d.fd_cout.divmod(i, t, co);
+    d.fd_taps.divmod(t, c, tap);
+    d.wd[i] = __float2bfloat16_rn(w[((size_t)co * d.cin + c) * taps + tap]);
   }
 }
 

@@ -195,8 +195,8 @@ static bool build(dirb200_net* net, const int* blocks_per_stage, int num_stages)
   NET_ALLOC(net->stat_partial, sizeof(float) * bn_partial_floats(net->feat_c));
   std::vector<PrepDesc> descs;
   auto add = [&](const ConvLayer& cv) {
-    descs.push_back(PrepDesc{cv.w_off, cv.s.cout, cv.stem ? 3 : cv.s.cin, cv.stem ? 7 : cv.s.kh, cv.stem ? 7 : cv.s.kw,
-                             cv.stem ? 1 : 0, cv.wf, cv.wd});
+    descs.push_back(make_prep_desc(cv.w_off, cv.s.cout, cv.stem ? 3 : cv.s.cin, cv.stem ? 7 : cv.s.kh, cv.stem ? 7 : cv.s.kw,
+                                   cv.stem ? 1 : 0, cv.wf, cv.wd));
   };
   add(net->stem);
   for (Block& B : net->blocks) {
