@@ -39,7 +39,6 @@ struct IgemmParams {
   // (hm x wm), the real pixel is (2y'+py, 2x'+px) of the full_h x full_w image, and only the filter taps whose
   // parity matches (tap_list) are visited -- 9 tap-passes over quarter-size grids instead of 9 over the full one.
   int cls_on, cls_py, cls_px, full_h, full_w;
-  int nstages;               // B-stationary mode: A-ring depth that fits beside the resident weights
   int ntaps_c;               // taps visited by this launch
   int tap_list[9];           // their indices r*kw + s (identity when cls_on == 0)
   // per visited tap (index = position in tap_list), filled by finish_params(): element offset of the tap from the
@@ -90,7 +89,6 @@ struct Cfg {
   static constexpr int kStatWarpBytes = (BN / kEpiCols) * 4 * 32 * 4;
   static constexpr int kStatOffset = kEpiOffset + (STAGED_EPI ? 4 * kEpiWarpBytes : 0);
   static constexpr int kSmemBytes = kStatOffset + (STAGED_EPI ? 4 * kStatWarpBytes : 0) + 1024;
-  // B-stationary layout: nstages (<= kStages) A slots, then the whole B matrix; barriers stay at kBarOffset
   static constexpr int kTmemCols = 2 * BN;  // two accumulators (epilogue of tile i overlaps the MMAs of tile i+1)
 };
 
@@ -157,39 +155,29 @@ __device__ __forceinline__ const __nv_bfloat16* tap_source(const IgemmParams& P,
   return ok ? P.src + (static_cast<size_t>(rp.nb + hi) * P.ws + wi) * P.cs + coff : P.src;
 }
 
-// BSTAT ("B stationary"): when every tile of the launch uses the same B matrix (one N tile) and it fits in smem, the
-// whole weight matrix is loaded once per CTA and the ring carries only the gathered A rows -- removes the per-tile
-// re-fetch of the weights through L2 for the narrow layers (stem, 64/128-channel convs).
+// CTA2 (fprop / stride-1 dgrad, BN = 256, TMA-fed A operand): launched as (2,1,1) clusters; the pair owns a 256 x 256
+// tile.  Per k-block each CTA TMA-loads its own 128 A rows and its half of B with .cta_group::2 loads whose bytes are
+// all counted on the LEADER's full barrier (one expect_tx arrival by the leader's TMA warp); the leader issues
+// tcgen05.mma.cta_group::2 and its commits arrive on the empty / accumulator-full barriers of both CTAs (multicast);
+// the peer's epilogue warps hand the accumulator back by arriving on the leader's barrier.
 //
-// CTA2 (fprop/dgrad, BN >= 128): launched as (2,1,1) clusters; the pair owns a 256 x BN tile.  Per k-block each CTA
-// gathers its own 128 A rows and TMA-loads its half of B; the leader's full barrier collects its own 128 gather
-// arrivals, the transaction bytes of BOTH B halves and one arrival relayed by the peer's (otherwise idle) MMA warp
-// when the peer's gather has landed; the leader issues tcgen05.mma.cta_group::2 and its commits arrive on the
-// empty / accumulator-full barriers of both CTAs (multicast); the peer's epilogue warps hand the accumulator back by
-// arriving on the leader's barrier.
-//
-// ATMA (1x1 / stride-1 convolutions): the "gathered" operand is a plain [pixels][channels] matrix, so the TMA warp
-// loads the A tiles as well (tmap_a; K-major 64 x 128 boxes for fprop/dgrad, two 64 x 64 MN-major boxes for wgrad)
-// and warps 0-3 stay idle.  Measured motivation: the cp.async gather sustains only ~16 KB per 0.6 us per SM
-// whatever the tile shape or ring depth, which bounds every GEMM fed by it at ~0.6 us per k-block.
-template <int BN, bool WGRAD, bool STEM, bool BSTAT = false, bool CTA2 = false, bool ATMA = false>
+// ATMA: the A operand comes by TMA -- tiled maps for 1x1 / stride-1 convolutions (a plain [pixels][channels] matrix:
+// K-major 64 x 128 boxes for fprop / dgrad, two 64 x 64 MN-major boxes for wgrad), im2col-mode maps for the 3x3 and
+// strided ones -- issued by warp 4; warps 0-3 then idle.  Without ATMA (stem, stride-2 dgrad parity classes) warps 0-3
+// gather the rows with cp.async.
+template <int BN, bool WGRAD, bool STEM, bool CTA2 = false, bool ATMA = false>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_a,
              const IgemmParams P) {
   using C = Cfg<BN, !WGRAD, CTA2>;
-  static_assert(!(BSTAT && WGRAD), "B-stationary mode is for fprop/dgrad");
-  static_assert(!CTA2 || (!STEM && !BSTAT && BN >= 128), "CTA pairs: non-stem GEMMs with BN >= 128 only");
-  static_assert(!(CTA2 && WGRAD && ATMA), "wgrad pairs: gather-fed A only so far");
-  static_assert(!ATMA || (!STEM && !BSTAT), "TMA-fed A operand: not for the stem / B-stationary forms");
+  static_assert(!CTA2 || (ATMA && !WGRAD && !STEM && BN >= 128), "CTA pairs: TMA-fed fprop / dgrad GEMMs only");
+  static_assert(!ATMA || !STEM, "TMA-fed A operand: not for the stem");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + C::kBarOffset;
-  // BSTAT layout: [kStages x A (16 KB)] [B: num_kblocks x kBBytes] ; else [kStages x (A | B)]
-  auto a_addr = [&](int s) { return smem_base + s * (BSTAT ? C::kABytes : C::kStageBytes); };
+  auto a_addr = [&](int s) { return smem_base + s * C::kStageBytes; };
   auto b_addr = [&](int s) { return smem_base + s * C::kStageBytes + C::kABytes; };
-  const uint32_t nstages = BSTAT ? static_cast<uint32_t>(P.nstages) : static_cast<uint32_t>(C::kStages);
-  const uint32_t bstat_base = smem_base + nstages * C::kABytes;
-  const uint32_t bstat_bar = bar_base + 8u * (2 * C::kStages + 5);
+  constexpr uint32_t nstages = C::kStages;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
@@ -242,15 +230,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < C::kStages; ++s) {
-        // gather threads + the TMA thread's expect_tx arrival; pair leader: + the peer's relayed arrival;
-        // pair peer: gather threads only (its B bytes are counted on the leader's barrier)
-        // (pairs with TMA-fed A: everything is counted on the leader's barrier by its one expect_tx arrival)
-        mbar_init(full_bar(s), ATMA ? 1
-                                    : (CTA2 ? (rank == 0 ? kProducerThreads + 2 : kProducerThreads)
-                                            : kProducerThreads + (BSTAT ? 0 : 1)));
+        // TMA-fed: the TMA thread's one expect_tx arrival (pairs: everything is counted on the leader's barrier);
+        // gather-fed: + the 128 gather threads
+        mbar_init(full_bar(s), ATMA ? 1 : kProducerThreads + 1);
         mbar_init(empty_bar(s), 1);
       }
-      mbar_init(bstat_bar, 1);
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);
         mbar_init(tempty_bar(a), CTA2 ? 8 : 4);      // one arrival per epilogue warp (of both CTAs of a pair)
@@ -423,19 +407,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
     }  // !ATMA: with a TMA-fed A operand these four warps have nothing to do
   } else if (warp == kTmaWarp) {
     // ============================ B producer (TMA) ============================
-    if (lane == 0 && BSTAT) {
-      // the whole B matrix, once
-      mbar_arrive_expect_tx(bstat_bar, static_cast<uint32_t>(P.num_kblocks) * C::kBBytes);
-      for (int kb = 0; kb < P.num_kblocks; ++kb) {
-        int kcoord = kb;
-        if constexpr (!STEM) {
-          uint32_t tcb, cbb;
-          P.fd_cpb.divmod(static_cast<uint32_t>(kb), tcb, cbb);
-          kcoord = P.tap_list[tcb] * P.cpb + static_cast<int>(cbb);
-        }
-        tma_load_2d(bstat_base + kb * C::kBBytes, &tmap_b, bstat_bar, kcoord * BK, 0);
-      }
-    } else if (!BSTAT) {
+    {
       // the whole warp walks the ring (converged); one elected lane issues.  Ring position and the (tap, channel
       // block) of the k-block are counters; tap coordinates come from the host-filled tables -- no division here.
       uint32_t rs = 0, rph = 0;
@@ -461,24 +433,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           if (++rs == nstages) { rs = 0; rph ^= 1u; }
           const int kb = kb_begin + it;
           if (elect_one()) {
-            if constexpr (CTA2 && WGRAD) {
-              // wgrad pairs: this CTA's BN/2 columns of the dY tile
-              if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * C::kBBytes);
-#pragma unroll
-              for (int i = 0; i < C::kBRows / 64; ++i)
-                tma_load_2d_cta2(b_addr(s) + i * 8192, &tmap_b, full_bar(s),
-                                 n0 + static_cast<int>(rank) * C::kBRows + 64 * i, kb * 64);
-            } else if constexpr (CTA2) {
+            if constexpr (CTA2) {
               // this CTA's half of the B tile; both halves are accounted on the leader's barrier
-              if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * (C::kBBytes + (ATMA ? C::kABytes : 0)));
-              if constexpr (ATMA) {
-                // ... and this CTA's 128 A rows
-                if (P.a_mode == 1)
-                  tma_load_2d_cta2(a_addr(s), &tmap_a, full_bar(s), kb * BK, m_tile * BM);
-                else
-                  tma_load_im2col_4d_cta2(a_addr(s), &tmap_a, full_bar(s), cb * BK, tile_w0, tile_h0, tile_n0,
-                                          P.tap_s[tc], P.tap_r[tc]);
-              }
+              if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * (C::kBBytes + C::kABytes));
+              // ... and this CTA's 128 A rows
+              if (P.a_mode == 1)
+                tma_load_2d_cta2(a_addr(s), &tmap_a, full_bar(s), kb * BK, m_tile * BM);
+              else
+                tma_load_im2col_4d_cta2(a_addr(s), &tmap_a, full_bar(s), cb * BK, tile_w0, tile_h0, tile_n0,
+                                        P.tap_s[tc], P.tap_r[tc]);
               const int kcoord = P.tap_list[tc] * P.cpb + cb;
               tma_load_2d_cta2(b_addr(s), &tmap_b, full_bar(s), kcoord * BK, n0 + static_cast<int>(rank) * C::kBRows);
             } else {
@@ -537,26 +500,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
   } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ==============================
     if (CTA2 && rank != 0) {
-      // pair peer: no MMAs to issue -- relay "my gathered A rows of this stage have landed" to the leader's barrier
-      // (nothing to relay when the A rows come by TMA: their bytes are counted on the leader's barrier directly)
-      if (lane == 0 && !ATMA) {
-        uint32_t rs = 0, rph = 0;
-        for (int t = tile_first; t < tile_end; t += tile_step) {
-          int split, m_tile, n_tile, kb_begin, nk;
-          decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
-          for (int it = 0; it < nk; ++it) {
-            const int s = static_cast<int>(rs);
-            mbar_wait(full_bar(s), rph);
-            mbar_arrive_remote(mapa_rank(full_bar(s), 0));
-            if (++rs == nstages) { rs = 0; rph ^= 1u; }
-          }
-        }
-      }
+      // pair peer: no MMAs to issue, nothing to relay (its operand bytes are counted on the leader's barrier)
     } else {
       // the whole warp walks the ring (converged: operands stay in uniform registers); one elected lane issues
       constexpr uint32_t idesc = make_idesc(CTA2 ? 2 * BM : BM, BN, WGRAD ? 1 : 0, WGRAD ? 1 : 0);
       uint32_t rs = 0, rph = 0, tcount = 0;
-      if constexpr (BSTAT) mbar_wait(bstat_bar, 0);
       for (int t = tile_first; t < tile_end; t += tile_step, ++tcount) {
         int split, m_tile, n_tile, kb_begin, nk;
         decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
@@ -572,8 +520,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
           // K-major: 8-row atoms 1024 B apart; MN-major: 64-wide chunks 8192 B apart (LBO), 8-k atoms 1024 B (SBO)
           const uint64_t adesc = make_smem_desc(a_addr(s), WGRAD ? 8192u : 16u, 1024u);
           const uint64_t bdesc =
-              make_smem_desc(BSTAT ? bstat_base + static_cast<uint32_t>(kb_begin + it) * C::kBBytes : b_addr(s),
-                             WGRAD ? 8192u : 16u, 1024u);
+              make_smem_desc(b_addr(s), WGRAD ? 8192u : 16u, 1024u);
           constexpr uint32_t kadv = WGRAD ? (2048u >> 4) : (32u >> 4);   // one UMMA_K (=16) step, in 16-byte units
           if (elect_one()) {
 #pragma unroll
@@ -871,29 +818,29 @@ static IgemmParams finish_params(const IgemmParams& P) {
   return Q;
 }
 
-template <int BN, bool WGRAD, bool STEM, bool BSTAT, bool ATMA = false>
+template <int BN, bool WGRAD, bool STEM, bool ATMA = false>
 static int launch_igemm_impl(const CUtensorMap& tm, const CUtensorMap& tma, const IgemmParams& Qin, cudaStream_t st) {
   using C = Cfg<BN, !WGRAD>;
   const IgemmParams Q = finish_params(Qin);
   static bool configured = false;
   if (!configured) {
-    DIRB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, WGRAD, STEM, BSTAT, false, ATMA>,
+    DIRB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, WGRAD, STEM, false, ATMA>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
   const int grid = Q.num_tiles < num_sms() ? Q.num_tiles : num_sms();
   t_last_layout = StatLayout{grid, Q.n_tiles, BN, 1};
-  igemm_kernel<BN, WGRAD, STEM, BSTAT, false, ATMA><<<grid, kThreads, C::kSmemBytes, st>>>(tm, tma, Q);
+  igemm_kernel<BN, WGRAD, STEM, false, ATMA><<<grid, kThreads, C::kSmemBytes, st>>>(tm, tma, Q);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
 
 // CTA-pair variant: (2,1,1) clusters, one pair per two SMs; Q.m_tiles / Q.num_tiles count 256-row pair tiles.
-template <int BN, bool ATMA = false, bool WGRAD = false>
+template <int BN>
 static int launch_igemm_cta2(const CUtensorMap& tm, const CUtensorMap& tma, const IgemmParams& Qin, cudaStream_t st) {
-  using C = Cfg<BN, !WGRAD, true>;
+  using C = Cfg<BN, true, true>;
   const IgemmParams Q = finish_params(Qin);
-  auto kern = igemm_kernel<BN, WGRAD, false, false, true, ATMA>;
+  auto kern = igemm_kernel<BN, false, false, true, true>;
   static bool configured = false;
   if (!configured) {
     DIRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -951,9 +898,9 @@ static int launch_igemm(const CUtensorMap& tm, const IgemmParams& P, int m_tiles
   Q.m_tiles = m_tiles;
   Q.num_tiles = m_tiles * P.n_tiles * splits;
   if constexpr (!STEM) {
-    if (tma) return launch_igemm_impl<BN, WGRAD, false, false, true>(tm, *tma, Q, st);
+    if (tma) return launch_igemm_impl<BN, WGRAD, false, true>(tm, *tma, Q, st);
   }
-  return launch_igemm_impl<BN, WGRAD, STEM, false>(tm, tm, Q, st);
+  return launch_igemm_impl<BN, WGRAD, STEM>(tm, tm, Q, st);
 }
 
 // GEMM-N tile width: 256 halves the A-operand traffic per FLOP (the conv kernels are bound by L2->SM operand
@@ -1015,7 +962,7 @@ static int launch_cta2(const __nv_bfloat16* wmat, int ktot, int n_dim, const Ige
   IgemmParams Q = P;
   Q.m_tiles = (m_tiles + 1) / 2;                 // 256-row pair tiles
   Q.num_tiles = Q.m_tiles * P.n_tiles;
-  return launch_igemm_cta2<256, true>(tm, tma, Q, st);
+  return launch_igemm_cta2<256>(tm, tma, Q, st);
 }
 static bool want_pairs(int bn, int num_kblocks) { return pairs_enabled() && bn == 256 && num_kblocks >= 4; }
 
