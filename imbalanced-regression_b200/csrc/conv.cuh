@@ -21,8 +21,29 @@ struct StatLayout {
 // written, nothing else is touched) -- the BatchNorm batch statistics without re-reading y.
 int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, const ConvShape& s, bool stem,
                cudaStream_t st, float* stat_partial = nullptr, StatLayout* layout = nullptr);
+// Inference form (BatchNorm folded into the conv, agedb-dir/resnet.py:46-66 under model.eval()):
+//   out = [relu]( conv(x, w) * scale[cout] + shift[cout]  [+ residual] )     -- one launch, no BN pass
+struct ConvEpilogue {
+  const float* scale;                 // [cout]  gamma / sqrt(running_var + eps)
+  const float* shift;                 // [cout]  beta - running_mean * scale
+  const __nv_bfloat16* residual;      // optional [pixels][cout] (identity path or the folded downsample branch)
+  bool relu;
+};
+int conv_fprop_affine(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* out, const ConvShape& s,
+                      const ConvEpilogue& epi, cudaStream_t st);
+// Optional fusion for a dgrad whose output dx is g = d loss / d relu(bn(y)) of the previous conv -> BN -> ReLU layer: the
+// epilogue also accumulates that BN's backward moments (sum dz, sum dz*y with dz = g * [y*scale + shift > 0]) into
+// partial[CTA][2][cin] (rows as *layout describes), replacing the bn_bwd_reduce pass.  Only where
+// conv_dgrad_fuses_bn_moments(s) (stride 1, TMA-fed A operand).
+struct DgradBnMoments {
+  const __nv_bfloat16* y;       // raw output of the previous conv, [pixels][cin] like dx
+  const float *scale, *shift;   // its BN's forward coefficients (the ReLU mask is re-derived from them)
+  float* partial;
+  StatLayout* layout;           // out
+};
+bool conv_dgrad_fuses_bn_moments(const ConvShape& s);
 int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* dx, const ConvShape& s,
-               cudaStream_t st);
+               cudaStream_t st, const DgradBnMoments* bnm = nullptr);
 int conv_wgrad_splits(const ConvShape& s);
 size_t conv_wgrad_workspace_bytes(const ConvShape& s);
 int conv_wgrad_partials(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* partial, const ConvShape& s, bool stem,

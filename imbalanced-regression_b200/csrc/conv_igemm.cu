@@ -62,6 +62,19 @@ struct IgemmParams {
   // CTA as stat_out[blockIdx.x][2][ldc] (fp32), columns [n_tile * BN, n_tile * BN + BN) of the CTA's fixed n_tile only
   // (see StatLayout for which rows hold which columns)
   float* stat_out;
+  // AFFINE kernels (inference: BatchNorm folded into the conv epilogue, agedb-dir/train.py:286-335 / resnet.py:46-66 in
+  // eval mode): out = [relu]( acc * epi_scale[col] + epi_shift[col] [+ epi_res[row][col]] )
+  const float* epi_scale;
+  const float* epi_shift;
+  const __nv_bfloat16* epi_res;   // optional residual (identity / downsample branch), same [pixels][ldc] layout as out
+  int epi_relu;
+  // BSTAT kernels (stride-1 dgrad whose output dX is the gradient g w.r.t. a = relu(bn(y)) of the PREVIOUS layer): the
+  // epilogue also accumulates that BatchNorm's backward moments  S0 = sum dz,  S1 = sum dz * y  with
+  // dz = g * [y * bst_scale + bst_shift > 0]  (g as stored, bf16) into stat_out[CTA][2][ldc] -- the separate
+  // bn_bwd_reduce pass over (g, y) disappears; y has the layout of the output ([pixels][ldc])
+  const __nv_bfloat16* bst_y;
+  const float* bst_scale;
+  const float* bst_shift;
 };
 
 // CTA2: the tile is computed by a CTA pair (cta_group::2, UMMA M = 256): this CTA owns 128 of the 256 rows and stages
@@ -165,13 +178,15 @@ __device__ __forceinline__ const __nv_bfloat16* tap_source(const IgemmParams& P,
 // K-major 64 x 128 boxes for fprop / dgrad, two 64 x 64 MN-major boxes for wgrad), im2col-mode maps for the 3x3 and
 // strided ones -- issued by warp 4; warps 0-3 then idle.  Without ATMA (stem, stride-2 dgrad parity classes) warps 0-3
 // gather the rows with cp.async.
-template <int BN, bool WGRAD, bool STEM, bool CTA2 = false, bool ATMA = false>
+template <int BN, bool WGRAD, bool STEM, bool CTA2 = false, bool ATMA = false, bool AFFINE = false, bool BSTAT = false>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_a,
              const IgemmParams P) {
   using C = Cfg<BN, !WGRAD, CTA2>;
   static_assert(!CTA2 || (ATMA && !WGRAD && !STEM && BN >= 128), "CTA pairs: TMA-fed fprop / dgrad GEMMs only");
   static_assert(!ATMA || !STEM, "TMA-fed A operand: not for the stem");
+  static_assert(!AFFINE || (ATMA && !WGRAD), "folded-BN epilogue: TMA-fed fprop GEMMs only");
+  static_assert(!BSTAT || (ATMA && !WGRAD && !AFFINE), "BN-backward moments in the epilogue: TMA-fed dgrad GEMMs only");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + C::kBarOffset;
@@ -561,6 +576,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
       int split, m_tile, n_tile, kb_begin, nk;
       decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
       const int acc = tcount & 1;
+      if constexpr (BSTAT) {
+        // the y rows this warp will need in its statistics passes: pulled into L2 while the tile's MMAs still run
+        const long long pr = static_cast<long long>(m_tile) * BM + quarter * 32 + lane;
+        if (pr < P.pixels) {
+          const __nv_bfloat16* yl = P.bst_y + pr * P.ldc + n_tile * BN;
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(yl + j * 64));
+        }
+      }
       mbar_wait(tfull_bar(acc), (tcount >> 1) & 1);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -595,6 +619,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
             uint32_t v[32];
             tmem_ld_32x32(taddr + cb * C::kEpiCols + c * 32, v);
             tmem_ld_wait();
+            if constexpr (AFFINE) {
+              // per-column scale / shift: the same address in every lane (one broadcast transaction per load)
+              const float4* sc4 = reinterpret_cast<const float4*>(P.epi_scale + n0 + cb * C::kEpiCols + c * 32);
+              const float4* sh4 = reinterpret_cast<const float4*>(P.epi_shift + n0 + cb * C::kEpiCols + c * 32);
+              const bool relu_now = P.epi_relu && P.epi_res == nullptr;    // with a residual the ReLU follows the add
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 a = __ldg(sc4 + q4), b = __ldg(sh4 + q4);
+                float r0 = fmaf(__uint_as_float(v[4 * q4]), a.x, b.x), r1 = fmaf(__uint_as_float(v[4 * q4 + 1]), a.y, b.y);
+                float r2 = fmaf(__uint_as_float(v[4 * q4 + 2]), a.z, b.z), r3 = fmaf(__uint_as_float(v[4 * q4 + 3]), a.w, b.w);
+                if (relu_now) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); r2 = fmaxf(r2, 0.f); r3 = fmaxf(r3, 0.f); }
+                v[4 * q4] = __float_as_uint(r0); v[4 * q4 + 1] = __float_as_uint(r1);
+                v[4 * q4 + 2] = __float_as_uint(r2); v[4 * q4 + 3] = __float_as_uint(r3);
+              }
+            }
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               uint32_t pk[4];
@@ -609,7 +648,29 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
             }
           }
           __syncwarp();
+          // BSTAT: lane l owns columns 2l, 2l+1 of the pass; its 32 y words (one per tile row of this warp; L2 hits
+          // thanks to the prefetch above) are requested now -- the accumulator registers are dead -- and consumed after
+          // the output rows have been stored (requesting them before the TMEM load spilled and measured slower)
+          uint32_t yw[32];
+          if constexpr (BSTAT) {
+            const __nv_bfloat16* yp = P.bst_y + n0 + cb * C::kEpiCols + 2 * lane;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const long long p = p0 + r;
+              yw[r] = p < P.pixels ? __ldg(reinterpret_cast<const unsigned int*>(yp + p * P.ldc)) : 0u;
+            }
+          }
           __nv_bfloat16* out_cols = reinterpret_cast<__nv_bfloat16*>(P.out) + n0 + cb * C::kEpiCols + col16 * 8;
+          uint4 resv[kIters];
+          if constexpr (AFFINE) {
+            // residual rows of this pass: all loads issued before the first use
+            if (P.epi_res != nullptr) {
+              const __nv_bfloat16* res_cols = P.epi_res + n0 + cb * C::kEpiCols + col16 * 8;
+#pragma unroll
+              for (int i = 0; i < kIters; ++i)
+                resv[i] = orow8[i] >= 0 ? *reinterpret_cast<const uint4*>(res_cols + orow8[i] * P.ldc) : make_uint4(0, 0, 0, 0);
+            }
+          }
 #pragma unroll
           for (int i = 0; i < kIters; ++i) {
             if (orow8[i] >= 0) {
@@ -617,10 +678,52 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                            : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
                            : "r"(stage_base + (i * kRowsPerIter + sub) * C::kStageRowBytes + col16 * 16));
+              if constexpr (AFFINE) {
+                if (P.epi_res != nullptr) {
+                  uint32_t o[4] = {val.x, val.y, val.z, val.w};
+                  const uint32_t rr[4] = {resv[i].x, resv[i].y, resv[i].z, resv[i].w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    float lo = __uint_as_float(o[e] << 16) + __uint_as_float(rr[e] << 16);
+                    float hi = __uint_as_float(o[e] & 0xffff0000u) + __uint_as_float(rr[e] & 0xffff0000u);
+                    if (P.epi_relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+                    o[e] = *reinterpret_cast<uint32_t*>(&h);
+                  }
+                  val = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+              }
               *reinterpret_cast<uint4*>(out_cols + orow8[i] * P.ldc) = val;
             }
           }
-          if (P.stat_out != nullptr) {
+          if constexpr (BSTAT) {
+            // dz = g * [bn(y) > 0] with the forward's own fmaf; S0 += dz, S1 += dz * y (two chains, packed fp32 math)
+            const uint32_t* sp = reinterpret_cast<const uint32_t*>(smem_raw + (stage_base - smem_u32(smem_raw))) + lane;
+            const float2 bsc = __ldg(reinterpret_cast<const float2*>(P.bst_scale + n0 + cb * C::kEpiCols + 2 * lane));
+            const float2 bsh = __ldg(reinterpret_cast<const float2*>(P.bst_shift + n0 + cb * C::kEpiCols + 2 * lane));
+            float2 sa = make_float2(0.f, 0.f), qa = sa, sb = sa, qb = sa;
+#pragma unroll
+            for (int r = 0; r < 32; r += 2) {
+              const uint32_t w0 = sp[r * (C::kStageRowBytes / 4)], w1 = sp[(r + 1) * (C::kStageRowBytes / 4)];
+              float2 g0 = make_float2(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xffff0000u));
+              float2 g1 = make_float2(__uint_as_float(w1 << 16), __uint_as_float(w1 & 0xffff0000u));
+              const float2 y0 = make_float2(__uint_as_float(yw[r] << 16), __uint_as_float(yw[r] & 0xffff0000u));
+              const float2 y1 = make_float2(__uint_as_float(yw[r + 1] << 16), __uint_as_float(yw[r + 1] & 0xffff0000u));
+              if (!(fmaf(y0.x, bsc.x, bsh.x) > 0.f)) g0.x = 0.f;
+              if (!(fmaf(y0.y, bsc.y, bsh.y) > 0.f)) g0.y = 0.f;
+              if (!(fmaf(y1.x, bsc.x, bsh.x) > 0.f)) g1.x = 0.f;
+              if (!(fmaf(y1.y, bsc.y, bsh.y) > 0.f)) g1.y = 0.f;
+              sa = __fadd2_rn(sa, g0);
+              qa = __ffma2_rn(g0, y0, qa);
+              sb = __fadd2_rn(sb, g1);
+              qb = __ffma2_rn(g1, y1, qb);
+            }
+            float* acc = stat_sm + cb * 4 * 32;
+            acc[0] += sa.x + sb.x;
+            acc[32] += sa.y + sb.y;
+            acc[64] += qa.x + qb.x;
+            acc[96] += qa.y + qb.y;
+          } else if (P.stat_out != nullptr) {
             // column sums over this warp's 32 rows: lane l owns columns 2l, 2l+1 of the pass (one bf16x2 word per
             // row; rows past the end of the tensor hold zeros).  Word (36 r + l): conflict-free.  Plain (non-volatile)
             // loads so that all 32 are in flight together, packed fp32 adds / FMAs (FADD2 / FFMA2), two chains.
@@ -818,29 +921,29 @@ static IgemmParams finish_params(const IgemmParams& P) {
   return Q;
 }
 
-template <int BN, bool WGRAD, bool STEM, bool ATMA = false>
+template <int BN, bool WGRAD, bool STEM, bool ATMA = false, bool AFFINE = false, bool BSTAT = false>
 static int launch_igemm_impl(const CUtensorMap& tm, const CUtensorMap& tma, const IgemmParams& Qin, cudaStream_t st) {
   using C = Cfg<BN, !WGRAD>;
   const IgemmParams Q = finish_params(Qin);
   static bool configured = false;
   if (!configured) {
-    DIRB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, WGRAD, STEM, false, ATMA>,
+    DIRB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, WGRAD, STEM, false, ATMA, AFFINE, BSTAT>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
   const int grid = Q.num_tiles < num_sms() ? Q.num_tiles : num_sms();
   t_last_layout = StatLayout{grid, Q.n_tiles, BN, 1};
-  igemm_kernel<BN, WGRAD, STEM, false, ATMA><<<grid, kThreads, C::kSmemBytes, st>>>(tm, tma, Q);
+  igemm_kernel<BN, WGRAD, STEM, false, ATMA, AFFINE, BSTAT><<<grid, kThreads, C::kSmemBytes, st>>>(tm, tma, Q);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
 
 // CTA-pair variant: (2,1,1) clusters, one pair per two SMs; Q.m_tiles / Q.num_tiles count 256-row pair tiles.
-template <int BN>
+template <int BN, bool AFFINE = false, bool BSTAT = false>
 static int launch_igemm_cta2(const CUtensorMap& tm, const CUtensorMap& tma, const IgemmParams& Qin, cudaStream_t st) {
   using C = Cfg<BN, true, true>;
   const IgemmParams Q = finish_params(Qin);
-  auto kern = igemm_kernel<BN, false, false, true, true>;
+  auto kern = igemm_kernel<BN, false, false, true, true, AFFINE, BSTAT>;
   static bool configured = false;
   if (!configured) {
     DIRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -898,7 +1001,17 @@ static int launch_igemm(const CUtensorMap& tm, const IgemmParams& P, int m_tiles
   Q.m_tiles = m_tiles;
   Q.num_tiles = m_tiles * P.n_tiles * splits;
   if constexpr (!STEM) {
-    if (tma) return launch_igemm_impl<BN, WGRAD, false, true>(tm, *tma, Q, st);
+    if (tma) {
+      if constexpr (!WGRAD) {
+        if (Q.epi_scale != nullptr) return launch_igemm_impl<BN, false, false, true, true>(tm, *tma, Q, st);
+        if (Q.bst_y != nullptr) return launch_igemm_impl<BN, false, false, true, false, true>(tm, *tma, Q, st);
+      }
+      return launch_igemm_impl<BN, WGRAD, false, true>(tm, *tma, Q, st);
+    }
+  }
+  if (Q.epi_scale != nullptr || Q.bst_y != nullptr) {
+    set_error("conv: the folded-BN / BN-backward epilogues need a TMA-fed A operand (DIRB200_ATMA / DIRB200_IM2COL on)");
+    return DIRB200_ERR_ARG;
   }
   return launch_igemm_impl<BN, WGRAD, STEM>(tm, tm, Q, st);
 }
@@ -962,23 +1075,31 @@ static int launch_cta2(const __nv_bfloat16* wmat, int ktot, int n_dim, const Ige
   IgemmParams Q = P;
   Q.m_tiles = (m_tiles + 1) / 2;                 // 256-row pair tiles
   Q.num_tiles = Q.m_tiles * P.n_tiles;
+  if (Q.epi_scale != nullptr) return launch_igemm_cta2<256, true>(tm, tma, Q, st);
+  if (Q.bst_y != nullptr) return launch_igemm_cta2<256, false, true>(tm, tma, Q, st);
   return launch_igemm_cta2<256>(tm, tma, Q, st);
 }
 static bool want_pairs(int bn, int num_kblocks) { return pairs_enabled() && bn == 256 && num_kblocks >= 4; }
 
 // Y[n,ho,wo,cout] = conv(X[n,h,w,cin], W[cout][kh][kw][cin])
 static int conv_fprop_impl(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, const ConvShape& s, bool stem,
-                           cudaStream_t st, float* stat_partial);
+                           cudaStream_t st, float* stat_partial, const ConvEpilogue* epi);
 
 int conv_fprop(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, const ConvShape& s, bool stem,
                cudaStream_t st, float* stat_partial, StatLayout* layout) {
-  const int rc = conv_fprop_impl(x, w, y, s, stem, st, stat_partial);
+  const int rc = conv_fprop_impl(x, w, y, s, stem, st, stat_partial, nullptr);
   if (layout) *layout = t_last_layout;
   return rc;
 }
 
+int conv_fprop_affine(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* out, const ConvShape& s,
+                      const ConvEpilogue& epi, cudaStream_t st) {
+  DIRB_CHECK_ARG(epi.scale && epi.shift, "conv_fprop_affine: scale / shift missing");
+  return conv_fprop_impl(x, w, out, s, false, st, nullptr, &epi);
+}
+
 static int conv_fprop_impl(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, const ConvShape& s, bool stem,
-                           cudaStream_t st, float* stat_partial) {
+                           cudaStream_t st, float* stat_partial, const ConvEpilogue* epi) {
   if (int rc = check_shape(s, stem, "conv_fprop")) return rc;
   const int ktot = s.kh * s.kw * s.cin;
   IgemmParams P{};
@@ -992,6 +1113,9 @@ static int conv_fprop_impl(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_
   for (int i = 0; i < 9; ++i) P.tap_list[i] = i;
   P.ldc = s.cout; P.out = y;
   P.stat_out = stat_partial;
+  if (epi) {
+    P.epi_scale = epi->scale; P.epi_shift = epi->shift; P.epi_res = epi->residual; P.epi_relu = epi->relu ? 1 : 0;
+  }
   const int m_tiles = static_cast<int>((P.pixels + BM - 1) / BM);
   const int bn = pick_bn(s.cout, m_tiles, !is_plain_gemm(s, stem));
   P.n_tiles = s.cout / bn;
@@ -1017,9 +1141,15 @@ static int conv_fprop_impl(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_
 }
 
 // dX[n,h,w,cin] = conv_transpose(dY[n,ho,wo,cout], Wt[cin][kh][kw][cout])
+bool conv_dgrad_fuses_bn_moments(const ConvShape& s) {
+  return s.stride == 1 && (is_plain_gemm(s, false) || (im2col_enabled() && s.kh == s.kw));
+}
+
 int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* dx, const ConvShape& s,
-               cudaStream_t st) {
+               cudaStream_t st, const DgradBnMoments* bnm) {
   if (int rc = check_shape(s, false, "conv_dgrad")) return rc;
+  DIRB_CHECK_ARG(!bnm || (conv_dgrad_fuses_bn_moments(s) && bnm->y && bnm->scale && bnm->shift && bnm->partial),
+                 "conv_dgrad: BN-backward moments are fused into TMA-fed stride-1 dgrads only");
   DIRB_CHECK_ARG(s.stride == 1 || s.stride == 2, "conv_dgrad: stride must be 1 or 2 (got %d)", s.stride);
   DIRB_CHECK_ARG(s.kh * s.kw <= 9, "conv_dgrad: at most 9 filter taps (got %dx%d)", s.kh, s.kw);
   const int ktot = s.kh * s.kw * s.cout;
@@ -1028,6 +1158,9 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
   P.kh = s.kh; P.kw = s.kw; P.stride = s.stride; P.pad = s.pad; P.transposed = 1;
   P.cpb = s.cout / 64;
   P.ldc = s.cin; P.out = dx;
+  if (bnm) {
+    P.bst_y = bnm->y; P.bst_scale = bnm->scale; P.bst_shift = bnm->shift; P.stat_out = bnm->partial;
+  }
   CUtensorMap tm;
   if (s.stride == 1) {
     P.pixels = static_cast<long long>(s.n) * s.h * s.w;
@@ -1052,10 +1185,16 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
       P.a_mode = 2; P.i2c_stride = 1; P.i2c_lo = lo;
       tma_fed = true;
     }
-    if (tma_fed && want_pairs(bn, P.num_kblocks)) return launch_cta2(wt, ktot, s.cin, P, m_tiles, st, ta);
-    if (int rc = make_tmap_bf16_2d(&tm, wt, ktot, s.cin, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
-    if (tma_fed) return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st, &ta);
-    return DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st);
+    int rc;
+    if (tma_fed && want_pairs(bn, P.num_kblocks)) {
+      rc = launch_cta2(wt, ktot, s.cin, P, m_tiles, st, ta);
+    } else {
+      if ((rc = make_tmap_bf16_2d(&tm, wt, ktot, s.cin, static_cast<uint64_t>(ktot) * 2, bn))) return rc;
+      rc = tma_fed ? DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st, &ta)
+                   : DISPATCH_BN(bn, false, false, tm, P, m_tiles, 1, st);
+    }
+    if (bnm && bnm->layout) *bnm->layout = t_last_layout;
+    return rc;
   }
   // stride 2: one launch per output-pixel parity class; a class without any tap receives no gradient (zeros)
   bool need_zero = false;

@@ -137,6 +137,42 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ y, int64_t rows, int c, float*
   column_reduce_finish<2>(acc, cg, cgroups, c, partial);
 }
 
+// Sums of the two slots of the per-CTA rows [rows][2][c] that hold channel i under layout L (conv epilogue statistics,
+// see StatLayout): CTA groups j, j + n_tiles, ...; `group` consecutive rows each.  (32, 32) thread block as above;
+// valid in threads with threadIdx.y == 0 after the call.
+__device__ __forceinline__ void sum_layout2(const float* __restrict__ partial, const StatLayout& L, int c, int i,
+                                            double (*sh)[32][32], double& r0, double& r1) {
+  double a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
+  if (i < c) {
+    const int j = i / L.bn;
+    const int ngroups = L.rows / L.group;
+    const int nk = j < ngroups ? (ngroups - 1 - j) / L.n_tiles + 1 : 0;
+    const int nrows = nk * L.group;
+    int t = threadIdx.y;
+    for (; t + 32 < nrows; t += 64) {            // four independent loads in flight
+      const int q0 = (j + (t / L.group) * L.n_tiles) * L.group + t % L.group;
+      const int q1 = (j + ((t + 32) / L.group) * L.n_tiles) * L.group + (t + 32) % L.group;
+      const float x0 = partial[((size_t)q0 * 2) * c + i], y0 = partial[((size_t)q0 * 2 + 1) * c + i];
+      const float x1 = partial[((size_t)q1 * 2) * c + i], y1 = partial[((size_t)q1 * 2 + 1) * c + i];
+      a0 += (double)x0; b0 += (double)y0; a1 += (double)x1; b1 += (double)y1;
+    }
+    if (t < nrows) {
+      const int q0 = (j + (t / L.group) * L.n_tiles) * L.group + t % L.group;
+      a0 += (double)partial[((size_t)q0 * 2) * c + i];
+      b0 += (double)partial[((size_t)q0 * 2 + 1) * c + i];
+    }
+  }
+  sh[0][threadIdx.y][threadIdx.x] = a0 + a1;
+  sh[1][threadIdx.y][threadIdx.x] = b0 + b1;
+  __syncthreads();
+  r0 = r1 = 0.0;
+  if (threadIdx.y == 0)
+    for (int w = 0; w < 32; ++w) {
+      r0 += sh[0][w][threadIdx.x];
+      r1 += sh[1][w][threadIdx.x];
+    }
+}
+
 // mean / invstd / scale / shift from the accumulated sums; running statistics as nn.BatchNorm2d (momentum 0.1,
 // unbiased running variance).
 __global__ void bn_finalize_kernel(const float* __restrict__ partial, StatLayout L, int64_t rows, int c,
@@ -146,36 +182,9 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, StatLayout
                                    float* __restrict__ scale, float* __restrict__ shift) {
   __shared__ double sh[2][32][32];
   const int i = blockIdx.x * 32 + threadIdx.x;
-  double a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
-  if (i < c) {
-    // rows that hold channel i (see StatLayout): CTA groups j, j + n_tiles, ...; `group` consecutive rows each
-    const int j = i / L.bn;
-    const int ngroups = L.rows / L.group;
-    const int nk = j < ngroups ? (ngroups - 1 - j) / L.n_tiles + 1 : 0;
-    const int nrows = nk * L.group;
-    int t = threadIdx.y;
-    for (; t + 32 < nrows; t += 64) {            // four independent loads in flight
-      const int r0 = (j + (t / L.group) * L.n_tiles) * L.group + t % L.group;
-      const int r1 = (j + ((t + 32) / L.group) * L.n_tiles) * L.group + (t + 32) % L.group;
-      const float x0 = partial[((size_t)r0 * 2) * c + i], y0 = partial[((size_t)r0 * 2 + 1) * c + i];
-      const float x1 = partial[((size_t)r1 * 2) * c + i], y1 = partial[((size_t)r1 * 2 + 1) * c + i];
-      a0 += (double)x0; b0 += (double)y0; a1 += (double)x1; b1 += (double)y1;
-    }
-    if (t < nrows) {
-      const int r0 = (j + (t / L.group) * L.n_tiles) * L.group + t % L.group;
-      a0 += (double)partial[((size_t)r0 * 2) * c + i];
-      b0 += (double)partial[((size_t)r0 * 2 + 1) * c + i];
-    }
-  }
-  sh[0][threadIdx.y][threadIdx.x] = a0 + a1;
-  sh[1][threadIdx.y][threadIdx.x] = b0 + b1;
-  __syncthreads();
+  double sx, sq;
+  sum_layout2(partial, L, c, i, sh, sx, sq);
   if (threadIdx.y != 0 || i >= c) return;
-  double sx = 0.0, sq = 0.0;
-  for (int w = 0; w < 32; ++w) {
-    sx += sh[0][w][threadIdx.x];
-    sq += sh[1][w][threadIdx.x];
-  }
   const double n = (double)rows;
   const double m = sx / n;
   double var = sq / n - m * m;
@@ -202,6 +211,16 @@ __global__ void bn_eval_coeffs_kernel(int c, const float* __restrict__ gamma, co
   const float sc = gamma[i] * rsqrtf(running_var[i] + eps);
   scale[i] = sc;
   shift[i] = beta[i] - running_mean[i] * sc;
+}
+
+__global__ void bn_eval_coeffs_all_kernel(const BnEvalDesc* __restrict__ descs, const float* __restrict__ params,
+                                          const float* __restrict__ running, float eps) {
+  const BnEvalDesc d = descs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.c) return;
+  const float sc = params[d.gamma_off + i] * rsqrtf(running[d.rv_off + i] + eps);
+  d.scale[i] = sc;
+  d.shift[i] = params[d.beta_off + i] - running[d.rm_off + i] * sc;
 }
 
 // out = [relu]( y*scale + shift  [+ res]  [+ res_y*res_scale + res_shift] )
@@ -271,7 +290,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
 //   MASK_BITS    (block output, BN + residual + ReLU):  the 1-bit-per-element mask bn_apply stored.
 // The reduction accumulates the raw moments  S0 = sum dz,  S1 = sum dz*y  [, S2 = sum dz*y2 for the downsample-branch
 // BN that shares dz]; dbeta = S0 and dgamma = invstd * (S1 - mean*S0) are formed in fp64 by bn_bwd_coeffs_kernel.
-enum { MASK_FROM_Y = 0, MASK_BITS = 1 };
+enum { MASK_FROM_Y = 0, MASK_BITS = 1, MASK_NONE = 2 };   // MASK_NONE: the incoming tensor is dz already
 
 template <int MODE>
 struct MaskSrc {
@@ -293,7 +312,7 @@ struct MaskSrc {
     if (MODE == MASK_FROM_Y) {
       if (!(fmaf(yv.x, sc.v[2 * w], sh.v[2 * w]) > 0.f)) g.x = 0.f;
       if (!(fmaf(yv.y, sc.v[2 * w + 1], sh.v[2 * w + 1]) > 0.f)) g.y = 0.f;
-    } else {
+    } else if (MODE == MASK_BITS) {
       if (!((m >> (2 * w)) & 1u)) g.x = 0.f;
       if (!((m >> (2 * w + 1)) & 1u)) g.y = 0.f;
     }
@@ -316,12 +335,15 @@ struct CompactG2 {
   }
 };
 
-template <int MODE, int G2M, bool HAS_Y2>
+// WRITE_DZ (identity blocks): dz is stored (bf16) -- it is the gradient of the shortcut path anyway -- and the sums
+// are taken over the STORED values, so that bn_bwd_apply can read dz (one tensor) instead of g1, g2 and the mask again.
+template <int MODE, int G2M, bool HAS_Y2, bool WRITE_DZ>
 __global__ void __launch_bounds__(256, 3)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2, CompactG2 cg2,
                      const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ y2,
                      const float* __restrict__ scale, const float* __restrict__ shift,
-                     const uint8_t* __restrict__ mask, int64_t rows, int c, float* __restrict__ partial) {
+                     const uint8_t* __restrict__ mask, int64_t rows, int c, float* __restrict__ partial,
+                     __nv_bfloat16* __restrict__ dz_out) {
   constexpr bool HAS_G2 = G2M != G2_NONE;
   const int cgroups = c / 8;
   const int cg = threadIdx.x % cgroups, lane = threadIdx.x / cgroups, lanes = blockDim.x / cgroups;
@@ -360,6 +382,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
     for (int u = 0; u < 2; ++u) {
       if (u == 1 && !two) break;
       const uint32_t gw[4] = {G[u].x, G[u].y, G[u].z, G[u].w}, yw[4] = {Y[u].x, Y[u].y, Y[u].z, Y[u].w};
+      uint32_t oz[4];
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         float2 g = bf2_to_f2(gw[w]);
@@ -371,6 +394,10 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
         }
         const float2 yv = bf2_to_f2(yw[w]);
         ms.apply(M[u], w, yv, g);
+        if (WRITE_DZ) {
+          oz[w] = f2_to_bf2(g.x, g.y);
+          g = bf2_to_f2(oz[w]);
+        }
         acc[0][2 * w] += g.x;
         acc[0][2 * w + 1] += g.y;
         acc[1][2 * w] = fmaf(g.x, yv.x, acc[1][2 * w]);
@@ -382,6 +409,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
           acc[K - 1][2 * w + 1] = fmaf(g.y, y2v.y, acc[K - 1][2 * w + 1]);
         }
       }
+      if (WRITE_DZ) *reinterpret_cast<uint4*>(dz_out + (u ? o1 : o0)) = make_uint4(oz[0], oz[1], oz[2], oz[3]);
     }
   }
   column_reduce_finish<K>(acc, cg, cgroups, c, partial);
@@ -391,6 +419,19 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* 
 //   A = gamma*invstd,  B = -gamma*invstd^2*dgamma/n,  C = gamma*invstd*(mean*invstd*dgamma/n - dbeta/n);
 // dbeta / dgamma are summed here from the reduce kernel's per-CTA partials [nblocks][K][c] (dbeta = slot 0,
 // dgamma = slot `gslot`); also accumulates them into the fp32 parameter gradients.
+__device__ __forceinline__ void bn_bwd_coeffs_write(double db, double s1, int i, int64_t rows, int c,
+                                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                    const float* __restrict__ gamma, float* __restrict__ grad_gamma,
+                                                    float* __restrict__ grad_beta, float* __restrict__ coef) {
+  const double n = (double)rows, is = (double)invstd[i], ga = (double)gamma[i], mu = (double)mean[i];
+  const double dg = is * (s1 - mu * db);          // sum dz * xhat from the raw moments
+  coef[i] = (float)(ga * is);
+  coef[c + i] = (float)(-ga * is * is * dg / n);
+  coef[2 * c + i] = (float)(ga * is * (mu * is * dg / n - db / n));
+  grad_gamma[i] += (float)dg;
+  grad_beta[i] += (float)db;
+}
+
 __global__ void bn_bwd_coeffs_kernel(const float* __restrict__ partial, int nblocks, int K, int gslot, int64_t rows,
                                      int c, const float* __restrict__ mean, const float* __restrict__ invstd,
                                      const float* __restrict__ gamma, float* __restrict__ grad_gamma,
@@ -400,13 +441,20 @@ __global__ void bn_bwd_coeffs_kernel(const float* __restrict__ partial, int nblo
   double db, s1;
   sum_partials2(partial, nblocks, K, 0, gslot, c, i, sh, db, s1);
   if (threadIdx.y != 0 || i >= c) return;
-  const double n = (double)rows, is = (double)invstd[i], ga = (double)gamma[i], mu = (double)mean[i];
-  const double dg = is * (s1 - mu * db);          // sum dz * xhat from the raw moments
-  coef[i] = (float)(ga * is);
-  coef[c + i] = (float)(-ga * is * is * dg / n);
-  coef[2 * c + i] = (float)(ga * is * (mu * is * dg / n - db / n));
-  grad_gamma[i] += (float)dg;
-  grad_beta[i] += (float)db;
+  bn_bwd_coeffs_write(db, s1, i, rows, c, mean, invstd, gamma, grad_gamma, grad_beta, coef);
+}
+
+// same, from the per-CTA rows a dgrad epilogue wrote (conv_dgrad with DgradBnMoments; rows as L describes)
+__global__ void bn_bwd_coeffs_layout_kernel(const float* __restrict__ partial, StatLayout L, int64_t rows, int c,
+                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                            const float* __restrict__ gamma, float* __restrict__ grad_gamma,
+                                            float* __restrict__ grad_beta, float* __restrict__ coef) {
+  __shared__ double sh[2][32][32];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  double db, s1;
+  sum_layout2(partial, L, c, i, sh, db, s1);
+  if (threadIdx.y != 0 || i >= c) return;
+  bn_bwd_coeffs_write(db, s1, i, rows, c, mean, invstd, gamma, grad_gamma, grad_beta, coef);
 }
 
 // dz = (g1 [+ g2]) * mask;  dy = A*dz + B*y + C  (and the same for the second BN);  optionally writes dz.
@@ -894,6 +942,13 @@ int bn_eval_coeffs(int c, const float* gamma, const float* beta, float eps, cons
   return DIRB200_OK;
 }
 
+int bn_eval_coeffs_all(const BnEvalDesc* descs_dev, int nlayers, int max_c, const float* params, const float* running,
+                       float eps, cudaStream_t st) {
+  bn_eval_coeffs_all_kernel<<<dim3((max_c + 255) / 256, nlayers), 256, 0, st>>>(descs_dev, params, running, eps);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
 int bn_apply(const __nv_bfloat16* y, const float* scale, const float* shift, const __nv_bfloat16* res,
              const __nv_bfloat16* res_y, const float* res_scale, const float* res_shift, bool relu, int64_t rows, int c,
              __nv_bfloat16* out, uint8_t* mask_out, cudaStream_t st) {
@@ -921,28 +976,32 @@ static CompactG2 make_compact(int g2_h, int g2_w) {
 // g2_h, g2_w > 0: g2 is the compact [n, g2_h/2, g2_w/2, c] tensor (rows are the pixels of the g2_h x g2_w maps)
 int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* y, const __nv_bfloat16* y2,
                   const float* scale, const float* shift, const uint8_t* mask, int64_t rows, int c, float* partial,
-                  int* nblocks, cudaStream_t st, int g2_h, int g2_w) {
+                  int* nblocks, cudaStream_t st, int g2_h, int g2_w, __nv_bfloat16* dz_out) {
   const CompactG2 cg2 = make_compact(g2_h, g2_w);
   DIRB_CHECK_ARG(g2_h == 0 || (g2 && mask && !y2 && g2_h % 2 == 0 && g2_w % 2 == 0 && rows % ((int64_t)g2_h * g2_w) == 0),
                  "bn_bwd_reduce: bad compact second gradient");
   const int cgroups = c / 8;
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_bwd_reduce: unsupported channel count %d", c);
   DIRB_CHECK_ARG(mask || (scale && shift && !g2 && !y2), "bn_bwd_reduce: mask-from-y form takes one gradient, one BN");
+  DIRB_CHECK_ARG(!dz_out || (mask && !y2), "bn_bwd_reduce: dz is stored for identity blocks only");
   const int lanes = 256 / cgroups;
   const size_t smem = 256 * (y2 ? 24 : 16) * sizeof(float);
-#define DIRB_RED(MODE, G2, Y2)                                                                            \
-  do {                                                                                                    \
-    static const int occ = resident_ctas(bn_bwd_reduce_kernel<MODE, G2, Y2>, 256 * 24 * sizeof(float));   \
-    *nblocks = reduce_grid(rows, lanes, occ);                                                             \
-    bn_bwd_reduce_kernel<MODE, G2, Y2><<<*nblocks, 256, smem, st>>>(g1, g2, cg2, y, y2, scale, shift, mask, rows, c, \
-                                                                    partial);                             \
+#define DIRB_RED(MODE, G2, Y2, DZ)                                                                            \
+  do {                                                                                                        \
+    static const int occ = resident_ctas(bn_bwd_reduce_kernel<MODE, G2, Y2, DZ>, 256 * 24 * sizeof(float));   \
+    *nblocks = reduce_grid(rows, lanes, occ);                                                                 \
+    bn_bwd_reduce_kernel<MODE, G2, Y2, DZ><<<*nblocks, 256, smem, st>>>(g1, g2, cg2, y, y2, scale, shift, mask, rows, c, \
+                                                                        partial, dz_out);                     \
   } while (0)
-  if (!mask) DIRB_RED(MASK_FROM_Y, G2_NONE, false);
-  else if (g2_h) DIRB_RED(MASK_BITS, G2_COMPACT, false);
-  else if (g2 && y2) DIRB_RED(MASK_BITS, G2_DENSE, true);
-  else if (g2) DIRB_RED(MASK_BITS, G2_DENSE, false);
-  else if (y2) DIRB_RED(MASK_BITS, G2_NONE, true);
-  else DIRB_RED(MASK_BITS, G2_NONE, false);
+  if (!mask) DIRB_RED(MASK_FROM_Y, G2_NONE, false, false);
+  else if (g2_h && dz_out) DIRB_RED(MASK_BITS, G2_COMPACT, false, true);
+  else if (g2_h) DIRB_RED(MASK_BITS, G2_COMPACT, false, false);
+  else if (g2 && y2) DIRB_RED(MASK_BITS, G2_DENSE, true, false);
+  else if (g2 && dz_out) DIRB_RED(MASK_BITS, G2_DENSE, false, true);
+  else if (g2) DIRB_RED(MASK_BITS, G2_DENSE, false, false);
+  else if (y2) DIRB_RED(MASK_BITS, G2_NONE, true, false);
+  else if (dz_out) DIRB_RED(MASK_BITS, G2_NONE, false, true);
+  else DIRB_RED(MASK_BITS, G2_NONE, false, false);
 #undef DIRB_RED
   DIRB_LAUNCHED();
   return DIRB200_OK;
@@ -957,6 +1016,18 @@ int bn_bwd_coeffs(const float* partial, int nblocks, int k, int gslot, int64_t r
   return DIRB200_OK;
 }
 
+int bn_bwd_coeffs_layout(const float* partial, const StatLayout& layout, int64_t rows, int c, const float* mean,
+                         const float* invstd, const float* gamma, float* grad_gamma, float* grad_beta, float* coef,
+                         cudaStream_t st) {
+  DIRB_CHECK_ARG(layout.rows > 0 && layout.n_tiles > 0 && layout.bn > 0 && layout.group > 0 &&
+                     layout.n_tiles * layout.bn >= c,
+                 "bn_bwd_coeffs_layout: bad partial layout");
+  bn_bwd_coeffs_layout_kernel<<<(c + 31) / 32, dim3(32, 32), 0, st>>>(partial, layout, rows, c, mean, invstd, gamma,
+                                                                      grad_gamma, grad_beta, coef);
+  DIRB_LAUNCHED();
+  return DIRB200_OK;
+}
+
 int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bfloat16* y, const float* coef,
                  const __nv_bfloat16* y2, const float* coef2, const float* scale, const float* shift,
                  const uint8_t* mask, int64_t rows, int c, __nv_bfloat16* dy, __nv_bfloat16* dy2,
@@ -965,7 +1036,8 @@ int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bf
   DIRB_CHECK_ARG(g2_h == 0 || (g2 && mask && !y2 && dz_out), "bn_bwd_apply: bad compact second gradient");
   const int cgroups = c / 8;
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_bwd_apply: unsupported channel count %d", c);
-  DIRB_CHECK_ARG(mask || (scale && shift && !g2 && !y2 && !dz_out), "bn_bwd_apply: mask-from-y form takes one gradient, one BN");
+  DIRB_CHECK_ARG(mask || (!g2 && !y2 && !dz_out && (scale != nullptr) == (shift != nullptr)),
+                 "bn_bwd_apply: the mask-from-y and the dz-input forms take one gradient, one BN");
   DIRB_CHECK_ARG(!(y2 && dz_out), "bn_bwd_apply: a block has either a downsample branch or an identity path");
   const int want = stream_grid(rows, 256 / cgroups);
 #define DIRB_APP(MODE, G2, Y2, DZ)                                                                                     \
@@ -975,7 +1047,8 @@ int bn_bwd_apply(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_bf
     bn_bwd_apply_kernel<MODE, G2, Y2, DZ><<<grid, 256, 0, st>>>(g1, g2, cg2, y, coef, y2, coef2, scale, shift, mask, rows, \
                                                                c, dy, dy2, dz_out);                                    \
   } while (0)
-  if (!mask) DIRB_APP(MASK_FROM_Y, G2_NONE, false, false);
+  if (!mask && !scale) DIRB_APP(MASK_NONE, G2_NONE, false, false);     // g1 is dz already (bn_bwd_reduce stored it)
+  else if (!mask) DIRB_APP(MASK_FROM_Y, G2_NONE, false, false);
   else if (g2_h) DIRB_APP(MASK_BITS, G2_COMPACT, false, true);
   else if (g2 && y2) DIRB_APP(MASK_BITS, G2_DENSE, true, false);
   else if (g2 && dz_out) DIRB_APP(MASK_BITS, G2_DENSE, false, true);

@@ -59,6 +59,8 @@ struct dirb200_net {
   float* bn_partial = nullptr;   // per-CTA partial sums of the BN column reductions (backward)
   float* stat_partial = nullptr; // per-CTA BN statistics [CTA][2][c] written by the conv fprop epilogue (conv.cuh)
   PrepDesc* prep_descs = nullptr; // device table for the single weight re-layout launch
+  BnEvalDesc* bn_eval_descs = nullptr;  // device table: every BN layer, for the single eval-coefficient launch
+  int num_bns = 0, max_bn_c = 0;
   int num_convs = 0;
   size_t param_count = 0, running_count = 0, activation_bytes = 0;
   std::vector<void*> allocs;
@@ -205,8 +207,21 @@ static bool build(dirb200_net* net, const int* blocks_per_stage, int num_stages)
   }
   net->num_convs = (int)descs.size();
   NET_ALLOC(net->prep_descs, sizeof(PrepDesc) * descs.size());
-  return cudaMemcpy(net->prep_descs, descs.data(), sizeof(PrepDesc) * descs.size(), cudaMemcpyHostToDevice) ==
-         cudaSuccess;
+  if (cudaMemcpy(net->prep_descs, descs.data(), sizeof(PrepDesc) * descs.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+    return false;
+  std::vector<BnEvalDesc> bd;
+  auto addbn = [&](const BNLayer& bn) {
+    bd.push_back(BnEvalDesc{bn.c, bn.gamma_off, bn.beta_off, bn.rm_off, bn.rv_off, bn.scale, bn.shift});
+    net->max_bn_c = std::max(net->max_bn_c, bn.c);
+  };
+  addbn(net->stem.bn);
+  for (Block& B : net->blocks) {
+    addbn(B.c1.bn); addbn(B.c2.bn); addbn(B.c3.bn);
+    if (B.has_ds) addbn(B.ds.bn);
+  }
+  net->num_bns = (int)bd.size();
+  NET_ALLOC(net->bn_eval_descs, sizeof(BnEvalDesc) * bd.size());
+  return cudaMemcpy(net->bn_eval_descs, bd.data(), sizeof(BnEvalDesc) * bd.size(), cudaMemcpyHostToDevice) == cudaSuccess;
 }
 
 #define RUN(expr)                    \
@@ -298,16 +313,79 @@ static int wgrad_reduce_stage(dirb200_net* net, int stage, float* grads, cudaStr
 
 // BN backward for a conv followed by BN+ReLU: g = d loss / d relu-output.  The ReLU mask is re-derived from
 // (y, scale, shift): the activation cv.a is not read.
+// moments: the layout of the (sum dz, sum dz*y) rows the dgrad that PRODUCED g already accumulated in its epilogue
+// (dgrad_with_bn_moments below) -- then the bn_bwd_reduce pass over (g, y) is skipped.
 static int conv_bn_backward(dirb200_net* net, ConvLayer& cv, const __nv_bfloat16* g, const float* params, float* grads,
-                            __nv_bfloat16* dy, cudaStream_t st) {
+                            __nv_bfloat16* dy, cudaStream_t st, const StatLayout* moments = nullptr) {
   BNLayer& bn = cv.bn;
-  int nblk = 0;
-  RUNP(kBnBwdReduce, bn_bwd_reduce(g, nullptr, cv.y, nullptr, bn.scale, bn.shift, nullptr, cv.rows, bn.c,
-                                   net->bn_partial, &nblk, st));
-  RUNP(kBnBwdApply, bn_bwd_coeffs(net->bn_partial, nblk, 2, 1, cv.rows, bn.c, bn.mean, bn.invstd,
-                                  params + bn.gamma_off, grads + bn.gamma_off, grads + bn.beta_off, bn.coef, st));
+  if (moments) {
+    RUNP(kBnBwdApply, bn_bwd_coeffs_layout(net->bn_partial, *moments, cv.rows, bn.c, bn.mean, bn.invstd,
+                                           params + bn.gamma_off, grads + bn.gamma_off, grads + bn.beta_off, bn.coef, st));
+  } else {
+    int nblk = 0;
+    RUNP(kBnBwdReduce, bn_bwd_reduce(g, nullptr, cv.y, nullptr, bn.scale, bn.shift, nullptr, cv.rows, bn.c,
+                                     net->bn_partial, &nblk, st));
+    RUNP(kBnBwdApply, bn_bwd_coeffs(net->bn_partial, nblk, 2, 1, cv.rows, bn.c, bn.mean, bn.invstd,
+                                    params + bn.gamma_off, grads + bn.gamma_off, grads + bn.beta_off, bn.coef, st));
+  }
   RUNP(kBnBwdApply, bn_bwd_apply(g, nullptr, cv.y, bn.coef, nullptr, nullptr, bn.scale, bn.shift, nullptr, cv.rows, bn.c,
                                  dy, nullptr, nullptr, st));
+  return DIRB200_OK;
+}
+
+// Inference forward (agedb-dir/train.py:286-335 validate(); resnet.py:46-66,128-138 under model.eval()): BatchNorm uses
+// the running statistics, so it is a per-channel affine map that folds into the conv epilogue -- every
+// conv -> BN [-> ReLU] and the whole conv3 -> BN -> (+ shortcut) -> ReLU tail of a block is ONE launch, and no raw conv
+// output is written.  ~58 launches instead of ~165.  DIRB200_FOLDED_EVAL=0 keeps the unfused sequence (A/B checks).
+static bool folded_eval() {
+  static const bool on = [] {
+    const char* e = getenv("DIRB200_FOLDED_EVAL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+
+static int forward_eval_folded(dirb200_net* net, const float* params, const float* running, float* enc_out,
+                               cudaStream_t st) {
+  RUNP(kBnStats, bn_eval_coeffs_all(net->bn_eval_descs, net->num_bns, net->max_bn_c, params, running, 1e-5f, st));
+  // stem: plain conv, then BN + ReLU inside the max pool (as in training; the activation is never materialised)
+  RUNP(kFprop, conv_fprop(net->x_s2d, net->stem.wf, net->stem.y, net->stem.s, true, st));
+  RUNP(kPool, bn_relu_maxpool_fwd(net->stem.y, net->stem.bn.scale, net->stem.bn.shift, net->n, net->stem.s.ho,
+                                  net->stem.s.wo, 64, net->pool_out, net->pool_idx, st));
+  for (Block& B : net->blocks) {
+    RUNP(kFprop, conv_fprop_affine(B.in, B.c1.wf, B.c1.a, B.c1.s, ConvEpilogue{B.c1.bn.scale, B.c1.bn.shift, nullptr, true}, st));
+    RUNP(kFprop, conv_fprop_affine(B.c1.a, B.c2.wf, B.c2.a, B.c2.s, ConvEpilogue{B.c2.bn.scale, B.c2.bn.shift, nullptr, true}, st));
+    const __nv_bfloat16* shortcut = B.in;
+    if (B.has_ds) {
+      RUNP(kFprop, conv_fprop_affine(B.in, B.ds.wf, B.ds.y, B.ds.s, ConvEpilogue{B.ds.bn.scale, B.ds.bn.shift, nullptr, false}, st));
+      shortcut = B.ds.y;
+    }
+    RUNP(kFprop, conv_fprop_affine(B.c2.a, B.c3.wf, B.out, B.c3.s, ConvEpilogue{B.c3.bn.scale, B.c3.bn.shift, shortcut, true}, st));
+  }
+  RUNP(kPool, avgpool_fwd(net->blocks.back().out, net->n, net->feat_hw, net->feat_c, enc_out, st));
+  return DIRB200_OK;
+}
+
+// DIRB200_FUSED_BWD_MOMENTS=0: separate bn_bwd_reduce passes everywhere (A/B measurements).
+static bool fused_bwd_moments() {
+  static const bool on = [] {
+    const char* e = getenv("DIRB200_FUSED_BWD_MOMENTS");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+
+// dgrad of `cv` whose output g is the gradient w.r.t. relu(bn(prev.y)): where the kernel can, the BN-backward moments of
+// `prev` come out of the epilogue (*fused = true, *lay = their row layout in net->bn_partial)
+static int dgrad_with_bn_moments(dirb200_net* net, const __nv_bfloat16* dy, ConvLayer& cv, ConvLayer& prev,
+                                 __nv_bfloat16* g, StatLayout* lay, bool* fused, cudaStream_t st) {
+  *fused = fused_bwd_moments() && conv_dgrad_fuses_bn_moments(cv.s);
+  if (!*fused) {
+    RUNP(kDgrad, conv_dgrad(dy, cv.wd, g, cv.s, st));
+    return DIRB200_OK;
+  }
+  const DgradBnMoments bm{prev.y, prev.bn.scale, prev.bn.shift, net->bn_partial, lay};
+  RUNP(kDgrad, conv_dgrad(dy, cv.wd, g, cv.s, st, &bm));
   return DIRB200_OK;
 }
 
@@ -376,6 +454,11 @@ int dirb200_resnet_forward(dirb200_net* net, const float* x_nchw, const float* p
   const bool tr = training != 0;
   RUNP(kPrep, prep_weights_all(params, net->prep_descs, net->num_convs, st));
   RUNP(kPrep, input_to_s2d(x_nchw, net->n, net->h, net->w, net->x_s2d, st));
+  if (!tr && folded_eval()) {
+    RUN(forward_eval_folded(net, params, bn_running, enc_out, st));
+    net->forward_was_training = false;
+    return DIRB200_OK;
+  }
   RUN(conv_bn_forward(net, net->stem, net->x_s2d, params, bn_running, tr, st));       // stem.a == nullptr: no bn_apply
   RUNP(kPool, bn_relu_maxpool_fwd(net->stem.y, net->stem.bn.scale, net->stem.bn.shift, net->n, net->stem.s.ho,
                                   net->stem.s.wo, 64, net->pool_out, net->pool_idx, st));
@@ -412,8 +495,10 @@ static int backward_blocks(dirb200_net* net, int lo, int hi, const float* params
     // ---- block output: out = relu(bn3(y3) + identity); dz = (gA + gB) * (out > 0)
     int nblk = 0;
     const int kparts = B.has_ds ? 3 : 2;
+    // identity blocks: the reduction also stores dz (= the gradient of the shortcut path, nB) so that the apply pass
+    // reads ONE gradient tensor instead of gA, gB and the mask again
     RUNP(kBnBwdReduce, bn_bwd_reduce(gA, gB, B.c3.y, B.has_ds ? B.ds.y : nullptr, nullptr, nullptr, B.mask, B.c3.rows,
-                                     b3.c, net->bn_partial, &nblk, st, gB_h, gB_w));
+                                     b3.c, net->bn_partial, &nblk, st, gB_h, gB_w, B.has_ds ? nullptr : nB));
     if (B.has_ds) {
       BNLayer& bd = B.ds.bn;
       RUNP(kBnBwdApply, bn_bwd_coeffs(net->bn_partial, nblk, kparts, 2, B.c3.rows, b3.c, bd.mean, bd.invstd,
@@ -421,19 +506,24 @@ static int backward_blocks(dirb200_net* net, int lo, int hi, const float* params
     }
     RUNP(kBnBwdApply, bn_bwd_coeffs(net->bn_partial, nblk, kparts, 1, B.c3.rows, b3.c, b3.mean, b3.invstd,
                                     params + b3.gamma_off, grads + b3.gamma_off, grads + b3.beta_off, b3.coef, st));
-    RUNP(kBnBwdApply, bn_bwd_apply(gA, gB, B.c3.y, b3.coef, B.has_ds ? B.ds.y : nullptr,
-                                   B.has_ds ? B.ds.bn.coef : nullptr, nullptr, nullptr, B.mask, B.c3.rows, b3.c, t1,
-                                   B.has_ds ? t2 : nullptr, B.has_ds ? nullptr : nB, st, gB_h, gB_w));
+    if (B.has_ds)
+      RUNP(kBnBwdApply, bn_bwd_apply(gA, gB, B.c3.y, b3.coef, B.ds.y, B.ds.bn.coef, nullptr, nullptr, B.mask, B.c3.rows,
+                                     b3.c, t1, t2, nullptr, st, gB_h, gB_w));
+    else
+      RUNP(kBnBwdApply, bn_bwd_apply(nB, nullptr, B.c3.y, b3.coef, nullptr, nullptr, nullptr, nullptr, nullptr, B.c3.rows,
+                                     b3.c, t1, nullptr, nullptr, st));
     gB_h = gB_w = 0;
     // ---- conv3
     RUN(wgrad_step(net, B.c2.a, t1, B.c3, st));
-    RUNP(kDgrad, conv_dgrad(t1, B.c3.wd, t3, B.c3.s, st));
+    StatLayout mlay{};
+    bool mfused = false;
+    RUN(dgrad_with_bn_moments(net, t1, B.c3, B.c2, t3, &mlay, &mfused, st));
     // ---- bn2 + conv2
-    RUN(conv_bn_backward(net, B.c2, t3, params, grads, t1, st));
+    RUN(conv_bn_backward(net, B.c2, t3, params, grads, t1, st, mfused ? &mlay : nullptr));
     RUN(wgrad_step(net, B.c1.a, t1, B.c2, st));
-    RUNP(kDgrad, conv_dgrad(t1, B.c2.wd, t3, B.c2.s, st));
+    RUN(dgrad_with_bn_moments(net, t1, B.c2, B.c1, t3, &mlay, &mfused, st));
     // ---- bn1 + conv1
-    RUN(conv_bn_backward(net, B.c1, t3, params, grads, t1, st));
+    RUN(conv_bn_backward(net, B.c1, t3, params, grads, t1, st, mfused ? &mlay : nullptr));
     RUN(wgrad_step(net, B.in, t1, B.c1, st));
     RUNP(kDgrad, conv_dgrad(t1, B.c1.wd, nA, B.c1.s, st));
     // ---- downsample branch

@@ -232,6 +232,86 @@ def test_eval_mode_and_no_grad_paths():
     assert int(m.bn1.num_batches_tracked) == 1
 
 
+@pytest.mark.parametrize("n,hw", [(16, 64), (4, 224)], ids=["b16_64", "b4_224"])
+def test_eval_forward_folded_bn_layerwise_vs_oracle(n, hw):
+    """Inference path (agedb-dir/train.py:286-335: model.eval(), BatchNorm on the running statistics): every
+    conv + folded BN [+ ReLU] launch and the conv3 + BN + shortcut + ReLU tail of each block against fp32 torch ops
+    applied to the runner's OWN input of that stage (teacher-forced), then the prediction end to end against the
+    oracle network in eval mode."""
+    import torch.nn.functional as F
+    m = make_model()
+    m.train()
+    with torch.no_grad():               # two training forwards: non-trivial running statistics
+        for k in range(2):
+            m(det_param(f"xw{k}", (n, 3, hw, hw), 1.0).to(DEV) * (1.0 + 0.5 * k))
+    m.eval()
+    sd = {k: v.detach().float() for k, v in m.state_dict().items()}
+    x = det_param("xev", (n, 3, hw, hw), 1.0).to(DEV)
+    with torch.no_grad():
+        pred = m(x)
+    shape = tuple(x.shape)
+    pk = lambda b, w: m.peek(shape, b, w)
+    q = lambda t: t.to(torch.bfloat16).float()
+
+    def fold(pre):
+        sc = sd[pre + "weight"] * torch.rsqrt(sd[pre + "running_var"] + 1e-5)
+        return sc[None, :, None, None], (sd[pre + "bias"] - sd[pre + "running_mean"] * sc)[None, :, None, None]
+
+    def conv(t, w, stride, pad):        # fp32 accumulation over bf16 operands, NOT rounded (the BN is applied first)
+        return F.conv2d(q(t), q(w), stride=stride, padding=pad)
+
+    tol = 4e-3
+    def check(name, got, ref):
+        e = rel(got, ref)
+        assert e <= tol, (name, e)
+
+    with torch.no_grad():
+        sc, sh = fold("bn1.")
+        check("stem.pool", pk(-1, 6), F.max_pool2d(q(F.relu(pk(-1, 0) * sc + sh)), 3, 2, 1))
+        bi = 0
+        for li, nblocks in enumerate((3, 4, 6, 3)):
+            for b in range(nblocks):
+                stride = 2 if (b == 0 and li > 0) else 1
+                pre = f"layer{li + 1}.{b}."
+                xin = pk(-1, 6) if bi == 0 else pk(bi - 1, 6)
+                sc, sh = fold(pre + "bn1.")
+                check(pre + "conv1+bn1", pk(bi, 1), q(F.relu(conv(xin, sd[pre + "conv1.weight"], 1, 0) * sc + sh)))
+                sc, sh = fold(pre + "bn2.")
+                check(pre + "conv2+bn2", pk(bi, 3), q(F.relu(conv(pk(bi, 1), sd[pre + "conv2.weight"], stride, 1) * sc + sh)))
+                if pre + "downsample.0.weight" in sd:
+                    sc, sh = fold(pre + "downsample.1.")
+                    check(pre + "ds", pk(bi, 5), q(conv(xin, sd[pre + "downsample.0.weight"], stride, 0) * sc + sh))
+                    idn = pk(bi, 5)
+                else:
+                    idn = xin
+                sc, sh = fold(pre + "bn3.")
+                # the epilogue rounds the BN output to bf16 before the shortcut is added (staging tile), then rounds again
+                check(pre + "out", pk(bi, 6), q(F.relu(q(conv(pk(bi, 3), sd[pre + "conv3.weight"], 1, 0) * sc + sh) + idn)))
+                bi += 1
+        # end to end: torch's own eval-mode network on the same parameters and running statistics (fp32)
+        def bn(t, pre):
+            s, h = fold(pre)
+            return t * s + h
+        t = F.max_pool2d(F.relu(bn(F.conv2d(x, sd["conv1.weight"], stride=2, padding=3), "bn1.")), 3, 2, 1)
+        for li, nblocks in enumerate((3, 4, 6, 3)):
+            for b in range(nblocks):
+                stride = 2 if (b == 0 and li > 0) else 1
+                pre = f"layer{li + 1}.{b}."
+                o = F.relu(bn(F.conv2d(t, sd[pre + "conv1.weight"]), pre + "bn1."))
+                o = F.relu(bn(F.conv2d(o, sd[pre + "conv2.weight"], stride=stride, padding=1), pre + "bn2."))
+                o = bn(F.conv2d(o, sd[pre + "conv3.weight"]), pre + "bn3.")
+                if pre + "downsample.0.weight" in sd:
+                    t = bn(F.conv2d(t, sd[pre + "downsample.0.weight"], stride=stride), pre + "downsample.1.")
+                t = F.relu(o + t)
+        ref_enc = t.mean(dim=(2, 3))
+        ref_pred = ref_enc @ sd["linear.weight"].t() + sd["linear.bias"]
+        # 53 bf16-stored layers end to end (every stage is pinned to 4e-3 above): the 2048-d encoding to 4 %, the scalar
+        # prediction (a near-cancelling dot product of it) as a sanity bound only
+        enc = pk(15, 6).mean(dim=(2, 3))
+        assert rel(enc, ref_enc) < 4e-2 and cos(enc, ref_enc) > 0.999, (rel(enc, ref_enc), cos(enc, ref_enc))
+        assert (pred - ref_pred).abs().max().item() < 0.05 * ref_enc.abs().mean().item() * sd["linear.weight"].abs().sum().item() + 1e-3
+
+
 def test_train_step_fused_adam_matches_torch_adam():
     """3 steps of (forward, weighted L1, backward, Adam) with our fused optimizer vs torch.optim.Adam driven by
     the same gradients: parameters stay equal to fp32 rounding."""
