@@ -489,7 +489,10 @@ def run_ours(args):
                 "frac": conv_flops / (conv_ms / 1e3) / 1e12 / peaks["bf16_sustained"], "traffic": traffic,
                 "traffic_unit": "GB of DRAM read+write per step over these launches (ncu)",
                 "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)",
-                "algorithmic_gflop_per_step": conv_flops / 1e9, "kernel_ms_per_step": conv_ms}
+                "algorithmic_gflop_per_step": conv_flops / 1e9, "kernel_ms_per_step": conv_ms,
+                "note": "the timed launches also do BatchNorm work in their epilogues (fprop: batch statistics of its "
+                        "output; 29 of the dgrads: the BN-backward moments of the previous layer, reading y once more) -- "
+                        "that time is counted here, the FLOPs are the convolutions' only"}
     breakdown = {k: {"ms_per_step": round(ms, 4), "launch_groups": cnt} for k, (ms, cnt) in prof.items()}
 
     # ---- (4) multi-GPU correctness evidence: after the timed steps every replica must hold bit-identical parameters

@@ -75,24 +75,35 @@ struct IgemmParams {
   const __nv_bfloat16* bst_y;
   const float* bst_scale;
   const float* bst_shift;
+  // PATCH kernels (3x3 / stride 1 / pad 1, 64 -> 64 channels): a GEMM tile is `patch_r` whole image rows in PADDED
+  // coordinates (row m of the tile = (yy, xx) = divmod(m, patch_wp), patch_wp = W + 2; rows with xx >= W or yy >= patch_r
+  // are dead), its A operand ONE (patch_r + 2) x patch_wp x 64-channel input patch that stays in shared memory for all
+  // nine taps: tap (r, s) reads it displaced by r * patch_wp + s rows (dgrad, `transposed`: (2 - r) * patch_wp + 2 - s).
+  int patch_r, patch_wp, patch_h, patch_w;
+  FastDiv fd_tpi, fd_wp;       // tiles per image (H / patch_r), patch_wp
 };
 
 // CTA2: the tile is computed by a CTA pair (cta_group::2, UMMA M = 256): this CTA owns 128 of the 256 rows and stages
 // only HALF of the B tile (BN/2 rows) -- 1/3 less L2->smem operand traffic per FLOP at BN = 256.
-template <int BN, bool STAGED_EPI, bool CTA2 = false>
+template <int BN, bool STAGED_EPI, bool CTA2 = false, bool PATCH = false>
 struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBRows = CTA2 ? BN / 2 : BN;      // B rows staged by this CTA
   static constexpr int kBBytes = kBRows * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  // PATCH: a ring stage (3 of them) is one input patch (<= 32 KB incl. the rows the last taps read past its end); the nine weight
+  // k-blocks are loaded once per CTA and stay resident behind the ring
+  static constexpr int kStageBytes = PATCH ? 32768 : kABytes + kBBytes;
+  static constexpr int kBresBytes = PATCH ? 9 * BN * BK * 2 : 0;
   // smem: operand ring + (fprop/dgrad) a per-epilogue-warp staging tile of 32 rows x kEpiCols columns, so output
   // rows leave as whole 128-byte lines (the tile's BN columns are drained in BN / kEpiCols passes; the narrow
   // staging buffer buys one to two more ring stages than a full-width one); one persistent CTA per SM
   static constexpr int kEpiCols = 64;
-  static constexpr int kStages = CTA2 ? ((BN == 256) ? 6 : 8)
-                                      : (STAGED_EPI ? ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8))
-                                                    : ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8)));
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kStages = PATCH ? 3
+                                 : CTA2 ? ((BN == 256) ? 6 : 8)
+                                        : (STAGED_EPI ? ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8))
+                                                      : ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8)));
+  static constexpr int kBresOffset = kStages * kStageBytes;
+  static constexpr int kBarOffset = kBresOffset + kBresBytes;
   static constexpr int kStageRowBytes = kEpiCols * 2 + 16;      // +16 B: conflict-free 16-byte column writes
   static constexpr int kEpiWarpBytes = 32 * kStageRowBytes;
   static constexpr int kEpiOffset = kBarOffset + 256;           // after the mbarriers ((2*kStages + 6) * 8 <= 176 B)
@@ -100,8 +111,11 @@ struct Cfg {
   // of the BN statistics (kept in smem, not registers, so that the column-pass loop stays rolled: unrolled four-fold
   // the epilogue outgrew the instruction cache and the epilogue-bound 1x1 layers lost 25 %)
   static constexpr int kStatWarpBytes = (BN / kEpiCols) * 4 * 32 * 4;
-  static constexpr int kStatOffset = kEpiOffset + (STAGED_EPI ? 4 * kEpiWarpBytes : 0);
-  static constexpr int kSmemBytes = kStatOffset + (STAGED_EPI ? 4 * kStatWarpBytes : 0) + 1024;
+  // PATCH: two epilogue groups (warps 6-9 drain accumulator 0, warps 0-3 -- idle gather warps otherwise -- accumulator
+  // 1): with one input patch per tile the mainloop of a 128 x 64 tile is shorter than one group's epilogue
+  static constexpr int kEpiWarps = PATCH ? 8 : 4;
+  static constexpr int kStatOffset = kEpiOffset + (STAGED_EPI ? kEpiWarps * kEpiWarpBytes : 0);
+  static constexpr int kSmemBytes = kStatOffset + (STAGED_EPI ? kEpiWarps * kStatWarpBytes : 0) + 1024;
   static constexpr int kTmemCols = 2 * BN;  // two accumulators (epilogue of tile i overlaps the MMAs of tile i+1)
 };
 
@@ -178,11 +192,13 @@ __device__ __forceinline__ const __nv_bfloat16* tap_source(const IgemmParams& P,
 // K-major 64 x 128 boxes for fprop / dgrad, two 64 x 64 MN-major boxes for wgrad), im2col-mode maps for the 3x3 and
 // strided ones -- issued by warp 4; warps 0-3 then idle.  Without ATMA (stem, stride-2 dgrad parity classes) warps 0-3
 // gather the rows with cp.async.
-template <int BN, bool WGRAD, bool STEM, bool CTA2 = false, bool ATMA = false, bool AFFINE = false, bool BSTAT = false>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, bool WGRAD, bool STEM, bool CTA2 = false, bool ATMA = false, bool AFFINE = false, bool BSTAT = false,
+          bool PATCH = false>
+__global__ void __launch_bounds__((ATMA && !PATCH) ? kThreads - kProducerThreads : kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_a,
              const IgemmParams P) {
-  using C = Cfg<BN, !WGRAD, CTA2>;
+  using C = Cfg<BN, !WGRAD, CTA2, PATCH>;
+  static_assert(!PATCH || (ATMA && !WGRAD && !CTA2 && !AFFINE && BN == 64), "patch-resident A operand: 64-wide fprop / dgrad");
   static_assert(!CTA2 || (ATMA && !WGRAD && !STEM && BN >= 128), "CTA pairs: TMA-fed fprop / dgrad GEMMs only");
   static_assert(!ATMA || !STEM, "TMA-fed A operand: not for the stem");
   static_assert(!AFFINE || (ATMA && !WGRAD), "folded-BN epilogue: TMA-fed fprop GEMMs only");
@@ -198,8 +214,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
   const uint32_t tmem_holder = bar_base + 8u * (2 * C::kStages + 4);
+  const uint32_t bres_bar = bar_base + 8u * (2 * C::kStages + 5);    // PATCH: the resident weights have landed
+  const uint32_t bres_addr = smem_base + C::kBresOffset;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // TMA-fed kernels are launched WITHOUT the four gather warps (192 threads: TMA, MMA, 4 epilogue warps; the warp
+  // numbering below keeps the roles' indices): with 10 warps a sub-partition hosts 3 of them and the register file caps
+  // a thread at 168 registers, which the epilogues with fused statistics / BN-backward moments spilled over; with 6
+  // warps (2 per sub-partition at most) the cap is 255.  warp & 3 (the TMEM lane quarter of an epilogue warp) is
+  // unchanged by the shift.
+  // (PATCH kernels keep all ten warps: the four low ones are a second epilogue group.)
+  const int warp = static_cast<int>(threadIdx.x >> 5) + ((ATMA && !PATCH) ? kProducerThreads / 32 : 0), lane = threadIdx.x & 31;
   // CTA pair: both CTAs of a cluster walk the same sequence of pair tiles (P.m_tiles counts 256-row pair tiles)
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
   const int tile_start = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
@@ -254,6 +278,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
         mbar_init(tfull_bar(a), 1);
         mbar_init(tempty_bar(a), CTA2 ? 8 : 4);      // one arrival per epilogue warp (of both CTAs of a pair)
       }
+      if constexpr (PATCH) mbar_init(bres_bar, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -267,7 +292,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_holder));
 
-  if (warp < 4) {
+  if (warp < 4 && !PATCH) {
     if constexpr (!ATMA) {
       // ============================ A producer (4 warps) ============================
       // Address generation is hoisted out of the k-loop: per tile each thread precomputes, for its 8 rows, the
@@ -422,7 +447,30 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
     }  // !ATMA: with a TMA-fed A operand these four warps have nothing to do
   } else if (warp == kTmaWarp) {
     // ============================ B producer (TMA) ============================
-    {
+    if constexpr (PATCH) {
+      // resident weights once, then one input patch per tile: (patch_r + 2) padded rows x patch_wp x 64 channels,
+      // zero-filled outside the image by the tiled TMA load (= the conv padding)
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bres_bar, C::kBresBytes);
+#pragma unroll 1
+        for (int tp = 0; tp < 9; ++tp) tma_load_2d(bres_addr + tp * (BN * BK * 2), &tmap_b, bres_bar, tp * BK, 0);
+      }
+      __syncwarp();
+      const uint32_t patch_bytes = static_cast<uint32_t>((P.patch_r + 2) * P.patch_wp * 128);
+      uint32_t rs = 0, rph = 0;
+      for (int t = tile_first; t < tile_end; t += tile_step) {
+        uint32_t img, ty;
+        P.fd_tpi.divmod(static_cast<uint32_t>(t), img, ty);
+        const int s = static_cast<int>(rs);
+        mbar_wait(empty_bar(s), rph ^ 1u);
+        if (++rs == nstages) { rs = 0; rph ^= 1u; }
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar(s), patch_bytes);
+          tma_load_4d(a_addr(s), &tmap_a, full_bar(s), 0, -1, static_cast<int>(ty) * P.patch_r - 1, static_cast<int>(img));
+        }
+        __syncwarp();
+      }
+    } else {
       // the whole warp walks the ring (converged); one elected lane issues.  Ring position and the (tap, channel
       // block) of the k-block are counters; tap coordinates come from the host-filled tables -- no division here.
       uint32_t rs = 0, rph = 0;
@@ -520,6 +568,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
       // the whole warp walks the ring (converged: operands stay in uniform registers); one elected lane issues
       constexpr uint32_t idesc = make_idesc(CTA2 ? 2 * BM : BM, BN, WGRAD ? 1 : 0, WGRAD ? 1 : 0);
       uint32_t rs = 0, rph = 0, tcount = 0;
+      const uint32_t patch_wp8 = static_cast<uint32_t>(P.patch_wp) * 8u;   // PATCH: one padded row, in 16-byte units
       for (int t = tile_first; t < tile_end; t += tile_step, ++tcount) {
         int split, m_tile, n_tile, kb_begin, nk;
         decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
@@ -527,6 +576,44 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
         mbar_wait(tempty_bar(acc), ((tcount >> 1) & 1) ^ 1u);     // epilogue(s) have drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
+        if constexpr (PATCH) {
+          if (tcount == 0) mbar_wait(bres_bar, 0);
+          const int s = static_cast<int>(rs);
+          mbar_wait(full_bar(s), rph);
+          if (++rs == nstages) { rs = 0; rph ^= 1u; }
+          tcgen05_fence_after();
+          if (elect_one()) {
+            // tap tp: the patch displaced by patch_off[tp] rows.  The 128-byte swizzle is a function of the shared-memory
+            // ADDRESS (TMA and UMMA agree on it), so a K-major descriptor may start at any 128-byte row of the patch
+            // with base_offset 0 (tools/exp_shift.cu, profiles/r2_exp_shifted_descriptor.log).  36 MMAs in straight
+            // line: descriptor = stage base + a per-tap constant (rolled, with the offsets read from the parameter
+            // block, the issue loop itself took 2.4x the MMAs' time)
+            // one filter row per iteration of a ROLLED loop (running descriptors, immediates for the column / k offsets):
+            // fully unrolled the compiler kept all 72 descriptors in vector registers and moved them to uniform
+            // registers in front of every MMA
+            uint64_t arow = make_smem_desc(a_addr(s), 16u, 1024u) + (P.transposed ? 2u * patch_wp8 : 0u);
+            uint64_t brow = make_smem_desc(bres_addr, 16u, 1024u);
+            const uint32_t srev = P.transposed ? 16u : 0u;             // dgrad: column displacement 2 - s
+#pragma unroll 1
+            for (int fr = 0; fr < 3; ++fr) {
+#pragma unroll
+              for (int fs = 0; fs < 3; ++fs) {
+                const uint64_t ad = arow + static_cast<uint64_t>(P.transposed ? srev - fs * 8u : fs * 8u);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_bf16(tmem_d, ad + static_cast<uint64_t>(k * 2),
+                            brow + static_cast<uint64_t>(fs * ((BN * BK * 2) >> 4) + k * 2), idesc,
+                            (fr > 0 || fs > 0 || k > 0) ? 1u : 0u);
+              }
+              arow = P.transposed ? arow - patch_wp8 : arow + patch_wp8;
+              brow += 3u * ((BN * BK * 2) >> 4);
+            }
+            umma_commit(empty_bar(s));
+            umma_commit(tfull_bar(acc));
+          }
+          __syncwarp();
+          continue;
+        }
         for (int it = 0; it < nk; ++it) {
           const int s = static_cast<int>(rs);
           mbar_wait(full_bar(s), rph);
@@ -561,25 +648,52 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
     }
     __syncwarp();
   } else {
-    // ============================== epilogue (4 warps) ==============================
+    // ============================== epilogue (4 warps; PATCH: two groups of 4) ==============================
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32)
     const int row = quarter * 32 + lane;
+    const int egroup = (PATCH && warp < 4) ? 1 : 0;   // PATCH: group g drains accumulator g (every second tile)
+    const int ewarp = egroup * 4 + quarter;           // index of this warp's staging tile / statistics slots
     uint32_t tcount = 0;
     // BN statistics of this warp's rows (fprop with stat_out): running column sums in this warp's smem slots
     float* stat_sm = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + C::kStatOffset) +
-                     (WGRAD ? 0 : quarter * (C::kStatWarpBytes / 4)) + lane;
+                     (WGRAD ? 0 : ewarp * (C::kStatWarpBytes / 4)) + lane;
     if constexpr (!WGRAD) {
       if (P.stat_out != nullptr)
         for (int i = 0; i < (BN / C::kEpiCols) * 4; ++i) stat_sm[i * 32] = 0.f;
+    }
+    // PATCH: tile row m = (yy, xx) in padded coordinates -> pixel offset yy * W + xx inside the tile's image rows (-1: a
+    // dead row); the same for every tile, so decoded once: for this lane's own row and for the 8 rows it stores
+    int patch_rel_own = -1, patch_rel8[8];
+    if constexpr (PATCH) {
+      auto rel = [&](int m) -> int {
+        uint32_t yy, xx;
+        P.fd_wp.divmod(static_cast<uint32_t>(m), yy, xx);
+        return (static_cast<int>(yy) < P.patch_r && static_cast<int>(xx) < P.patch_w) ? static_cast<int>(yy) * P.patch_w + static_cast<int>(xx) : -1;
+      };
+      patch_rel_own = rel(quarter * 32 + lane);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) patch_rel8[i] = rel(quarter * 32 + i * 4 + (lane >> 3));
     }
     for (int t = tile_first; t < tile_end; t += tile_step, ++tcount) {
       int split, m_tile, n_tile, kb_begin, nk;
       decode_tile(t, split, m_tile, n_tile, kb_begin, nk);
       const int acc = tcount & 1;
+      if constexpr (PATCH) {
+        if (acc != egroup) continue;               // the other group's tile
+      }
+      int patch_base = 0;                          // PATCH: first output row of the tile's image rows
+      if constexpr (PATCH) {                       // (output rows fit 31 bits: n * h * w < 2^31 is checked on the host)
+        uint32_t img, ty;
+        P.fd_tpi.divmod(static_cast<uint32_t>(t), img, ty);
+        patch_base = static_cast<int>((img * P.patch_h + ty * P.patch_r) * P.patch_w);
+      }
+      int my_orow = 0;                             // PATCH: output row of this lane's own tile row
+      if constexpr (PATCH) my_orow = patch_rel_own >= 0 ? patch_base + patch_rel_own : -1;
       if constexpr (BSTAT) {
         // the y rows this warp will need in its statistics passes: pulled into L2 while the tile's MMAs still run
-        const long long pr = static_cast<long long>(m_tile) * BM + quarter * 32 + lane;
-        if (pr < P.pixels) {
+        long long pr = static_cast<long long>(m_tile) * BM + quarter * 32 + lane;
+        if constexpr (PATCH) pr = my_orow;
+        if (pr >= 0 && pr < P.pixels) {
           const __nv_bfloat16* yl = P.bst_y + pr * P.ldc + n_tile * BN;
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(yl + j * 64));
@@ -592,7 +706,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
       if constexpr (!WGRAD) {
         // TMEM -> registers -> bf16 -> this warp's smem staging tile (32 rows x kEpiCols), then the rows go out as
         // coalesced 16-byte-per-lane stores (one full 128-byte line per row and pass)
-        const uint32_t stage_base = smem_base + C::kEpiOffset + quarter * C::kEpiWarpBytes;
+        const uint32_t stage_base = smem_base + C::kEpiOffset + ewarp * C::kEpiWarpBytes;
         const uint32_t my_row = stage_base + lane * C::kStageRowBytes;
         constexpr int kLanesPerRow = C::kEpiCols * 2 / 16;      // 8 lanes x 16 B = one 128-byte line
         constexpr int kRowsPerIter = 32 / kLanesPerRow;         // 4 rows per store iteration
@@ -600,15 +714,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
         const int sub = lane / kLanesPerRow, col16 = lane % kLanesPerRow;
         const long long p0 = static_cast<long long>(m_tile) * BM + quarter * 32;
         // output row of each of the 8 tile rows this lane stores (-1: out of range), resolved once per tile
-        long long orow8[kIters];
+        // (32-bit: the host checks that the output has fewer than 2^31 rows)
+        int orow8[kIters];
 #pragma unroll
         for (int i = 0; i < kIters; ++i) {
           const long long p = p0 + i * kRowsPerIter + sub;
-          long long orow = (p < P.pixels && nk > 0) ? p : -1;
+          int orow = (p < P.pixels && nk > 0) ? static_cast<int>(p) : -1;
+          if constexpr (PATCH) orow = patch_rel8[i] >= 0 ? patch_base + patch_rel8[i] : -1;
           if (orow >= 0 && P.cls_on) {                          // class pixel -> row of the full image
             const uint32_t pk = pack_pixel(p, P);
             const int n = (pk >> 18) & 0x1FFF, yy = (pk >> 9) & 0x1FF, xx = pk & 0x1FF;
-            orow = (static_cast<long long>(n) * P.full_h + 2 * yy + P.cls_py) * P.full_w + 2 * xx + P.cls_px;
+            orow = (n * P.full_h + 2 * yy + P.cls_py) * P.full_w + 2 * xx + P.cls_px;
           }
           orow8[i] = orow;
         }
@@ -641,6 +757,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
               for (int e = 0; e < 4; ++e) {
                 __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[8 * jj + 2 * e]), __uint_as_float(v[8 * jj + 2 * e + 1]));
                 pk[e] = *reinterpret_cast<uint32_t*>(&h);
+                if constexpr (PATCH) {
+                  if (my_orow < 0) pk[e] = 0u;      // dead tile row (padding column / past the tile's image rows): keep it out of the sums
+                }
               }
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + c * 64 + jj * 16), "r"(pk[0]),
                            "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
@@ -656,8 +775,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
             const __nv_bfloat16* yp = P.bst_y + n0 + cb * C::kEpiCols + 2 * lane;
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
-              const long long p = p0 + r;
-              yw[r] = p < P.pixels ? __ldg(reinterpret_cast<const unsigned int*>(yp + p * P.ldc)) : 0u;
+              if constexpr (PATCH) {
+                const int p = __shfl_sync(0xffffffffu, my_orow, r);
+                yw[r] = p >= 0 ? __ldg(reinterpret_cast<const unsigned int*>(yp + static_cast<long long>(p) * P.ldc)) : 0u;
+              } else {
+                const long long p = p0 + r;
+                yw[r] = p < P.pixels ? __ldg(reinterpret_cast<const unsigned int*>(yp + p * P.ldc)) : 0u;
+              }
             }
           }
           __nv_bfloat16* out_cols = reinterpret_cast<__nv_bfloat16*>(P.out) + n0 + cb * C::kEpiCols + col16 * 8;
@@ -668,7 +792,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
               const __nv_bfloat16* res_cols = P.epi_res + n0 + cb * C::kEpiCols + col16 * 8;
 #pragma unroll
               for (int i = 0; i < kIters; ++i)
-                resv[i] = orow8[i] >= 0 ? *reinterpret_cast<const uint4*>(res_cols + orow8[i] * P.ldc) : make_uint4(0, 0, 0, 0);
+                resv[i] = orow8[i] >= 0 ? *reinterpret_cast<const uint4*>(res_cols + static_cast<long long>(orow8[i]) * P.ldc)
+                                        : make_uint4(0, 0, 0, 0);
             }
           }
 #pragma unroll
@@ -693,7 +818,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
                   val = make_uint4(o[0], o[1], o[2], o[3]);
                 }
               }
-              *reinterpret_cast<uint4*>(out_cols + orow8[i] * P.ldc) = val;
+              *reinterpret_cast<uint4*>(out_cols + static_cast<long long>(orow8[i]) * P.ldc) = val;
             }
           }
           if constexpr (BSTAT) {
@@ -780,16 +905,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
         // columns of this CTA's n_tile.  Every CTA of the launch owns >= 1 tile (grid <= tiles), so every row of
         // its n_tile's column range is written: the consumer (bn_finalize) reads exactly those, no zero-fill needed.
         __syncwarp();
-        asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
+        if constexpr (PATCH) asm volatile("bar.sync 1, 256;" ::: "memory");   // both epilogue groups
+        else asm volatile("bar.sync 1, 128;" ::: "memory");                  // the four epilogue warps
         const float* all = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + C::kStatOffset);
         constexpr int kWarpFloats = C::kStatWarpBytes / 4;
         float* dst = P.stat_out + static_cast<size_t>(blockIdx.x) * 2 * P.ldc + fixed_n * BN;
-        for (int o = quarter * 32 + lane; o < 2 * BN; o += 128) {
-          const int k = o / BN, col = o - k * BN;
-          const int cb = col / C::kEpiCols, ln = (col % C::kEpiCols) >> 1, e = col & 1;
-          const int idx = (cb * 4 + k * 2 + e) * 32 + ln;
-          const float v = (all[idx] + all[kWarpFloats + idx]) + (all[2 * kWarpFloats + idx] + all[3 * kWarpFloats + idx]);
-          dst[static_cast<size_t>(k) * P.ldc + col] = v;
+        if (egroup == 0) {
+          for (int o = quarter * 32 + lane; o < 2 * BN; o += 128) {
+            const int k = o / BN, col = o - k * BN;
+            const int cb = col / C::kEpiCols, ln = (col % C::kEpiCols) >> 1, e = col & 1;
+            const int idx = (cb * 4 + k * 2 + e) * 32 + ln;
+            float v = (all[idx] + all[kWarpFloats + idx]) + (all[2 * kWarpFloats + idx] + all[3 * kWarpFloats + idx]);
+            if constexpr (PATCH)
+              v += (all[4 * kWarpFloats + idx] + all[5 * kWarpFloats + idx]) + (all[6 * kWarpFloats + idx] + all[7 * kWarpFloats + idx]);
+            dst[static_cast<size_t>(k) * P.ldc + col] = v;
+          }
         }
       }
     }
@@ -803,6 +933,144 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__
     tcgen05_fence_after();
     if constexpr (CTA2) tmem_dealloc_cta2(tmem_base, C::kTmemCols);
     else tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+
+// ---- weight gradient of the 3x3 / stride 1 / pad 1, 64 -> 64 convolutions in the patch-resident form -----------------
+// dW[(r, s, ci), co] = sum over pixels p of X[p + (r - 1, s - 1), ci] * dY[p, co].  The split-K wgrad above re-gathers X
+// once per filter tap (1.44 GB through the L2->SM path at batch 256, tensor pipe 22 % -- profiles/r2_igemm_full.md).
+// Here a k-slab is `patch_r` whole image rows in padded coordinates (row q = (yy, xx) = divmod(q, W + 2)):
+//   * the X patch ((patch_r + 2) x (W + 2) x 64 ch, zero-filled borders) is loaded ONCE and feeds all nine taps: tap
+//     (r, s) is an MN-major descriptor starting r * (W + 2) + s rows into it; two taps form the M = 128 of one MMA, their
+//     64-channel chunks `LBO` = the distance between their start rows apart;
+//   * dY arrives as a (W + 2)-wide box (the two extra columns out of range = zeros) so that its row q matches patch row
+//     q; rows [patch_r * (W + 2), 128) of its slot are zeroed once and never written again;
+//   * all of a CTA's slabs accumulate into the SAME five TMEM accumulators (taps (0,1) (2,3) (4,5) (6,7) (8,-)), which are
+//     written out once at the end as this CTA's split-K partial [Cout][9 * 64] (split index = blockIdx.x).
+// Warps: 0 = TMA, 1 = MMA (+ TMEM owner), 2-5 = final drain (TMEM lane quarter = warp & 3).
+constexpr int kWgpThreads = 192;
+constexpr int kWgpStages = 4, kWgpASlot = 32768, kWgpBSlot = 16384, kWgpStage = kWgpASlot + kWgpBSlot;
+constexpr int kWgpSmemBytes = kWgpStages * kWgpStage + 256 + 1024;
+
+__global__ void __launch_bounds__(kWgpThreads, 1)
+wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                   const IgemmParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kWgpStages * kWgpStage;
+  auto a_addr = [&](int s) { return smem_base + s * kWgpStage; };
+  auto b_addr = [&](int s) { return smem_base + s * kWgpStage + kWgpASlot; };
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kWgpStages + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * kWgpStages), tmem_holder = bar_base + 8u * (2 * kWgpStages + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // the whole ring is zeroed once (generic proxy; made visible to the async proxy before any TMA / MMA touches it): the
+  // TMA boxes cover only the first (patch_r + 2) * wp rows of an X slot and patch_r * wp rows of a dY slot, the MMAs read
+  // 128 K rows of both -- the dY rows past the slab must be zeros, and the X rows they meet must not be stale NaNs
+  for (int i = threadIdx.x; i < kWgpStages * kWgpStage / 16; i += kWgpThreads)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem_base + i * 16), "r"(0u) : "memory");
+  fence_proxy_async();
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kWgpStages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      mbar_init(done_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_holder, 512);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_holder));
+
+  const int tile_first = blockIdx.x, tile_step = gridDim.x, tile_end = P.m_tiles;
+  if (warp == 0) {
+    const uint32_t bytes = static_cast<uint32_t>(((P.patch_r + 2) + P.patch_r) * P.patch_wp * 128);
+    uint32_t rs = 0, rph = 0;
+    for (int t = tile_first; t < tile_end; t += tile_step) {
+      uint32_t img, ty;
+      P.fd_tpi.divmod(static_cast<uint32_t>(t), img, ty);
+      const int s = static_cast<int>(rs);
+      mbar_wait(empty_bar(s), rph ^ 1u);
+      if (++rs == kWgpStages) { rs = 0; rph ^= 1u; }
+      if (elect_one()) {
+        const int y0 = static_cast<int>(ty) * P.patch_r;
+        mbar_arrive_expect_tx(full_bar(s), bytes);
+        tma_load_4d(a_addr(s), &tmap_x, full_bar(s), 0, -1, y0 - 1, static_cast<int>(img));
+        tma_load_4d(b_addr(s), &tmap_dy, full_bar(s), 0, 0, y0, static_cast<int>(img));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(128, 64, 1, 1);
+    const uint32_t wp8 = static_cast<uint32_t>(P.patch_wp) * 8u;      // one padded row in 16-byte units
+    uint32_t rs = 0, rph = 0, first = 1;
+    for (int t = tile_first; t < tile_end; t += tile_step) {
+      const int s = static_cast<int>(rs);
+      mbar_wait(full_bar(s), rph);
+      if (++rs == kWgpStages) { rs = 0; rph ^= 1u; }
+      tcgen05_fence_after();
+      if (elect_one()) {
+        // MN-major descriptors: k rows 128 B apart, 8-row atoms 1024 B apart (SBO); the second 64-channel chunk of A
+        // (= the pair's second tap) LBO apart.  Bits [16,30) hold LBO >> 4.
+        const uint64_t abase = make_smem_desc(a_addr(s), 0u, 1024u), bbase = make_smem_desc(b_addr(s), 8192u, 1024u);
+        const uint64_t lbo1 = static_cast<uint64_t>(8u) << 16;                    // next tap = next patch row
+        const uint64_t lbo_wrap = static_cast<uint64_t>(wp8 - 16u) << 16;         // tap (r, 2) -> (r + 1, 0)
+        uint64_t a0 = abase + lbo1, a1 = abase + 16u + lbo_wrap, a2 = abase + (wp8 + 8u) + lbo1,
+                 a3 = abase + 2u * wp8 + lbo1, a4 = abase + (2u * wp8 + 16u) + lbo1, b = bbase;
+#pragma unroll 1
+        for (int ks = 0; ks < 8; ++ks) {                      // 8 x 16 padded positions = the slab's K = 128
+          const uint32_t accum = (first && ks == 0) ? 0u : 1u;
+          umma_bf16(tmem_base + 0 * 64, a0, b, idesc, accum);
+          umma_bf16(tmem_base + 1 * 64, a1, b, idesc, accum);
+          umma_bf16(tmem_base + 2 * 64, a2, b, idesc, accum);
+          umma_bf16(tmem_base + 3 * 64, a3, b, idesc, accum);
+          umma_bf16(tmem_base + 4 * 64, a4, b, idesc, accum);
+          a0 += 128u; a1 += 128u; a2 += 128u; a3 += 128u; a4 += 128u; b += 128u;      // 16 rows x 128 B, in 16-byte units
+        }
+        umma_commit(empty_bar(s));
+      }
+      first = 0;
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(done_bar);
+    __syncwarp();
+  } else {
+    // final drain: accumulator j holds rows (tap 2j, ci) in lanes 0-63 and (tap 2j + 1, ci) in lanes 64-127
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tcgen05_fence_after();
+    constexpr int ktot = 9 * 64;
+    float* out = reinterpret_cast<float*>(P.out) + static_cast<size_t>(blockIdx.x) * P.ldc * ktot;
+#pragma unroll 1
+    for (int j = 0; j < 5; ++j) {
+      const int tap = 2 * j + (row >> 6);
+      const int krow = tap * 64 + (row & 63);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + j * 64 + c * 32 + (static_cast<uint32_t>(quarter * 32) << 16), v);
+        tmem_ld_wait();
+        if (tap < 9) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) out[static_cast<size_t>(c * 32 + jj) * ktot + krow] = __uint_as_float(v[jj]);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -899,6 +1167,8 @@ static IgemmParams finish_params(const IgemmParams& P) {
   Q.fd_kw = make_fastdiv(static_cast<uint32_t>(Q.kw > 0 ? Q.kw : 1));
   Q.fd_ntiles = make_fastdiv(static_cast<uint32_t>(Q.n_tiles > 0 ? Q.n_tiles : 1));
   Q.fd_persplit = make_fastdiv(static_cast<uint32_t>(Q.m_tiles * Q.n_tiles > 0 ? Q.m_tiles * Q.n_tiles : 1));
+  Q.fd_tpi = make_fastdiv(static_cast<uint32_t>(Q.patch_r > 0 ? Q.patch_h / Q.patch_r : 1));
+  Q.fd_wp = make_fastdiv(static_cast<uint32_t>(Q.patch_wp > 0 ? Q.patch_wp : 1));
   const int nt = Q.ntaps_c < 9 ? Q.ntaps_c : 9;
   for (int i = 0; i < 9; ++i) {
     Q.tap_eoff[i] = 0;
@@ -921,19 +1191,19 @@ static IgemmParams finish_params(const IgemmParams& P) {
   return Q;
 }
 
-template <int BN, bool WGRAD, bool STEM, bool ATMA = false, bool AFFINE = false, bool BSTAT = false>
+template <int BN, bool WGRAD, bool STEM, bool ATMA = false, bool AFFINE = false, bool BSTAT = false, bool PATCH = false>
 static int launch_igemm_impl(const CUtensorMap& tm, const CUtensorMap& tma, const IgemmParams& Qin, cudaStream_t st) {
-  using C = Cfg<BN, !WGRAD>;
+  using C = Cfg<BN, !WGRAD, false, PATCH>;
   const IgemmParams Q = finish_params(Qin);
   static bool configured = false;
   if (!configured) {
-    DIRB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, WGRAD, STEM, false, ATMA, AFFINE, BSTAT>,
+    DIRB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, WGRAD, STEM, false, ATMA, AFFINE, BSTAT, PATCH>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
   const int grid = Q.num_tiles < num_sms() ? Q.num_tiles : num_sms();
   t_last_layout = StatLayout{grid, Q.n_tiles, BN, 1};
-  igemm_kernel<BN, WGRAD, STEM, false, ATMA, AFFINE, BSTAT><<<grid, kThreads, C::kSmemBytes, st>>>(tm, tma, Q);
+  igemm_kernel<BN, WGRAD, STEM, false, ATMA, AFFINE, BSTAT, PATCH><<<grid, (ATMA && !PATCH) ? kThreads - kProducerThreads : kThreads, C::kSmemBytes, st>>>(tm, tma, Q);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }
@@ -951,7 +1221,7 @@ static int launch_igemm_cta2(const CUtensorMap& tm, const CUtensorMap& tma, cons
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(num_sms() & ~1, 1, 1);
-  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.blockDim = dim3(kThreads - kProducerThreads, 1, 1);     // TMA-fed: no gather warps
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1038,6 +1308,8 @@ static int check_shape(const ConvShape& s, bool stem, const char* who) {
   DIRB_CHECK_ARG(s.n > 0 && s.h > 0 && s.w > 0 && s.kh > 0 && s.kw > 0 && s.stride > 0 && s.pad >= 0,
                  "%s: bad conv shape", who);
   DIRB_CHECK_ARG(s.cout % 64 == 0, "%s: Cout must be a multiple of 64 (got %d)", who, s.cout);
+  DIRB_CHECK_ARG(static_cast<long long>(s.n) * s.h * s.w < (1LL << 31) && static_cast<long long>(s.n) * s.ho * s.wo < (1LL << 31),
+                 "%s: more than 2^31 pixels", who);
   if (stem)
     DIRB_CHECK_ARG(s.cin == 16 && s.kh == 4 && s.kw == 4 && s.stride == 1, "%s: stem expects the 4x4x16 s2d form", who);
   else
@@ -1081,6 +1353,71 @@ static int launch_cta2(const __nv_bfloat16* wmat, int ktot, int n_dim, const Ige
 }
 static bool want_pairs(int bn, int num_kblocks) { return pairs_enabled() && bn == 256 && num_kblocks >= 4; }
 
+// Patch-resident form for the 3x3 / stride 1 / pad 1, 64 -> 64 convolutions (layer1's conv2: fprop and dgrad).  With a
+// 128 x 64 tile the im2col form pulls every input pixel nine times plus the weight tile per k-block through the L2->SM
+// path (1.39 GB per launch at batch 256, 11.3 TB/s = the delivery limit, tensor pipe 25 % -- profiles/r2_igemm_full.md);
+// here a tile is `r` whole image rows in padded coordinates, its input patch is loaded ONCE by a tiled TMA box
+// (zero-filled borders) and the nine taps are UMMA descriptors displaced inside that patch; the weights stay resident.
+// DIRB200_PATCH=0 disables.
+static bool patch_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DIRB200_PATCH");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on && im2col_enabled();
+}
+// rows per tile: the largest divisor r of h with r * (w + 2) <= 128 (0: shape not supported)
+static int patch_rows(int h, int w, int channels, int kh, int kw, int stride, int pad, int n_dim) {
+  if (!patch_enabled() || kh != 3 || kw != 3 || stride != 1 || pad != 1 || channels != 64 || n_dim != 64) return 0;
+  const int wp = w + 2;
+  if (wp > 128 || (2 * wp + 2 + 128) * 128 > 32768) return 0;
+  for (int r = 128 / wp; r >= 1; --r)
+    if (h % r == 0 && r + 2 <= 256) return r;
+  return 0;
+}
+// tiled 4-D map of an NHWC bf16 tensor with 64 channels: boxes of (w + 2) columns x `box_rows` rows x 64 channels
+// (coordinates may start at -1: the out-of-range border arrives as zeros)
+static int make_tmap_patch(CUtensorMap* tm, const __nv_bfloat16* src, int n, int h, int w, int box_rows) {
+  typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  Fn fn = reinterpret_cast<Fn>(encode_fn());
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return DIRB200_ERR_CUDA;
+  }
+  cuuint64_t dims[4] = {64, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {128, (cuuint64_t)w * 128, (cuuint64_t)h * w * 128};
+  cuuint32_t box[4] = {64, (cuuint32_t)(w + 2), (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(src), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (patch) failed (%d) w=%d h=%d n=%d rows=%d", (int)cr, w, h, n, box_rows);
+    return DIRB200_ERR_CUDA;
+  }
+  return DIRB200_OK;
+}
+
+// src: the tensor the taps slide over ([n, h, w, 64]); wmat: [64][9 * 64] K-major; flipped: dgrad (tap (r, s) reads the
+// patch displaced by (2 - r, 2 - s))
+static int launch_patch(const __nv_bfloat16* src, const __nv_bfloat16* wmat, IgemmParams P, int n, int h, int w, int r,
+                        bool flipped, cudaStream_t st) {
+  CUtensorMap ta, tb;
+  if (int rc = make_tmap_patch(&ta, src, n, h, w, r + 2)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tb, wmat, 9 * 64, 64, 9 * 64 * 2, 64)) return rc;
+  P.patch_r = r; P.patch_wp = w + 2; P.patch_h = h; P.patch_w = w;
+  P.transposed = flipped ? 1 : 0;
+  P.a_mode = 3;
+  P.n_tiles = 1;
+  P.m_tiles = n * (h / r);
+  P.num_tiles = P.m_tiles;
+  P.num_kblocks = 9;
+  if (P.bst_y != nullptr) return launch_igemm_impl<64, false, false, true, false, true, true>(tb, ta, P, st);
+  return launch_igemm_impl<64, false, false, true, false, false, true>(tb, ta, P, st);
+}
+
 // Y[n,ho,wo,cout] = conv(X[n,h,w,cin], W[cout][kh][kw][cin])
 static int conv_fprop_impl(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, const ConvShape& s, bool stem,
                            cudaStream_t st, float* stat_partial, const ConvEpilogue* epi);
@@ -1115,6 +1452,10 @@ static int conv_fprop_impl(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_
   P.stat_out = stat_partial;
   if (epi) {
     P.epi_scale = epi->scale; P.epi_shift = epi->shift; P.epi_res = epi->residual; P.epi_relu = epi->relu ? 1 : 0;
+  }
+  if (!stem && !epi) {
+    if (const int pr = patch_rows(s.h, s.w, s.cin, s.kh, s.kw, s.stride, s.pad, s.cout))
+      return launch_patch(x, w, P, s.n, s.h, s.w, pr, false, st);
   }
   const int m_tiles = static_cast<int>((P.pixels + BM - 1) / BM);
   const int bn = pick_bn(s.cout, m_tiles, !is_plain_gemm(s, stem));
@@ -1167,6 +1508,11 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
     P.ntaps_c = s.kh * s.kw;
     for (int i = 0; i < 9; ++i) P.tap_list[i] = i;
     P.num_kblocks = ktot / 64;
+    if (const int pr = patch_rows(s.ho, s.wo, s.cout, s.kh, s.kw, s.stride, s.pad, s.cin)) {
+      const int rc = launch_patch(dy, wt, P, s.n, s.ho, s.wo, pr, true, st);
+      if (bnm && bnm->layout) *bnm->layout = t_last_layout;
+      return rc;
+    }
     const int m_tiles = static_cast<int>((P.pixels + BM - 1) / BM);
     const int bn = pick_bn(s.cin, m_tiles, !is_plain_gemm(s, false));
     P.n_tiles = s.cin / bn;
@@ -1236,6 +1582,10 @@ static int wgrad_bn(const ConvShape& s) { return s.cout % 256 == 0 ? 256 : (s.co
 // costs about waves x (k-blocks per split + 6).  Picking the minimiser avoids the "one item too many" third wave the
 // old ceil(2 * sms / tiles) rule produced for the 3x3 layers (e.g. 9 tiles x 33 splits = 297 items on 148 SMs).
 int conv_wgrad_splits(const ConvShape& s) {
+  if (const int pr = patch_rows(s.h, s.w, s.cin, s.kh, s.kw, s.stride, s.pad, s.cout)) {
+    const int slabs = s.n * (s.h / pr);             // patch form: one partial per CTA
+    return slabs < num_sms() ? slabs : num_sms();
+  }
   const long long pixels = static_cast<long long>(s.n) * s.ho * s.wo;
   const int kblocks = static_cast<int>((pixels + 63) / 64);
   const int chunks = s.kh * s.kw * s.cin / 64;
@@ -1281,6 +1631,25 @@ int conv_wgrad_partials(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
   const int splits = conv_wgrad_splits(s);
   P.kblocks_per_split = (P.num_kblocks + splits - 1) / splits;
   P.ldc = s.cout; P.out = partial;
+  if (!stem) {
+    if (const int pr = patch_rows(s.h, s.w, s.cin, s.kh, s.kw, s.stride, s.pad, s.cout)) {
+      CUtensorMap tx, tdy;
+      if (int rc = make_tmap_patch(&tx, x, s.n, s.h, s.w, pr + 2)) return rc;
+      if (int rc = make_tmap_patch(&tdy, dy, s.n, s.ho, s.wo, pr)) return rc;
+      P.patch_r = pr; P.patch_wp = s.w + 2; P.patch_h = s.h; P.patch_w = s.w;
+      P.m_tiles = s.n * (s.h / pr);
+      const IgemmParams Q = finish_params(P);
+      static bool configured = false;
+      if (!configured) {
+        DIRB_CUDA(cudaFuncSetAttribute(wgrad_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgpSmemBytes));
+        configured = true;
+      }
+      *splits_out = splits;
+      wgrad_patch_kernel<<<splits, kWgpThreads, kWgpSmemBytes, st>>>(tx, tdy, Q);
+      DIRB_LAUNCHED();
+      return DIRB200_OK;
+    }
+  }
   const int bn = wgrad_bn(s);
   P.n_tiles = s.cout / bn;
   const int m_tiles = (P.total_chunks + 1) / 2;

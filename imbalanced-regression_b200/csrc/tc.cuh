@@ -91,6 +91,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tma
       : "memory");
 }
 
+// tiled-mode 4-D load (NHWC tensor as C, W, H, N): a box starting at (c, w, h, n); coordinates may be negative /
+// past the extent, out-of-range elements arrive as zeros (the conv padding)
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c, int w, int h,
+                                            int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+}
+
 // im2col-mode TMA load of an NHWC tensor (rank 4: C, W, H, N): `pixelsPerColumn` output positions starting at the
 // base pixel (w, h, n) -- walking the descriptor's bounding box with its traversal strides -- each displaced by the
 // filter-tap offset (off_w, off_h); `channelsPerPixel` channels from c; out-of-image elements arrive as zeros.

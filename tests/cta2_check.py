@@ -4,6 +4,7 @@ by pytest; tests/test_gpu_conv_variants.py runs the parity half in subprocesses)
     python tests/cta2_check.py parity                    # defaults: CTA pairs (256-wide, >= 4 k-blocks) + tiled / im2col TMA
     DIRB200_CTA2=0   python tests/cta2_check.py parity   # single-CTA tiles only
     DIRB200_IM2COL=0 python tests/cta2_check.py parity   # cp.async gather for the 3x3 / strided convs
+    DIRB200_PATCH=0  python tests/cta2_check.py parity   # im2col TMA instead of the patch-resident 64 -> 64 3x3 form
     DIRB200_ATMA=0   python tests/cta2_check.py parity   # cp.async gather for every conv
     <switches> python tests/cta2_check.py time [substr]  # per-layer fprop/dgrad/wgrad times, batch-256 ResNet-50 shapes
                                                           # (also written to gpurun_out/conv_layers_<tag>.json)
@@ -38,6 +39,8 @@ PARITY = [
     (64, 14, 14, 256, 1024, 1, 1, 0),   # several tiles per cluster, accumulator double buffering
     (75, 14, 14, 256, 256, 3, 1, 1),    # 115 m-tiles of a 3x3: pairs + im2col TMA, odd tile count
     (64, 28, 28, 512, 256, 1, 1, 0),    # pairs + tiled TMA, 8 k-blocks
+    (4, 56, 56, 64, 64, 3, 1, 1),       # layer1 3x3: patch-resident form by default (DIRB200_PATCH=0: im2col TMA)
+    (3, 12, 20, 64, 64, 3, 1, 1),
 ]
 
 # (name, n, h, w, cin, cout, k, stride, pad, count): every distinct non-stem conv of the batch-256 ResNet-50 step

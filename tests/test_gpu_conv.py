@@ -87,6 +87,12 @@ def run_conv(n, h, w, cin, cout, k, stride, pad, seed=0, check_dgrad=True, devic
     (75, 14, 14, 256, 256, 3, 1, 1),   # CTA pairs + im2col TMA: 115 m-tiles (odd: last pair has an empty peer half)
     (64, 28, 28, 512, 256, 1, 1, 0),   # CTA pairs + tiled TMA: 392 m-tiles, 8 k-blocks
     (64, 14, 14, 256, 1024, 1, 1, 0),  # CTA pairs, 4 n-tiles per cluster walk, accumulator double buffering
+    # patch-resident 3x3 form (64 -> 64, stride 1): tiles of r whole padded image rows, nine displaced descriptors
+    (3, 12, 20, 64, 64, 3, 1, 1),      # r = 4 rows of 22 padded columns (88 of 128 tile rows live), non-square
+    (5, 7, 9, 64, 64, 3, 1, 1),        # r = 7: one tile per image
+    (4, 56, 56, 64, 64, 3, 1, 1),      # the layer1 shape: r = 2 rows of 58, 112 tiles on 112 CTAs
+    (1, 6, 60, 64, 64, 3, 1, 1),       # widest supported row (62 padded columns): the last tap reads to the slot's end
+    (2, 5, 100, 64, 64, 3, 1, 1),      # too wide for a patch slot: im2col form
 ])
 def test_conv_forms(cfg):
     run_conv(*cfg)
