@@ -410,11 +410,16 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- this arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    json_fd = 1
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL's log (whatever level the caller asked for) goes to stderr: stdout stays the one JSON line
         os.environ.setdefault("NCCL_DEBUG", "WARN")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout must stay the one JSON line, but NCCL writes its banner ("NCCL version ...") and, at higher
+        # NCCL_DEBUG levels, its whole log to file descriptor 1: keep a private copy of the real stdout for the JSON
+        # line and point fd 1 at stderr for everything else this process (and the libraries in it) prints
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=device)
     import _lib
     peaks = measured_peaks()
@@ -536,7 +541,8 @@ def run_ours(args):
                "model_flops_utilisation_note": "24.29 GFLOP/img fwd+bwd vs the nominal dense bf16 peak (2250 TFLOP/s)",
                "step_frac_of_measured_bf16_peak": FWDBWD_GFLOP_PER_IMG * args.batch / ms_per_step / peaks["bf16_sustained"],
                "replica_check": replica_check}
-        print(json.dumps(out), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -585,55 +585,92 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, i
 // The activation is never written: the backward re-derives the ReLU mask from (y, scale, shift) and routes gradients by
 // the stored argmax, so nothing downstream reads it (saves 411 MB written + read at batch 256).  Values are rounded to
 // bf16 before they are compared, i.e. exactly what pooling the stored activation gave; idx = r*3+s of the first maximum.
+// A thread owns a 2x2 block of OUTPUT pixels x 8 channels: the 5x5 input patch they cover is loaded once (6.25 loads and
+// BN+ReLU evaluations per output instead of 9) row by row -- five 16-byte loads in flight, then the running maxima of
+// the (up to) two output rows x two output columns that contain the row are updated in (r, s) order, which keeps the
+// first-maximum tie rule.
 __global__ void __launch_bounds__(256)
 bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                            const float* __restrict__ shift, int n, int h, int w, int c,
                            __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx) {
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1, cg = c / 8;
-  const int64_t total = (int64_t)n * ho * wo * cg;
+  const int hb = (ho + 1) / 2, wb = (wo + 1) / 2;
+  const int64_t total = (int64_t)n * hb * wb * cg;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(i % cg);
     int64_t t = i / cg;
-    const int xo = (int)(t % wo); t /= wo;
-    const int yo = (int)(t % ho);
-    const int b = (int)(t / ho);
+    const int xb = (int)(t % wb); t /= wb;
+    const int yb = (int)(t % hb);
+    const int b = (int)(t / hb);
     const V8 sc = loadf8(scale + g * 8), sh = loadf8(shift + g * 8);
-    // the (up to) nine loads first
-    uint4 v[9];
-    bool ok[9];
+    float best[4][8];                    // [oy * 2 + ox]
+    uint32_t bi[4][2];                   // argmax r*3+s, one byte per channel
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 4; ++k) {
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const int yi = 2 * yo - 1 + r, xi = 2 * xo - 1 + q;
-        ok[r * 3 + q] = yi >= 0 && yi < h && xi >= 0 && xi < w;
-        v[r * 3 + q] = ok[r * 3 + q] ? *reinterpret_cast<const uint4*>(y + (((int64_t)b * h + yi) * w + xi) * c + g * 8)
-                                     : make_uint4(0, 0, 0, 0);
+      for (int j = 0; j < 8; ++j) best[k][j] = -INFINITY;
+      bi[k][0] = bi[k][1] = 0u;
+    }
+    const int y0 = 4 * yb - 1, x0 = 4 * xb - 1;     // first input row / column of the 5x5 patch
+#pragma unroll
+    for (int ry = 0; ry < 5; ++ry) {
+      const int yi = y0 + ry;
+      const bool yok = yi >= 0 && yi < h;
+      uint4 v[5];
+#pragma unroll
+      for (int cx = 0; cx < 5; ++cx) {
+        const int xi = x0 + cx;
+        v[cx] = (yok && xi >= 0 && xi < w) ? *reinterpret_cast<const uint4*>(y + (((int64_t)b * h + yi) * w + xi) * c + g * 8)
+                                           : make_uint4(0, 0, 0, 0);
       }
-    float best[8];
-    int bi[8];
+      if (!yok) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+      for (int cx = 0; cx < 5; ++cx) {
+        const int xi = x0 + cx;
+        if (xi < 0 || xi >= w) continue;
+        const uint32_t yw[4] = {v[cx].x, v[cx].y, v[cx].z, v[cx].w};
+        float a[8];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      if (!ok[k]) continue;
-      const uint32_t yw[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+        for (int p = 0; p < 4; ++p) {
+          const float2 yv = bf2_to_f2(yw[p]);
+          const float2 r2 = bf2_to_f2(f2_to_bf2(fmaxf(fmaf(yv.x, sc.v[2 * p], sh.v[2 * p]), 0.f),
+                                                fmaxf(fmaf(yv.y, sc.v[2 * p + 1], sh.v[2 * p + 1]), 0.f)));
+          a[2 * p] = r2.x;
+          a[2 * p + 1] = r2.y;
+        }
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const float2 yv = bf2_to_f2(yw[p]);
-        const float2 a = bf2_to_f2(f2_to_bf2(fmaxf(fmaf(yv.x, sc.v[2 * p], sh.v[2 * p]), 0.f),
-                                             fmaxf(fmaf(yv.y, sc.v[2 * p + 1], sh.v[2 * p + 1]), 0.f)));
-        if (a.x > best[2 * p]) { best[2 * p] = a.x; bi[2 * p] = k; }
-        if (a.y > best[2 * p + 1]) { best[2 * p + 1] = a.y; bi[2 * p + 1] = k; }
+        for (int oy = 0; oy < 2; ++oy) {
+          const int r = ry - 2 * oy;                 // filter row of this input row in output row oy
+          if (r < 0 || r > 2) continue;
+#pragma unroll
+          for (int ox = 0; ox < 2; ++ox) {
+            const int q = cx - 2 * ox;
+            if (q < 0 || q > 2) continue;
+            const uint32_t pos = (uint32_t)(r * 3 + q);
+            const int k = oy * 2 + ox;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (a[j] > best[k][j]) {
+                best[k][j] = a[j];
+                bi[k][j >> 2] = (bi[k][j >> 2] & ~(0xffu << (8 * (j & 3)))) | (pos << (8 * (j & 3)));
+              }
+          }
+        }
       }
     }
-    V8 o;
-    __align__(8) uint8_t ib[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { o.v[j] = best[j]; ib[j] = (uint8_t)bi[j]; }
-    const int64_t off = (((int64_t)b * ho + yo) * wo + xo) * c + g * 8;
-    store8(out + off, o);
-    *reinterpret_cast<uint2*>(idx + off) = *reinterpret_cast<uint2*>(ib);
+    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+      for (int ox = 0; ox < 2; ++ox) {
+        const int yo = 2 * yb + oy, xo = 2 * xb + ox;
+        if (yo >= ho || xo >= wo) continue;
+        V8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = best[oy * 2 + ox][j];
+        const int64_t off = (((int64_t)b * ho + yo) * wo + xo) * c + g * 8;
+        store8(out + off, o);
+        *reinterpret_cast<uint2*>(idx + off) = make_uint2(bi[oy * 2 + ox][0], bi[oy * 2 + ox][1]);
+      }
   }
 }
 
@@ -1071,7 +1108,8 @@ int maxpool_fwd(const __nv_bfloat16* x, int n, int h, int w, int c, __nv_bfloat1
 int bn_relu_maxpool_fwd(const __nv_bfloat16* y, const float* scale, const float* shift, int n, int h, int w, int c,
                         __nv_bfloat16* out, uint8_t* idx, cudaStream_t st) {
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
-  bn_relu_maxpool_fwd_kernel<<<grid1d((int64_t)n * ho * wo * c / 8), 256, 0, st>>>(y, scale, shift, n, h, w, c, out, idx);
+  bn_relu_maxpool_fwd_kernel<<<grid1d((int64_t)n * ((ho + 1) / 2) * ((wo + 1) / 2) * c / 8), 256, 0, st>>>(y, scale, shift, n, h, w, c,
+                                                                                                out, idx);
   DIRB_LAUNCHED();
   return DIRB200_OK;
 }

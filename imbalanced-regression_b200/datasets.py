@@ -189,3 +189,46 @@ def stsb_prepare_weights(scores, reweight, lds=False, lds_kernel='gaussian', lds
               _lib.stream_ptr())
     weights, _ = stsb_weights_from_bins(bins.cpu().numpy(), reweight, lds, lds_kernel, lds_ks, lds_sigma, bucket_num)
     return torch.from_numpy(weights).to(device)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Input pipeline on the device.  The reference transforms every sample on the host, one PIL image
+# at a time (datasets.py:38-53); here the decode + resize stay where they are, and everything after the resize --
+# RandomCrop(img_size, padding=16), RandomHorizontalFlip, ToTensor, Normalize -- runs as ONE kernel over the batch of
+# uint8 images (a quarter of the bytes of the fp32 tensor cross PCIe).
+def draw_augment_params(n, size, pad=16, generator=None):
+    """The random draws of RandomCrop(size, padding=pad) + RandomHorizontalFlip() for n samples, consumed from the torch
+    generator in exactly the order the reference's per-sample Compose does (crop row, crop column, flip coin), so that
+    a seeded run reproduces torchvision's choices: returns (crop_yx int32 [n, 2], flip uint8 [n])."""
+    crop = torch.empty(n, 2, dtype=torch.int32)
+    flip = torch.empty(n, dtype=torch.uint8)
+    for k in range(n):
+        # transforms.RandomCrop.get_params: the padded image is (size + 2 pad)^2, the crop size^2
+        crop[k, 0] = int(torch.randint(0, 2 * pad + 1, size=(1,), generator=generator).item())
+        crop[k, 1] = int(torch.randint(0, 2 * pad + 1, size=(1,), generator=generator).item())
+        flip[k] = 1 if float(torch.rand(1, generator=generator)) < 0.5 else 0      # RandomHorizontalFlip(p=0.5)
+    return crop, flip
+
+
+def gpu_transform_batch(images_u8, train=True, pad=16, crop_yx=None, flip=None, generator=None, out=None):
+    """images_u8: uint8 [N, S, S, 3] (RGB, HWC, already resized to img_size) on the GPU -> float32 [N, 3, S, S], the tensor
+    the reference's train / val transform (datasets.py:38-53) produces, bit for bit for the same draws.
+    train=True draws the crop origins / flips (or takes crop_yx / flip); train=False is the validation chain."""
+    assert images_u8.is_cuda and images_u8.dtype == torch.uint8 and images_u8.dim() == 4 and images_u8.shape[3] == 3
+    assert images_u8.shape[1] == images_u8.shape[2], "square images (Resize((img_size, img_size)))"
+    images_u8 = images_u8.contiguous()
+    n, size = images_u8.shape[0], images_u8.shape[1]
+    dev = images_u8.device
+    if train:
+        if crop_yx is None or flip is None:
+            crop_yx, flip = draw_augment_params(n, size, pad, generator)
+        crop_yx = crop_yx.to(device=dev, dtype=torch.int32).contiguous()
+        flip = flip.to(device=dev, dtype=torch.uint8).contiguous()
+        assert crop_yx.shape == (n, 2) and flip.shape == (n,)
+    else:
+        crop_yx = flip = None
+    if out is None:
+        out = torch.empty(n, 3, size, size, dtype=torch.float32, device=dev)
+    _lib.call("dirb200_augment_batch", _lib.ptr(images_u8), _lib.ptr(crop_yx) if crop_yx is not None else None,
+              _lib.ptr(flip) if flip is not None else None, n, size, pad, 0.5, 0.5, _lib.ptr(out), _lib.stream_ptr())
+    return out

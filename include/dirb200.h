@@ -167,6 +167,15 @@ int dirb200_lds_weights_sharded(const float* labels, int64_t n, int64_t n_total,
 int dirb200_lds_table_lookup(const float* values, int64_t n, float mult, int max_bin, const float* table,
                              float* weights_out, void* stream);
 
+/* ------------------------------------------------ input pipeline ---- */
+/* Batched device form of the per-sample torchvision chain agedb-dir/datasets.py:38-53 after the resize:
+ * RandomCrop(size, padding=pad) -> RandomHorizontalFlip -> ToTensor -> Normalize(mean, std), bit-identical to
+ * torchvision for the same draws.  images u8 [n][size][size][3] (RGB, HWC) -> out f32 [n][3][size][size].
+ * crop_yx int32 [n][2] = (top, left) of the crop in the zero-padded image, 0 .. 2*pad (NULL: (pad, pad) = the
+ * validation chain, :46-51); flip u8 [n] (NULL: no flips).  value = (u8 / 255 - mean) / std; padding = u8 0. */
+int dirb200_augment_batch(const uint8_t* images, const int* crop_yx, const uint8_t* flip, int n, int size, int pad,
+                          float mean, float stdv, float* out, void* stream);
+
 /* ------------------------------------------------ evaluation metrics ---- */
 /* hist[int(label)] += 1 for 0 <= int(label) < nbins (int64, bit-exact, ADDS; no clamping): the per-label-value
  * training counts that shot_metrics compares against, agedb-dir/train.py:339,350. */
