@@ -28,6 +28,7 @@ constexpr int BK = 64;   // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kProducerThreads = 128;   // warps 0-3
 constexpr int kTmaWarp = 4, kMmaWarp = 5; // warps 6-9: epilogue (warp & 3 = TMEM lane quarter)
 constexpr int kThreads = 320;
+constexpr int kMaxTaps = 25;   // up to 5x5 filters (the NYUD2 decoder / refinement convs, nyud2-dir/models/modules.py:11-20,154-160)
 
 struct IgemmParams {
   const __nv_bfloat16* src;  // gathered tensor, NHWC
@@ -40,11 +41,11 @@ struct IgemmParams {
   // parity matches (tap_list) are visited -- 9 tap-passes over quarter-size grids instead of 9 over the full one.
   int cls_on, cls_py, cls_px, full_h, full_w;
   int ntaps_c;               // taps visited by this launch
-  int tap_list[9];           // their indices r*kw + s (identity when cls_on == 0)
+  int tap_list[kMaxTaps];    // their indices r*kw + s (identity when cls_on == 0)
   // per visited tap (index = position in tap_list), filled by finish_params(): element offset of the tap from the
   // row's origin in the gathered tensor, and the im2col-TMA offsets (flipped for dgrad)
-  long long tap_eoff[9];
-  unsigned short tap_r[9], tap_s[9];
+  long long tap_eoff[kMaxTaps];
+  unsigned short tap_r[kMaxTaps], tap_s[kMaxTaps];
   FastDiv fd_hw, fd_wm, fd_cpb, fd_kw, fd_ntiles, fd_persplit;
   int cpb;                   // 64-channel blocks per filter tap (cs / 64); stem: unused
   long long pixels;          // n * hm * wm
@@ -1169,8 +1170,8 @@ static IgemmParams finish_params(const IgemmParams& P) {
   Q.fd_persplit = make_fastdiv(static_cast<uint32_t>(Q.m_tiles * Q.n_tiles > 0 ? Q.m_tiles * Q.n_tiles : 1));
   Q.fd_tpi = make_fastdiv(static_cast<uint32_t>(Q.patch_r > 0 ? Q.patch_h / Q.patch_r : 1));
   Q.fd_wp = make_fastdiv(static_cast<uint32_t>(Q.patch_wp > 0 ? Q.patch_wp : 1));
-  const int nt = Q.ntaps_c < 9 ? Q.ntaps_c : 9;
-  for (int i = 0; i < 9; ++i) {
+  const int nt = Q.ntaps_c < kMaxTaps ? Q.ntaps_c : kMaxTaps;
+  for (int i = 0; i < kMaxTaps; ++i) {
     Q.tap_eoff[i] = 0;
     Q.tap_r[i] = Q.tap_s[i] = 0;
   }
@@ -1446,8 +1447,8 @@ static int conv_fprop_impl(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_
   P.pixels = static_cast<long long>(s.n) * s.ho * s.wo;
   P.num_kblocks = ktot / 64;
   P.ntaps_c = s.kh * s.kw;
-  DIRB_CHECK_ARG(stem || P.ntaps_c <= 9, "conv_fprop: at most 9 filter taps (got %dx%d)", s.kh, s.kw);
-  for (int i = 0; i < 9; ++i) P.tap_list[i] = i;
+  DIRB_CHECK_ARG(stem || P.ntaps_c <= kMaxTaps, "conv_fprop: at most %d filter taps (got %dx%d)", kMaxTaps, s.kh, s.kw);
+  for (int i = 0; i < kMaxTaps; ++i) P.tap_list[i] = i;
   P.ldc = s.cout; P.out = y;
   P.stat_out = stat_partial;
   if (epi) {
@@ -1492,7 +1493,8 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
   DIRB_CHECK_ARG(!bnm || (conv_dgrad_fuses_bn_moments(s) && bnm->y && bnm->scale && bnm->shift && bnm->partial),
                  "conv_dgrad: BN-backward moments are fused into TMA-fed stride-1 dgrads only");
   DIRB_CHECK_ARG(s.stride == 1 || s.stride == 2, "conv_dgrad: stride must be 1 or 2 (got %d)", s.stride);
-  DIRB_CHECK_ARG(s.kh * s.kw <= 9, "conv_dgrad: at most 9 filter taps (got %dx%d)", s.kh, s.kw);
+  DIRB_CHECK_ARG(s.kh * s.kw <= (s.stride == 1 ? kMaxTaps : 9), "conv_dgrad: at most %d filter taps (stride 2: 9; got %dx%d)",
+                 kMaxTaps, s.kh, s.kw);
   const int ktot = s.kh * s.kw * s.cout;
   IgemmParams P{};
   P.src = dy; P.n = s.n; P.hs = s.ho; P.ws = s.wo; P.cs = s.cout; P.hm = s.h; P.wm = s.w;
@@ -1506,7 +1508,7 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
   if (s.stride == 1) {
     P.pixels = static_cast<long long>(s.n) * s.h * s.w;
     P.ntaps_c = s.kh * s.kw;
-    for (int i = 0; i < 9; ++i) P.tap_list[i] = i;
+    for (int i = 0; i < kMaxTaps; ++i) P.tap_list[i] = i;
     P.num_kblocks = ktot / 64;
     if (const int pr = patch_rows(s.ho, s.wo, s.cout, s.kh, s.kw, s.stride, s.pad, s.cin)) {
       const int rc = launch_patch(dy, wt, P, s.n, s.ho, s.wo, pr, true, st);
@@ -1627,7 +1629,8 @@ int conv_wgrad_partials(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
   P.num_kblocks = static_cast<int>((P.pixels + 63) / 64);
   P.total_chunks = s.kh * s.kw * s.cin / 64;
   P.ntaps_c = s.kh * s.kw;
-  for (int i = 0; i < 9; ++i) P.tap_list[i] = i;
+  DIRB_CHECK_ARG(stem || P.ntaps_c <= kMaxTaps, "conv_wgrad: at most %d filter taps (got %dx%d)", kMaxTaps, s.kh, s.kw);
+  for (int i = 0; i < kMaxTaps; ++i) P.tap_list[i] = i;
   const int splits = conv_wgrad_splits(s);
   P.kblocks_per_split = (P.num_kblocks + splits - 1) / splits;
   P.ldc = s.cout; P.out = partial;

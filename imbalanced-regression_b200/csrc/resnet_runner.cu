@@ -54,14 +54,6 @@ struct dirb200_net {
   int pool_h = 0, pool_w = 0;
   int feat_c = 0, feat_hw = 0;
   __nv_bfloat16* scratch[8] = {};
-  // DIRB200_WGRAD_OVERLAP=1: the weight-gradient GEMMs run on a side stream beside the dgrad / BN chain (they are only
-  // needed by the per-stage split-K reduction).  The dy tensors they read rotate through small rings; `done` marks the
-  // side-stream reader of a ring buffer finished, the next writer on the main stream waits for it.
-  struct DyBuf { __nv_bfloat16* p = nullptr; cudaEvent_t done = nullptr; bool pending = false; };
-  DyBuf dy1[3], dy2[2];
-  int dy1_next = 0, dy2_next = 0;
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   WgradReduceDesc* reduce_descs = nullptr;     // device table, conv layers in backward-stage order
   std::vector<int> reduce_begin;               // first table entry of stage s (0 = stem, 1.. = layer groups); +1 sentinel
   float* bn_partial = nullptr;   // per-CTA partial sums of the BN column reductions (backward)
@@ -110,14 +102,6 @@ static bool dev_alloc(dirb200_net* net, void** p, size_t bytes) {
   net->allocs.push_back(*p);
   net->activation_bytes += bytes;
   return true;
-}
-
-static bool wgrad_overlap() {
-  static const bool on = [] {
-    const char* e = getenv("DIRB200_WGRAD_OVERLAP");
-    return e != nullptr && e[0] == '1';
-  }();
-  return on;
 }
 
 #define NET_ALLOC(ptr, bytes)                                                     \
@@ -200,20 +184,6 @@ static bool build(dirb200_net* net, const int* blocks_per_stage, int num_stages)
   net->feat_c = inplanes;
   net->feat_hw = h * w;
   for (int i = 0; i < 8; ++i) NET_ALLOC(net->scratch[i], max_act * 2);
-  net->dy1[0].p = net->scratch[4];
-  net->dy2[0].p = net->scratch[5];
-  if (wgrad_overlap()) {
-    NET_ALLOC(net->dy1[1].p, max_act * 2);
-    NET_ALLOC(net->dy1[2].p, max_act * 2);
-    NET_ALLOC(net->dy2[1].p, max_act * 2);
-    if (cudaStreamCreateWithFlags(&net->side, cudaStreamNonBlocking) != cudaSuccess) return false;
-    if (cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming) != cudaSuccess) return false;
-    if (cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming) != cudaSuccess) return false;
-    for (auto& b : net->dy1)
-      if (cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming) != cudaSuccess) return false;
-    for (auto& b : net->dy2)
-      if (cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming) != cudaSuccess) return false;
-  }
   {
     // split-K reduction jobs: every conv owns its partial buffer; one launch reduces a whole backward stage
     std::vector<WgradReduceDesc> rd;
@@ -345,41 +315,9 @@ static int conv_bn_forward(dirb200_net* net, ConvLayer& cv, const __nv_bfloat16*
 
 // weight-gradient GEMM of one conv into its own split-K partial buffer; the reduction into the flat gradient happens
 // once per backward stage (wgrad_reduce_stage)
-static int wgrad_step(dirb200_net* net, const __nv_bfloat16* x, dirb200_net::DyBuf& dyb, ConvLayer& cv, cudaStream_t st) {
+static int wgrad_step(dirb200_net* net, const __nv_bfloat16* x, const __nv_bfloat16* dy, ConvLayer& cv, cudaStream_t st) {
   int splits = 1;
-  if (net->side && !net->profiling) {
-    // fork: the side stream sees everything the main stream has issued so far (dy is complete), runs the GEMM, and
-    // marks the dy buffer free for its next writer
-    DIRB_CUDA(cudaEventRecord(net->ev_fork, st));
-    DIRB_CUDA(cudaStreamWaitEvent(net->side, net->ev_fork, 0));
-    RUN(conv_wgrad_partials(x, dyb.p, cv.wpart, cv.s, cv.stem, &splits, net->side));
-    DIRB_CUDA(cudaEventRecord(dyb.done, net->side));
-    dyb.pending = true;
-    return DIRB200_OK;
-  }
-  RUNP(kWgrad, conv_wgrad_partials(x, dyb.p, cv.wpart, cv.s, cv.stem, &splits, st));
-  return DIRB200_OK;
-}
-
-// next buffer of a dy ring for a writer on the main stream (waits for the side-stream GEMM that still reads it)
-static int take_dy(dirb200_net* net, dirb200_net::DyBuf* ring, int n, int& next, cudaStream_t st, dirb200_net::DyBuf** out) {
-  dirb200_net::DyBuf& b = ring[net->side ? next : 0];
-  if (net->side) next = (next + 1) % n;
-  if (b.pending) {
-    DIRB_CUDA(cudaStreamWaitEvent(st, b.done, 0));
-    b.pending = false;
-  }
-  *out = &b;
-  return DIRB200_OK;
-}
-
-// join: everything the side stream still runs is ordered before what the main stream issues next
-static int join_side(dirb200_net* net, cudaStream_t st) {
-  if (!net->side) return DIRB200_OK;
-  DIRB_CUDA(cudaEventRecord(net->ev_join, net->side));
-  DIRB_CUDA(cudaStreamWaitEvent(st, net->ev_join, 0));
-  for (auto& b : net->dy1) b.pending = false;
-  for (auto& b : net->dy2) b.pending = false;
+  RUNP(kWgrad, conv_wgrad_partials(x, dy, cv.wpart, cv.s, cv.stem, &splits, st));
   return DIRB200_OK;
 }
 
@@ -545,11 +483,6 @@ int dirb200_resnet_create(int n, int h, int w, const int* blocks_per_stage, int 
 void dirb200_resnet_destroy(dirb200_net* net) {
   if (!net) return;
   if (net->cap_stream) cudaStreamDestroy(net->cap_stream);
-  if (net->side) cudaStreamDestroy(net->side);
-  if (net->ev_fork) cudaEventDestroy(net->ev_fork);
-  if (net->ev_join) cudaEventDestroy(net->ev_join);
-  for (auto& b : net->dy1) if (b.done) cudaEventDestroy(b.done);
-  for (auto& b : net->dy2) if (b.done) cudaEventDestroy(b.done);
   if (net->g_fwd.exec) cudaGraphExecDestroy(net->g_fwd.exec);
   for (auto& g : net->g_bwd)
     if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -643,13 +576,9 @@ namespace dirb200 {
 // blocks [lo, hi) in reverse order; the incoming gradient pair is net->bw_gA / bw_gB
 static int backward_blocks(dirb200_net* net, int lo, int hi, const float* params, float* grads, cudaStream_t st) {
   __nv_bfloat16 *gA = net->bw_gA, *gB = net->bw_gB, *nA = net->bw_nA, *nB = net->bw_nB, *spareB = net->bw_spareB;
-  __nv_bfloat16* t3 = net->scratch[6];
+  __nv_bfloat16 *t1 = net->scratch[4], *t2 = net->scratch[5], *t3 = net->scratch[6];
   int gB_h = net->bw_gB_h, gB_w = net->bw_gB_w;
   for (int bi = hi - 1; bi >= lo; --bi) {
-    dirb200_net::DyBuf *d1 = nullptr, *d2 = nullptr;     // dy of the conv about to be differentiated (main / downsample branch)
-    RUN(take_dy(net, net->dy1, 3, net->dy1_next, st, &d1));
-    if (net->blocks[bi].has_ds) RUN(take_dy(net, net->dy2, 2, net->dy2_next, st, &d2));
-    __nv_bfloat16 *t1 = d1->p, *t2 = d2 ? d2->p : nullptr;
     Block& B = net->blocks[bi];
     BNLayer& b3 = B.c3.bn;
     // ---- block output: out = relu(bn3(y3) + identity); dz = (gA + gB) * (out > 0)
@@ -674,25 +603,21 @@ static int backward_blocks(dirb200_net* net, int lo, int hi, const float* params
                                      b3.c, t1, nullptr, nullptr, st));
     gB_h = gB_w = 0;
     // ---- conv3
-    RUN(wgrad_step(net, B.c2.a, *d1, B.c3, st));
+    RUN(wgrad_step(net, B.c2.a, t1, B.c3, st));
     StatLayout mlay{};
     bool mfused = false;
     RUN(dgrad_with_bn_moments(net, t1, B.c3, B.c2, t3, &mlay, &mfused, st));
     // ---- bn2 + conv2
-    RUN(take_dy(net, net->dy1, 3, net->dy1_next, st, &d1));
-    t1 = d1->p;
     RUN(conv_bn_backward(net, B.c2, t3, params, grads, t1, st, mfused ? &mlay : nullptr));
-    RUN(wgrad_step(net, B.c1.a, *d1, B.c2, st));
+    RUN(wgrad_step(net, B.c1.a, t1, B.c2, st));
     RUN(dgrad_with_bn_moments(net, t1, B.c2, B.c1, t3, &mlay, &mfused, st));
     // ---- bn1 + conv1
-    RUN(take_dy(net, net->dy1, 3, net->dy1_next, st, &d1));
-    t1 = d1->p;
     RUN(conv_bn_backward(net, B.c1, t3, params, grads, t1, st, mfused ? &mlay : nullptr));
-    RUN(wgrad_step(net, B.in, *d1, B.c1, st));
+    RUN(wgrad_step(net, B.in, t1, B.c1, st));
     RUNP(kDgrad, conv_dgrad(t1, B.c1.wd, nA, B.c1.s, st));
     // ---- downsample branch
     if (B.has_ds) {
-      RUN(wgrad_step(net, B.in, *d2, B.ds, st));
+      RUN(wgrad_step(net, B.in, t2, B.ds, st));
       const ConvShape& d = B.ds.s;
       if (d.stride == 2 && d.kh == 1 && d.kw == 1 && d.pad == 0 && d.h % 2 == 0 && d.w % 2 == 0 && bi > 0 &&
           !net->blocks[bi - 1].has_ds) {
@@ -752,14 +677,11 @@ int dirb200_resnet_backward_stage(dirb200_net* net, int stage, const float* d_en
       RUN(backward_blocks(net, net->stage_begin[stage], net->stage_begin[stage + 1], params, grads, st));
     } else {
       // ---- stem: maxpool -> bn1+relu -> conv1 (no data gradient needed)
-      __nv_bfloat16* t3 = net->scratch[6];
-      dirb200_net::DyBuf* d1 = nullptr;
-      RUN(take_dy(net, net->dy1, 3, net->dy1_next, st, &d1));
+      __nv_bfloat16 *t1 = net->scratch[4], *t3 = net->scratch[6];
       RUNP(kPool, maxpool_bwd(net->bw_gA, net->bw_gB, net->pool_idx, net->n, net->stem.s.ho, net->stem.s.wo, 64, t3, st));
-      RUN(conv_bn_backward(net, net->stem, t3, params, grads, d1->p, st));
-      RUN(wgrad_step(net, net->x_s2d, *d1, net->stem, st));
+      RUN(conv_bn_backward(net, net->stem, t3, params, grads, t1, st));
+      RUN(wgrad_step(net, net->x_s2d, t1, net->stem, st));
     }
-    RUN(join_side(net, st));
     RUN(wgrad_reduce_stage(net, stage, grads, st));
     return DIRB200_OK;
   };

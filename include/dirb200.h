@@ -167,6 +167,19 @@ int dirb200_lds_weights_sharded(const float* labels, int64_t n, int64_t n_total,
 int dirb200_lds_table_lookup(const float* values, int64_t n, float mult, int max_bin, const float* table,
                              float* weights_out, void* stream);
 
+/* ------------------------------------------------ dense-prediction ops (NYUD2-DIR) ---- */
+/* The NYUD2 decoder / feature-fusion / refinement modules (nyud2-dir/models/modules.py:6-174) are 1x1 / 3x3 / 5x5
+ * convolutions (dirb200_conv_fprop / _dgrad / _wgrad take filters up to 5x5 at stride 1), bilinear up-sampling and a
+ * channel concat.  NHWC bf16 like the conv stage; channel counts multiples of 8.
+ * upsample: F.upsample(x, size=(ho, wo), mode='bilinear') with align_corners = False (modules.py:24), the weights
+ * formed and associated as ATen does; the backward is a deterministic gather (ATen scatters with atomics). */
+int dirb200_upsample_bilinear_fwd(const void* x, int n, int h, int w, int c, int ho, int wo, void* out, void* stream);
+int dirb200_upsample_bilinear_bwd(const void* dy, int n, int h, int w, int c, int ho, int wo, void* dx, void* stream);
+/* dst[p][dst_off + j] = src[p][src_off + j] for j < c, p < pixels (row strides in elements): torch.cat(..., 1) of
+ * NHWC tensors (modules.py:120) is one call per source; its backward is the same call with the roles swapped. */
+int dirb200_copy_channels(const void* src, int src_stride, int src_off, void* dst, int dst_stride, int dst_off, int c,
+                          int64_t pixels, void* stream);
+
 /* ------------------------------------------------ input pipeline ---- */
 /* Batched device form of the per-sample torchvision chain agedb-dir/datasets.py:38-53 after the resize:
  * RandomCrop(size, padding=pad) -> RandomHorizontalFlip -> ToTensor -> Normalize(mean, std), bit-identical to
