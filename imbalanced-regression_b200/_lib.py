@@ -57,6 +57,13 @@ _SIGS = {
     "dirb200_lds_weights_sharded": (c_int, [P, c_int64, c_int64, c_int, c_int, P, c_int, P, P, P, P]),
     "dirb200_int_label_histogram": (c_int, [P, c_int64, c_int, P, P]),
     "dirb200_shot_metrics": (c_int, [P, P, c_int64, P, c_int, c_int, c_int, P, P]),
+    "dirb200_bn_workspace_bytes": (c_size_t, [c_int]),
+    "dirb200_bn_train_fwd": (c_int, [P, c_int64, c_int, P, P, c_float, c_float, P, P, c_int, P, P, P, P, P, P]),
+    "dirb200_bn_train_bwd": (c_int, [P, P, c_int64, c_int, P, P, P, P, c_int, P, P, P, P, P]),
+    "dirb200_maxpool3x3s2_fwd": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P]),
+    "dirb200_maxpool3x3s2_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
+    "dirb200_avgpool_fwd": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "dirb200_avgpool_bwd": (c_int, [P, c_int, c_int, c_int, P, P]),
     "dirb200_upsample_bilinear_fwd": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     "dirb200_upsample_bilinear_bwd": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     "dirb200_copy_channels": (c_int, [P, c_int, c_int, P, c_int, c_int, c_int, c_int64, P]),

@@ -1019,7 +1019,8 @@ int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_b
                  "bn_bwd_reduce: bad compact second gradient");
   const int cgroups = c / 8;
   DIRB_CHECK_ARG(c % 8 == 0 && cgroups <= 256 && 256 % cgroups == 0, "bn_bwd_reduce: unsupported channel count %d", c);
-  DIRB_CHECK_ARG(mask || (scale && shift && !g2 && !y2), "bn_bwd_reduce: mask-from-y form takes one gradient, one BN");
+  DIRB_CHECK_ARG(mask || (!g2 && !y2 && (scale != nullptr) == (shift != nullptr)),
+                 "bn_bwd_reduce: the mask-from-y and the no-ReLU forms take one gradient, one BN");
   DIRB_CHECK_ARG(!dz_out || (mask && !y2), "bn_bwd_reduce: dz is stored for identity blocks only");
   const int lanes = 256 / cgroups;
   const size_t smem = 256 * (y2 ? 24 : 16) * sizeof(float);
@@ -1030,7 +1031,8 @@ int bn_bwd_reduce(const __nv_bfloat16* g1, const __nv_bfloat16* g2, const __nv_b
     bn_bwd_reduce_kernel<MODE, G2, Y2, DZ><<<*nblocks, 256, smem, st>>>(g1, g2, cg2, y, y2, scale, shift, mask, rows, c, \
                                                                         partial, dz_out);                     \
   } while (0)
-  if (!mask) DIRB_RED(MASK_FROM_Y, G2_NONE, false, false);
+  if (!mask && !scale) DIRB_RED(MASK_NONE, G2_NONE, false, false);        // BN without a ReLU behind it
+  else if (!mask) DIRB_RED(MASK_FROM_Y, G2_NONE, false, false);
   else if (g2_h && dz_out) DIRB_RED(MASK_BITS, G2_COMPACT, false, true);
   else if (g2_h) DIRB_RED(MASK_BITS, G2_COMPACT, false, false);
   else if (g2 && y2) DIRB_RED(MASK_BITS, G2_DENSE, true, false);
@@ -1139,6 +1141,70 @@ int avgpool_bwd(const float* genc, int n, int hw, int c, __nv_bfloat16* dx, cuda
 using namespace dirb200;
 
 extern "C" {
+
+/* ---- BatchNorm2d (training mode) / pooling on NHWC bf16 tensors: the layers between the convolutions, as entry points
+ * of their own (the ResNet runner sequences the same kernels internally; the NYUD2 decoder modules need them singly). */
+size_t dirb200_bn_workspace_bytes(int c) { return sizeof(float) * static_cast<size_t>(bn_partial_floats(c)); }
+
+int dirb200_bn_train_fwd(const void* y, int64_t rows, int c, const float* gamma, const float* beta, float eps,
+                         float momentum, float* running_mean, float* running_var, int relu, void* out, float* save_mean,
+                         float* save_invstd, float* scale_shift, void* workspace, void* stream) {
+  DIRB_CHECK_ARG(y && out && gamma && beta && save_mean && save_invstd && scale_shift && workspace && rows > 0,
+                 "bn_train_fwd: null pointer");
+  cudaStream_t st = as_stream(stream);
+  float* partial = static_cast<float*>(workspace);
+  int nblk = 0;
+  if (int rc = bn_stats(static_cast<const __nv_bfloat16*>(y), rows, c, partial, &nblk, st)) return rc;
+  if (int rc = bn_finalize(partial, StatLayout{nblk, 1, c, 1}, rows, c, gamma, beta, eps, momentum, running_mean, running_var,
+                           save_mean, save_invstd, scale_shift, scale_shift + c, st))
+    return rc;
+  return bn_apply(static_cast<const __nv_bfloat16*>(y), scale_shift, scale_shift + c, nullptr, nullptr, nullptr, nullptr,
+                  relu != 0, rows, c, static_cast<__nv_bfloat16*>(out), nullptr, st);
+}
+
+int dirb200_bn_train_bwd(const void* grad_out, const void* y, int64_t rows, int c, const float* gamma,
+                         const float* save_mean, const float* save_invstd, const float* scale_shift, int relu,
+                         float* grad_gamma, float* grad_beta, void* grad_y, void* workspace, void* stream) {
+  DIRB_CHECK_ARG(grad_out && y && gamma && save_mean && save_invstd && grad_gamma && grad_beta && grad_y && workspace &&
+                     rows > 0 && (!relu || scale_shift),
+                 "bn_train_bwd: null pointer");
+  cudaStream_t st = as_stream(stream);
+  float* partial = static_cast<float*>(workspace);
+  float* coef = partial + bn_partial_floats(c) - 3 * c;        // the reduction uses at most 2/3 of the buffer
+  const float* sc = relu ? scale_shift : nullptr;
+  const float* sh = relu ? scale_shift + c : nullptr;
+  int nblk = 0;
+  if (int rc = bn_bwd_reduce(static_cast<const __nv_bfloat16*>(grad_out), nullptr, static_cast<const __nv_bfloat16*>(y),
+                             nullptr, sc, sh, nullptr, rows, c, partial, &nblk, st))
+    return rc;
+  if (int rc = bn_bwd_coeffs(partial, nblk, 2, 1, rows, c, save_mean, save_invstd, gamma, grad_gamma, grad_beta, coef, st))
+    return rc;
+  return bn_bwd_apply(static_cast<const __nv_bfloat16*>(grad_out), nullptr, static_cast<const __nv_bfloat16*>(y), coef,
+                      nullptr, nullptr, sc, sh, nullptr, rows, c, static_cast<__nv_bfloat16*>(grad_y), nullptr, nullptr, st);
+}
+
+int dirb200_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c, void* out, uint8_t* argmax, void* stream) {
+  DIRB_CHECK_ARG(x && out && argmax && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "maxpool_fwd: bad arguments");
+  return maxpool_fwd(static_cast<const __nv_bfloat16*>(x), n, h, w, c, static_cast<__nv_bfloat16*>(out), argmax,
+                     as_stream(stream));
+}
+
+int dirb200_maxpool3x3s2_bwd(const void* grad_out, const uint8_t* argmax, int n, int h, int w, int c, void* grad_x,
+                             void* stream) {
+  DIRB_CHECK_ARG(grad_out && argmax && grad_x && n > 0 && c > 0 && c % 8 == 0, "maxpool_bwd: bad arguments");
+  return maxpool_bwd(static_cast<const __nv_bfloat16*>(grad_out), nullptr, argmax, n, h, w, c,
+                     static_cast<__nv_bfloat16*>(grad_x), as_stream(stream));
+}
+
+int dirb200_avgpool_fwd(const void* x, int n, int hw, int c, float* out, void* stream) {
+  DIRB_CHECK_ARG(x && out && n > 0 && hw > 0 && c > 0 && c % 8 == 0, "avgpool_fwd: bad arguments");
+  return avgpool_fwd(static_cast<const __nv_bfloat16*>(x), n, hw, c, out, as_stream(stream));
+}
+
+int dirb200_avgpool_bwd(const float* grad_out, int n, int hw, int c, void* grad_x, void* stream) {
+  DIRB_CHECK_ARG(grad_out && grad_x && n > 0 && hw > 0 && c > 0 && c % 8 == 0, "avgpool_bwd: bad arguments");
+  return avgpool_bwd(grad_out, n, hw, c, static_cast<__nv_bfloat16*>(grad_x), as_stream(stream));
+}
 
 int dirb200_linear1_fwd(const float* x, const float* w, const float* bias, int64_t n, int d, float* pred,
                         void* stream) {

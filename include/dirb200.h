@@ -167,6 +167,30 @@ int dirb200_lds_weights_sharded(const float* labels, int64_t n, int64_t n_total,
 int dirb200_lds_table_lookup(const float* values, int64_t n, float mult, int max_bin, const float* table,
                              float* weights_out, void* stream);
 
+/* ------------------------------------------------ BatchNorm / pooling layers ---- */
+/* nn.BatchNorm2d in training mode on an NHWC bf16 tensor y [rows][c] (rows = N*H*W; c a multiple of 8, <= 2048),
+ * optionally followed by ReLU (agedb-dir/resnet.py:46-51,128-130; nyud2-dir/models/modules.py:13-21): batch statistics
+ * (biased variance) -> running statistics updated in place with `momentum` (unbiased variance; NULL: not tracked) ->
+ * out = [relu](gamma * (y - mean) * invstd + beta).  save_mean / save_invstd [c] and scale_shift [2][c] are kept for
+ * the backward.  workspace: dirb200_bn_workspace_bytes(c). */
+size_t dirb200_bn_workspace_bytes(int c);
+int dirb200_bn_train_fwd(const void* y, int64_t rows, int c, const float* gamma, const float* beta, float eps,
+                         float momentum, float* running_mean, float* running_var, int relu, void* out, float* save_mean,
+                         float* save_invstd, float* scale_shift, void* workspace, void* stream);
+/* grad_out = d loss / d out -> grad_y = d loss / d y (bf16), grad_gamma / grad_beta ACCUMULATED (fp32 [c]).  With relu the
+ * mask is re-derived from (y, scale_shift) -- the activation itself is not read. */
+int dirb200_bn_train_bwd(const void* grad_out, const void* y, int64_t rows, int c, const float* gamma,
+                         const float* save_mean, const float* save_invstd, const float* scale_shift, int relu,
+                         float* grad_gamma, float* grad_beta, void* grad_y, void* workspace, void* stream);
+/* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (resnet.py:82) on NHWC bf16, argmax (r*3+s of the first maximum)
+ * kept as one byte per output element; backward for even H, W. */
+int dirb200_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c, void* out, uint8_t* argmax, void* stream);
+int dirb200_maxpool3x3s2_bwd(const void* grad_out, const uint8_t* argmax, int n, int h, int w, int c, void* grad_x,
+                             void* stream);
+/* nn.AvgPool2d over the whole hw-pixel map (resnet.py:87) : NHWC bf16 [n][hw][c] <-> fp32 [n][c] */
+int dirb200_avgpool_fwd(const void* x, int n, int hw, int c, float* out, void* stream);
+int dirb200_avgpool_bwd(const float* grad_out, int n, int hw, int c, void* grad_x, void* stream);
+
 /* ------------------------------------------------ dense-prediction ops (NYUD2-DIR) ---- */
 /* The NYUD2 decoder / feature-fusion / refinement modules (nyud2-dir/models/modules.py:6-174) are 1x1 / 3x3 / 5x5
  * convolutions (dirb200_conv_fprop / _dgrad / _wgrad take filters up to 5x5 at stride 1), bilinear up-sampling and a

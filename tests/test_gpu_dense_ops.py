@@ -101,3 +101,90 @@ def test_up_projection_block_composed():
     out.backward(dy)
     ref.backward(nchw(dy))
     assert rel(nchw(xb.grad), xr.grad) < 3e-2
+
+
+@pytest.mark.parametrize("relu", [True, False], ids=["bn_relu", "bn_only"])
+def test_batch_norm_train_fwd_bwd(relu):
+    import dense_ops as D
+    g = torch.Generator().manual_seed(4)
+    n, c, h, w = 3, 128, 10, 12
+    x = (torch.randn(n, c, h, w, generator=g) * 1.5 + 0.3).to(DEV)
+    xb = nhwc(x).requires_grad_(True)
+    xr = nchw(xb.detach()).requires_grad_(True)
+    bn = torch.nn.BatchNorm2d(c).to(DEV)
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.2 * torch.randn(c, generator=g).to(DEV))
+        bn.bias.copy_(0.1 * torch.randn(c, generator=g).to(DEV))
+    gam = bn.weight.detach().clone().requires_grad_(True)
+    bet = bn.bias.detach().clone().requires_grad_(True)
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    out = D.batch_norm_train(xb, gam, bet, rm, rv, 0.1, 1e-5, relu)
+    bn.train()
+    ref = bn(xr)
+    if relu:
+        ref = F.relu(ref)
+    assert rel(nchw(out.detach()), ref.detach()) < 4e-3
+    assert rel(rm, bn.running_mean) < 1e-4 and rel(rv, bn.running_var) < 1e-4
+    dy = nhwc(torch.randn(n, c, h, w, generator=g).to(DEV))
+    out.backward(dy)
+    ref.backward(nchw(dy))
+    assert rel(nchw(xb.grad), xr.grad) < 1e-2
+    assert rel(gam.grad, bn.weight.grad) < 1e-2 and rel(bet.grad, bn.bias.grad) < 1e-2
+
+
+def test_pool_entry_points():
+    import _lib
+    g = torch.Generator().manual_seed(5)
+    n, c, h, w = 2, 64, 12, 16
+    x = torch.randn(n, c, h, w, generator=g).to(DEV)
+    xb = nhwc(x)
+    ho, wo = 6, 8
+    out = torch.empty(n, ho, wo, c, dtype=torch.bfloat16, device=DEV)
+    idx = torch.empty(n, ho, wo, c, dtype=torch.uint8, device=DEV)
+    st = _lib.stream_ptr()
+    _lib.call("dirb200_maxpool3x3s2_fwd", _lib.ptr(xb), n, h, w, c, _lib.ptr(out), _lib.ptr(idx), st)
+    xr = nchw(xb).requires_grad_(True)
+    ref = F.max_pool2d(xr, 3, 2, 1)
+    assert torch.equal(nchw(out), ref.detach())
+    dy = nhwc(torch.randn(n, c, ho, wo, generator=g).to(DEV))
+    dx = torch.empty_like(xb)
+    _lib.call("dirb200_maxpool3x3s2_bwd", _lib.ptr(dy), _lib.ptr(idx), n, h, w, c, _lib.ptr(dx), st)
+    ref.backward(nchw(dy))
+    assert rel(nchw(dx), xr.grad) < 4e-3
+    enc = torch.empty(n, c, dtype=torch.float32, device=DEV)
+    _lib.call("dirb200_avgpool_fwd", _lib.ptr(xb), n, h * w, c, _lib.ptr(enc), st)
+    assert rel(enc, nchw(xb).mean(dim=(2, 3))) < 1e-5
+    gx = torch.empty_like(xb)
+    genc = torch.randn(n, c, generator=g).to(DEV)
+    _lib.call("dirb200_avgpool_bwd", _lib.ptr(genc), n, h * w, c, _lib.ptr(gx), st)
+    assert rel(nchw(gx), (genc / (h * w))[:, :, None, None].expand(n, c, h, w)) < 4e-3
+
+
+def test_refinement_module_forward_backward():
+    """Module R of nyud2-dir (modules.py:128-174) assembled from the operators: forward and all parameter gradients
+    against the same torch graph on bf16-rounded storage points; state_dict keys as the reference's."""
+    import dense_ops as D
+    g = torch.Generator().manual_seed(6)
+    n, c, h, w = 2, 128, 12, 16
+    m = D.RefinementR(c).to(DEV)
+    m.train()
+    assert set(m.state_dict()) >= {"conv0.weight", "bn0.weight", "bn0.running_mean", "conv1.weight", "bn1.bias",
+                                   "conv2.weight", "conv2.bias"}
+    x = nhwc(torch.randn(n, c, h, w, generator=g).to(DEV)).requires_grad_(True)
+    out = m(x)
+    q = lambda t: t.to(torch.bfloat16).float()
+    xr = nchw(x.detach()).requires_grad_(True)
+    ref_m = torch.nn.Sequential()
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in m.named_parameters()}
+    def bn(t, pre):
+        return F.batch_norm(t, None, None, p[pre + ".weight"], p[pre + ".bias"], True, 0.1, 1e-5)
+    r0 = q(F.relu(bn(q(F.conv2d(xr, q(p["conv0.weight"]), padding=2)), "bn0")))
+    r1 = q(F.relu(bn(q(F.conv2d(r0, q(p["conv1.weight"]), padding=2)), "bn1")))
+    ref = F.conv2d(r1, q(p["conv2.weight"]), padding=2) + p["conv2.bias"][None, :, None, None]
+    assert rel(nchw(out.detach()), ref.detach()) < 2e-2
+    dy = nhwc(torch.randn(n, 1, h, w, generator=g).to(DEV))
+    out.backward(dy)
+    ref.backward(nchw(dy))
+    assert rel(nchw(x.grad), xr.grad) < 5e-2
+    for k, v in m.named_parameters():
+        assert v.grad is not None and rel(v.grad.float(), p[k].grad) < 5e-2, (k, rel(v.grad.float(), p[k].grad))

@@ -78,6 +78,21 @@ def main():
     ms = timed(fds_update, reps=3)
     out["fds_update_ms"] = round(ms, 3)
     out["fds_update_gbs"] = round(feats.numel() * 4 / ms / 1e6, 1)
+    # the whole refinement module R (conv0-bn0-relu-conv1-bn1-relu-conv2, training mode), forward + backward
+    del x, dy, y, dx, ws, feats, depth, up, xs, gdn
+    torch.cuda.empty_cache()
+    m = D.RefinementR(c).to(dev)
+    m.train()
+    xin = torch.randn(n, h, w, c, device=dev).to(torch.bfloat16).requires_grad_(True)
+    gout = torch.randn(n, h, w, 1, device=dev).to(torch.bfloat16)
+    def r_step():
+        m.zero_grad(set_to_none=True)
+        xin.grad = None
+        m(xin).backward(gout)
+    ms = timed(r_step, reps=3)
+    out["R_module_fwd_bwd_ms"] = round(ms, 2)
+    out["R_module_conv_gflop_fwd_bwd"] = round(3 * 2 * gflop + 3 * 2.0 * n * h * w * c * 64 * k * k / 1e9, 1)   # conv2 runs 64 padded outputs
+    out["R_module_images_per_s"] = round(n / ms * 1e3, 1)
     print(json.dumps(out))
 
 
