@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <atomic>
 #include "../../include/dirb200.h"
 
@@ -38,12 +39,19 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
     DIRB_CUDA(cudaGetLastError());                \
   } while (0)
 
+// SMs the persistent kernels size their grids for.  DIRB200_SMS=<n> caps it (experiments: leaving SMs to a concurrent
+// NCCL kernel -- a persistent grid with a static tile walk takes twice as long when even one of its CTAs has to wait
+// for an SM).
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (const char* e = getenv("DIRB200_SMS")) {
+      const int cap = atoi(e);
+      if (cap > 0 && cap < n) n = cap;
+    }
   }
   return n;
 }

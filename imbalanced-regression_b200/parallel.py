@@ -58,9 +58,12 @@ class ShardSampler(Sampler):
 
 
 class DataParallel(nn.Module):
-    def __init__(self, module, overlap=True):
+    def __init__(self, module, overlap=None):
         super().__init__()
         self.module = module
+        if overlap is None:                       # DIRB200_OVERLAP_ALLREDUCE=0: one all-reduce after the backward pass
+            import os
+            overlap = os.environ.get("DIRB200_OVERLAP_ALLREDUCE", "1") != "0"
         self._works, self._done = [], []          # pending async all-reduces, flat ranges they cover
         if overlap and is_distributed() and hasattr(module, "_grad_bucket_hook"):
             module._grad_bucket_hook = self._reduce_bucket
