@@ -1178,7 +1178,14 @@ static IgemmParams finish_params(const IgemmParams& P) {
   for (int i = 0; i < nt && Q.kw > 0; ++i) {
     const int tp = Q.tap_list[i];
     int r = tp / Q.kw, sx = tp - r * Q.kw;
-    if (Q.transposed) {
+    if (Q.transposed && Q.cls_on) {
+      // parity class of a stride-2 dgrad: tap (r, s) reads dy pixel (y' + (py + pad - r) / 2, x' + (px + pad - s) / 2);
+      // im2col offsets are relative to the base-pixel box's lower corner i2c_lo
+      Q.tap_r[i] = static_cast<unsigned short>((Q.cls_py + Q.pad - r) / 2 - Q.i2c_lo);
+      Q.tap_s[i] = static_cast<unsigned short>((Q.cls_px + Q.pad - sx) / 2 - Q.i2c_lo);
+      r >>= 1; sx >>= 1;
+      Q.tap_eoff[i] = -static_cast<long long>(r * Q.ws + sx) * Q.cs;
+    } else if (Q.transposed) {
       Q.tap_r[i] = static_cast<unsigned short>(Q.kh - 1 - r);
       Q.tap_s[i] = static_cast<unsigned short>(Q.kw - 1 - sx);
       if (Q.stride == 2) { r >>= 1; sx >>= 1; }
@@ -1572,6 +1579,23 @@ int conv_dgrad(const __nv_bfloat16* dy, const __nv_bfloat16* wt, __nv_bfloat16* 
     const int bn = pick_bn(s.cin, m_tiles, true);
     Q.n_tiles = s.cin / bn;
     if (int rc = make_tmap_bf16_2d(&tm, wt, ktot, s.cin, static_cast<uint64_t>(ktot) * 2, bn)) return rc;
+    if (im2col_enabled()) {
+      // the class is a stride-1 "convolution" over the dy grid whose taps sit at offsets (py + pad - r) / 2: im2col-mode
+      // TMA with the base-pixel box [lo, lo + class grid) (out-of-range dy pixels arrive as zeros)
+      int lo = 1 << 20;
+      for (int i = 0; i < Q.ntaps_c; ++i) {
+        const int r = Q.tap_list[i] / s.kw, q = Q.tap_list[i] % s.kw;
+        const int orr = (Q.cls_py + s.pad - r) / 2, oq = (Q.cls_px + s.pad - q) / 2;
+        lo = orr < lo ? orr : lo;
+        lo = oq < lo ? oq : lo;
+      }
+      CUtensorMap ta;
+      if (int rc = make_tmap_im2col_bf16(&ta, dy, s.cout, s.wo, s.ho, s.n, lo, lo, lo + Q.wm - s.wo, lo + Q.hm - s.ho, 1, BM))
+        return rc;
+      Q.a_mode = 2; Q.i2c_stride = 1; Q.i2c_lo = lo;
+      if (int rc = DISPATCH_BN(bn, false, false, tm, Q, m_tiles, 1, st, &ta)) return rc;
+      continue;
+    }
     if (int rc = DISPATCH_BN(bn, false, false, tm, Q, m_tiles, 1, st)) return rc;
   }
   return DIRB200_OK;
