@@ -117,36 +117,23 @@ wgrad_reduce_all_kernel(const WgradReduceDesc* __restrict__ descs, float* __rest
     }
     return;
   }
-  // four consecutive k = four consecutive input channels of one (co, tap) (cin is a multiple of 64): 16-byte loads of
-  // the partials, four independent chains over the splits, 32-bit index arithmetic (a layer has < 2^31 weights)
-  const uint32_t ktot = (uint32_t)(d.kh * d.kw * d.cin);
-  const uint32_t total4 = ktot * (uint32_t)d.cout / 4u;
-  const uint32_t taps = (uint32_t)(d.kh * d.kw), cin = (uint32_t)d.cin;
-  const float4* part4 = reinterpret_cast<const float4*>(d.partial);
-  for (uint32_t i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < total4; i4 += gridDim.x * blockDim.x) {
-    const float4* p = part4 + i4;
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+  const int64_t ktot = (int64_t)d.kh * d.kw * d.cin;
+  const int64_t total = ktot * d.cout;
+  const int taps = d.kh * d.kw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float* p = d.partial + i;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four independent chains: the loads of a thread overlap
     int sp = 0;
     for (; sp + 4 <= d.splits; sp += 4) {
-      const float4 v0 = p[(size_t)sp * total4], v1 = p[(size_t)(sp + 1) * total4];
-      const float4 v2 = p[(size_t)(sp + 2) * total4], v3 = p[(size_t)(sp + 3) * total4];
-      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
-      a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
-      a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
-      a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+      a0 += p[(int64_t)sp * total];
+      a1 += p[(int64_t)(sp + 1) * total];
+      a2 += p[(int64_t)(sp + 2) * total];
+      a3 += p[(int64_t)(sp + 3) * total];
     }
-    for (; sp < d.splits; ++sp) {
-      const float4 v0 = p[(size_t)sp * total4];
-      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
-    }
-    const uint32_t i = i4 * 4u;
-    const uint32_t co = i / ktot, k = i - co * ktot;
-    const uint32_t t = k / cin, c = k - t * cin;
-    float* o = dw + ((size_t)co * cin + c) * taps + t;
-    o[0] += (a0.x + a1.x) + (a2.x + a3.x);
-    o[taps] += (a0.y + a1.y) + (a2.y + a3.y);
-    o[2 * taps] += (a0.z + a1.z) + (a2.z + a3.z);
-    o[3 * taps] += (a0.w + a1.w) + (a2.w + a3.w);
+    for (; sp < d.splits; ++sp) a0 += p[(int64_t)sp * total];
+    const int64_t co = i / ktot, k = i - co * ktot;
+    const int c = (int)(k % d.cin), t = (int)(k / d.cin);
+    dw[(co * d.cin + c) * taps + t] += (a0 + a1) + (a2 + a3);
   }
 }
 
