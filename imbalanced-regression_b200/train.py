@@ -31,7 +31,7 @@ from torch.utils.data import DataLoader, Dataset
 from resnet import resnet50
 from loss import *  # noqa: F401,F403  (looked up by name, as the reference does at train.py:255)
 from datasets import AgeDB, IMDBWIKI, lds_prepare_weights
-from utils import AverageMeter, ProgressMeter, adjust_learning_rate, prepare_folders, save_checkpoint
+from utils import AverageMeter, ProgressMeter, adjust_learning_rate, nvtx_range, prepare_folders, save_checkpoint
 from optim import FusedAdam, FusedSGD
 from parallel import DataParallel, ShardSampler, is_distributed
 
@@ -145,14 +145,18 @@ def train(train_loader, model, optimizer, epoch, args, stats_loader=None):
     for idx, (inputs, targets, weights) in enumerate(train_loader):
         data_time.update(time.time() - end)
         inputs, targets, weights = (t.cuda(non_blocking=True) for t in (inputs, targets, weights))
-        outputs = model(inputs, targets, epoch)
-        if args.fds:
-            outputs, _ = outputs
-        loss = loss_fn(outputs, targets, weights)
+        with nvtx_range("dirb200/forward"):
+            outputs = model(inputs, targets, epoch)
+            if args.fds:
+                outputs, _ = outputs
+            loss = loss_fn(outputs, targets, weights)
         optimizer.zero_grad()
-        loss.backward()
-        model.reduce_gradients()
-        optimizer.step()
+        with nvtx_range("dirb200/backward"):
+            loss.backward()
+        with nvtx_range("dirb200/grad_allreduce"):
+            model.reduce_gradients()
+        with nvtx_range("dirb200/optimizer"):
+            optimizer.step()
         if idx % args.print_freq == 0:            # the only host sync of the loop (reference: every step)
             value = loss.item()
             assert not (np.isnan(value) or value > 1e6), f"Loss explosion: {value}"
@@ -171,7 +175,7 @@ def train(train_loader, model, optimizer, epoch, args, stats_loader=None):
         fds = model.module.FDS
         loader = stats_loader if stats_loader is not None else train_loader
         fds.begin_epoch_stats(torch.as_tensor(_label_column(loader), dtype=torch.float32).cuda())
-        with torch.no_grad():
+        with torch.no_grad(), nvtx_range("dirb200/fds_collection_pass"):
             for (inputs, targets, _) in loader:
                 targets = targets.cuda(non_blocking=True)
                 _, feature = model(inputs.cuda(non_blocking=True), targets, epoch)

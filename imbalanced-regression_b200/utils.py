@@ -93,3 +93,27 @@ def get_lds_kernel_window(kernel, ks, sigma):
         return triang(ks)
     taps = np.asarray([np.exp(-abs(x) / sigma) / (2. * sigma) for x in np.arange(-half_ks, half_ks + 1)])
     return taps / max(taps)
+
+
+class nvtx_range:
+    """NVTX range around a phase of the step (tracing), visible in nsys / ncu timelines.  Active only with
+    DIRB200_NVTX=1 (torch.cuda.nvtx.range_push / range_pop cost a few microseconds of host time each)."""
+    _on = None
+
+    def __init__(self, name):
+        self.name = name
+        if nvtx_range._on is None:
+            import os
+            nvtx_range._on = os.environ.get("DIRB200_NVTX") == "1"
+
+    def __enter__(self):
+        if nvtx_range._on:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if nvtx_range._on:
+            import torch
+            torch.cuda.nvtx.range_pop()
+        return False
