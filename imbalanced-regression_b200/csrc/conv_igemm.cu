@@ -1338,7 +1338,8 @@ static bool is_plain_gemm(const ConvShape& s, bool stem) {
   return !stem && s.kh == 1 && s.kw == 1 && s.stride == 1 && s.pad == 0 && atma_enabled();
 }
 // Every other non-stem conv (3x3, strided) takes its A operand through im2col-mode TMA (fprop, stride-1 dgrad, wgrad);
-// the stride-2 dgrad parity classes and the stem keep the cp.async gather.  DIRB200_IM2COL=0: gather for those too.
+// (incl. the parity classes of a stride-2 dgrad); only the stem keeps the cp.async gather.  DIRB200_IM2COL=0: gather
+// for all of those.
 static bool im2col_enabled() {
   static const bool on = [] {
     const char* e = getenv("DIRB200_IM2COL");
