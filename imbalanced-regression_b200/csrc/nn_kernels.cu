@@ -606,9 +606,11 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, i
 // the stored argmax, so nothing downstream reads it (saves 411 MB written + read at batch 256).  Values are rounded to
 // bf16 before they are compared, i.e. exactly what pooling the stored activation gave; idx = r*3+s of the first maximum.
 // A thread owns a 2x2 block of OUTPUT pixels x 8 channels: the 5x5 input patch they cover is loaded once (6.25 loads and
-// BN+ReLU evaluations per output instead of 9) row by row -- five 16-byte loads in flight, then the running maxima of
-// the (up to) two output rows x two output columns that contain the row are updated in (r, s) order, which keeps the
-// first-maximum tie rule.
+// BN+ReLU evaluations per output instead of 9) row by row -- five 16-byte loads in flight.  Running maximum AND argmax
+// of a window live in ONE integer per channel: key = (bf16 bits of the activation << 4) | (15 - pos).  Activations are
+// >= 0 after the ReLU, so their bf16 bit patterns order like the values, and on equal values the smaller filter position
+// wins (PyTorch's first-maximum rule); an update is one OR + one integer max instead of a compare, a select and a
+// byte insert (the kernel was ALU-bound on those).
 __global__ void __launch_bounds__(256)
 bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                            const float* __restrict__ shift, int n, int h, int w, int c,
@@ -623,14 +625,11 @@ bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __r
     const int yb = (int)(t % hb);
     const int b = (int)(t / hb);
     const V8 sc = loadf8(scale + g * 8), sh = loadf8(shift + g * 8);
-    float best[4][8];                    // [oy * 2 + ox]
-    uint32_t bi[4][2];                   // argmax r*3+s, one byte per channel
+    uint32_t best[4][8];                 // [oy * 2 + ox][channel]: (bf16 bits << 4) | (15 - pos)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) best[k][j] = -INFINITY;
-      bi[k][0] = bi[k][1] = 0u;
-    }
+      for (int j = 0; j < 8; ++j) best[k][j] = 0u;
     const int y0 = 4 * yb - 1, x0 = 4 * xb - 1;     // first input row / column of the 5x5 patch
 #pragma unroll
     for (int ry = 0; ry < 5; ++ry) {
@@ -649,14 +648,14 @@ bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __r
         const int xi = x0 + cx;
         if (xi < 0 || xi >= w) continue;
         const uint32_t yw[4] = {v[cx].x, v[cx].y, v[cx].z, v[cx].w};
-        float a[8];
+        uint32_t kb[8];                  // bf16 bits of relu(bn(y)) << 4
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           const float2 yv = bf2_to_f2(yw[p]);
-          const float2 r2 = bf2_to_f2(f2_to_bf2(fmaxf(fmaf(yv.x, sc.v[2 * p], sh.v[2 * p]), 0.f),
-                                                fmaxf(fmaf(yv.y, sc.v[2 * p + 1], sh.v[2 * p + 1]), 0.f)));
-          a[2 * p] = r2.x;
-          a[2 * p + 1] = r2.y;
+          const uint32_t pk = f2_to_bf2(fmaxf(fmaf(yv.x, sc.v[2 * p], sh.v[2 * p]), 0.f),
+                                        fmaxf(fmaf(yv.y, sc.v[2 * p + 1], sh.v[2 * p + 1]), 0.f));
+          kb[2 * p] = (pk & 0x7fffu) << 4;                  // (sign bit dropped: a ReLU output of -0 counts as 0)
+          kb[2 * p + 1] = (pk >> 12) & 0x7fff0u;
         }
 #pragma unroll
         for (int oy = 0; oy < 2; ++oy) {
@@ -666,14 +665,10 @@ bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __r
           for (int ox = 0; ox < 2; ++ox) {
             const int q = cx - 2 * ox;
             if (q < 0 || q > 2) continue;
-            const uint32_t pos = (uint32_t)(r * 3 + q);
+            const uint32_t tie = 15u - (uint32_t)(r * 3 + q);
             const int k = oy * 2 + ox;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (a[j] > best[k][j]) {
-                best[k][j] = a[j];
-                bi[k][j >> 2] = (bi[k][j >> 2] & ~(0xffu << (8 * (j & 3)))) | (pos << (8 * (j & 3)));
-              }
+            for (int j = 0; j < 8; ++j) best[k][j] = max(best[k][j], kb[j] | tie);
           }
         }
       }
@@ -684,12 +679,15 @@ bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __r
       for (int ox = 0; ox < 2; ++ox) {
         const int yo = 2 * yb + oy, xo = 2 * xb + ox;
         if (yo >= ho || xo >= wo) continue;
-        V8 o;
+        const uint32_t* bk = best[oy * 2 + ox];
+        uint32_t ow[4], iw[2] = {0u, 0u};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o.v[j] = best[oy * 2 + ox][j];
+        for (int p = 0; p < 4; ++p) ow[p] = (bk[2 * p] >> 4) | ((bk[2 * p + 1] >> 4) << 16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) iw[j >> 2] |= (15u - (bk[j] & 15u)) << (8 * (j & 3));
         const int64_t off = (((int64_t)b * ho + yo) * wo + xo) * c + g * 8;
-        store8(out + off, o);
-        *reinterpret_cast<uint2*>(idx + off) = make_uint2(bi[oy * 2 + ox][0], bi[oy * 2 + ox][1]);
+        *reinterpret_cast<uint4*>(out + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        *reinterpret_cast<uint2*>(idx + off) = make_uint2(iw[0], iw[1]);
       }
   }
 }
