@@ -13,4 +13,5 @@ _lib.register({
     "dirb200_conv_dgrad": (c_int, [P, P, P] + _I9 + [P]),
     "dirb200_conv_wgrad_workspace_bytes": (c_size_t, _I9 + [c_int]),
     "dirb200_conv_wgrad": (c_int, [P, P, P, P, c_size_t] + _I9 + [c_int, c_int, P]),
+    "dirb200_conv_plan": (c_int, _I9 + [c_int, c_int, P]),
 })

@@ -72,6 +72,7 @@ inline PrepDesc make_prep_desc(size_t w_off, int cout, int cin, int kh, int kw, 
   d.fd_taps = make_fastdiv((uint32_t)(kh * kw));
   return d;
 }
+int conv_plan(const ConvShape& s, bool stem, int op, int* plan);   // host-only: the GEMM form a conv would get
 int prep_weights_all(const float* params, const PrepDesc* descs_dev, int nlayers, cudaStream_t st);
 int prep_weights(const float* w, int cout, int cin, int kh, int kw, bool stem, __nv_bfloat16* wf, __nv_bfloat16* wd,
                  cudaStream_t st);

@@ -309,4 +309,16 @@ int dirb200_conv_wgrad(const void* x, const void* dy, float* dw, void* workspace
                     accumulate != 0, as_stream(stream));
 }
 
+/* Host-only (no CUDA call): the GEMM form dirb200_conv_fprop / _dgrad / _wgrad (op 0 / 1 / 2) would launch for this
+ * shape: plan7[0] tile width BN, [1] CTA pairs, [2] A-operand form (0 cp.async gather, 1 tiled TMA, 2 im2col TMA, 3
+ * patch-resident), [3] image rows per tile of the patch form, [4] split-K factor, [5] launches, [6] dgrad can carry the
+ * BN-backward moments of the previous layer. */
+int dirb200_conv_plan(int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad, int stem, int op,
+                      int* plan7) {
+  DIRB_CHECK_ARG(plan7 && op >= 0 && op <= 2, "conv_plan: bad arguments");
+  ConvShape s;
+  if (int rc = to_shape(n, h, w, cin, cout, kh, kw, stride, pad, stem, &s)) return rc;
+  return conv_plan(s, stem != 0, op, plan7);
+}
+
 }  // extern "C"

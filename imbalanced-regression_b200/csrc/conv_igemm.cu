@@ -1704,4 +1704,64 @@ int conv_wgrad_partials(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
   return DISPATCH_BN(bn, true, false, tm, P, m_tiles, splits, st);
 }
 
+// Host-only description of the launch a conv would get (no CUDA call): which tile width, operand feeding form, CTA pairs
+// and split-K factor the selection logic above picks.  op: 0 fprop, 1 dgrad, 2 wgrad.
+// plan[0] = BN, plan[1] = 1 if CTA pairs, plan[2] = A-operand form (0 cp.async gather, 1 tiled TMA, 2 im2col TMA,
+// 3 patch-resident), plan[3] = rows per tile of the patch form (else 0), plan[4] = split-K factor (wgrad; else 1),
+// plan[5] = launches (stride-2 dgrad: one per non-empty parity class), plan[6] = 1 if the dgrad can carry the BN-backward
+// moments of the previous layer.
+int conv_plan(const ConvShape& s, bool stem, int op, int* plan) {
+  for (int i = 0; i < 7; ++i) plan[i] = 0;
+  plan[4] = plan[5] = 1;
+  if (int rc = check_shape(s, stem, "conv_plan")) return rc;
+  if (op == 2) {
+    plan[0] = wgrad_bn(s);
+    plan[4] = conv_wgrad_splits(s);
+    if (!stem && patch_rows(s.h, s.w, s.cin, s.kh, s.kw, s.stride, s.pad, s.cout)) {
+      plan[0] = 64; plan[2] = 3; plan[3] = patch_rows(s.h, s.w, s.cin, s.kh, s.kw, s.stride, s.pad, s.cout);
+    } else if (stem) {
+      plan[2] = 0;
+    } else {
+      plan[2] = is_plain_gemm(s, stem) ? 1 : (im2col_enabled() ? 2 : 0);
+    }
+    return DIRB200_OK;
+  }
+  const bool dgrad = op == 1;
+  DIRB_CHECK_ARG(!(dgrad && stem), "conv_plan: the stem has no data gradient");
+  const int n_dim = dgrad ? s.cin : s.cout, k_ch = dgrad ? s.cout : s.cin;
+  if (dgrad && s.stride == 2) {
+    int launches = 0, bn = 64;
+    for (int cls = 0; cls < 4; ++cls) {
+      const int py = cls >> 1, px = cls & 1;
+      int nt = 0;
+      for (int r = 0; r < s.kh; ++r)
+        for (int q = 0; q < s.kw; ++q)
+          if (((py + s.pad - r) & 1) == 0 && ((px + s.pad - q) & 1) == 0) ++nt;
+      const int hm = (s.h - py + 1) / 2, wm = (s.w - px + 1) / 2;
+      if (nt == 0 || hm <= 0 || wm <= 0) continue;
+      ++launches;
+      const long long pixels = static_cast<long long>(s.n) * hm * wm;
+      bn = pick_bn(s.cin, (pixels + BM - 1) / BM, true);
+    }
+    plan[0] = bn; plan[2] = im2col_enabled() ? 2 : 0; plan[5] = launches;
+    return DIRB200_OK;
+  }
+  const int gh = dgrad ? s.ho : s.h, gw = dgrad ? s.wo : s.w;
+  if (!stem) {
+    if (const int pr = patch_rows(gh, gw, k_ch, s.kh, s.kw, s.stride, s.pad, n_dim)) {
+      plan[0] = 64; plan[2] = 3; plan[3] = pr; plan[6] = dgrad && conv_dgrad_fuses_bn_moments(s);
+      return DIRB200_OK;
+    }
+  }
+  const long long pixels = dgrad ? static_cast<long long>(s.n) * s.h * s.w : static_cast<long long>(s.n) * s.ho * s.wo;
+  const long long m_tiles = (pixels + BM - 1) / BM;
+  const int bn = pick_bn(n_dim, m_tiles, !is_plain_gemm(s, stem));
+  const bool tma_fed = is_plain_gemm(s, stem) || (!stem && im2col_enabled() && (!dgrad || s.kh == s.kw));
+  plan[0] = bn;
+  plan[2] = stem ? 0 : (is_plain_gemm(s, stem) ? 1 : (tma_fed ? 2 : 0));
+  plan[1] = tma_fed && want_pairs(bn, s.kh * s.kw * k_ch / 64);
+  plan[6] = dgrad && conv_dgrad_fuses_bn_moments(s);
+  return DIRB200_OK;
+}
+
 }  // namespace dirb200

@@ -255,6 +255,14 @@ int dirb200_conv_fprop(const void* x, const void* w_fprop, void* y, int n, int h
 int dirb200_conv_dgrad(const void* dy, const void* w_dgrad, void* dx, int n, int h, int w, int cin,
                        int cout, int kh, int kw, int stride, int pad, void* stream);
 
+/* Host-only (no CUDA call, works without a device): which GEMM form the three entry points above / below would launch for
+ * a shape (op: 0 fprop, 1 dgrad, 2 wgrad).  plan7[0] tile width BN; [1] 1 = CTA pairs (cta_group::2); [2] A-operand form:
+ * 0 cp.async gather, 1 tiled TMA, 2 im2col-mode TMA, 3 patch-resident (one input patch in shared memory, taps as
+ * displaced descriptors); [3] image rows per tile of the patch form; [4] split-K factor (wgrad); [5] launches (a stride-2
+ * dgrad runs one per non-empty output-pixel parity class); [6] 1 = this dgrad can also accumulate the BN-backward
+ * moments of the previous layer in its epilogue. */
+int dirb200_conv_plan(int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad, int stem, int op,
+                      int* plan7);
 size_t dirb200_conv_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout, int kh, int kw,
                                           int stride, int pad, int stem);
 

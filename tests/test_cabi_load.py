@@ -81,3 +81,44 @@ def test_wgrad_split_search_never_leaves_a_straggler_wave():
         assert fill >= 0.85, (hh, cin, cout, k, s, splits, items)
         assert kblocks // splits >= 8
     assert worst >= 0.85
+
+
+def test_conv_plan_selects_the_intended_gemm_forms():
+    """Host-only selection logic of the conv stage (dirb200_conv_plan; no device needed): the batch-256 ResNet-50 shapes
+    get the forms DESIGN.md section 4.1 describes."""
+    import ctypes
+    import _lib, _convlib  # noqa: F401
+
+    def plan(h, cin, cout, k, s, p, op, stem=0, hw_in=None):
+        a = (ctypes.c_int * 7)()
+        hh = hw_in or h
+        rc = _lib.raw("dirb200_conv_plan")(256, hh, hh, cin, cout, k, k, s, p, stem, op, a)
+        assert rc == 0, _lib.last_error()
+        return dict(zip(("bn", "pairs", "feed", "patch_rows", "splits", "launches", "bn_moments"), a))
+
+    GATHER, TILED, IM2COL, PATCH = 0, 1, 2, 3
+    # layer1 conv2 (64 -> 64 3x3 at 56x56): patch-resident in all three passes, 2 padded rows per tile, one partial per CTA
+    for op in (0, 1, 2):
+        q = plan(56, 64, 64, 3, 1, 1, op)
+        assert (q["feed"], q["patch_rows"], q["bn"]) == (PATCH, 2, 64), q
+    assert plan(56, 64, 64, 3, 1, 1, 2)["splits"] == 148 and plan(56, 64, 64, 3, 1, 1, 1)["bn_moments"] == 1
+    # 1x1 stride-1 GEMMs: tiled TMA; K-heavy 256-wide ones as CTA pairs
+    assert plan(56, 64, 256, 1, 1, 0, 0) == dict(bn=256, pairs=0, feed=TILED, patch_rows=0, splits=1, launches=1, bn_moments=0)
+    q = plan(14, 256, 1024, 1, 1, 0, 0)
+    assert (q["bn"], q["pairs"], q["feed"]) == (256, 1, TILED)
+    q = plan(7, 2048, 512, 1, 1, 0, 1)                   # dgrad: N = Cin = 2048 -> 256-wide pair tiles, carries BN moments
+    assert (q["bn"], q["pairs"], q["bn_moments"]) == (256, 1, 1)
+    # 3x3 layers: im2col TMA; pairs from layer3 on; stride-2 dgrad = 4 TMA-fed parity-class launches, no BN moments
+    q = plan(28, 128, 128, 3, 1, 1, 0)
+    assert (q["bn"], q["pairs"], q["feed"]) == (128, 0, IM2COL)
+    q = plan(14, 256, 256, 3, 1, 1, 0)
+    assert (q["bn"], q["pairs"], q["feed"]) == (256, 1, IM2COL)
+    q = plan(56, 128, 128, 3, 2, 1, 1)
+    assert (q["feed"], q["launches"], q["bn_moments"]) == (IM2COL, 4, 0)
+    q = plan(56, 256, 512, 1, 2, 0, 1)                   # 1x1 stride-2 downsample: only the (even, even) class has a tap
+    assert q["launches"] == 1
+    # wgrad never runs as pairs; every split keeps work (checked in detail by the test above)
+    assert plan(14, 256, 256, 3, 1, 1, 2)["pairs"] == 0
+    # 5x5 (NYUD2 refinement conv) goes through im2col TMA as well; the stem keeps the cp.async gather
+    assert plan(240, 128, 128, 5, 1, 2, 0)["feed"] == IM2COL
+    assert plan(224, 3, 64, 7, 2, 3, 0, stem=1)["feed"] == GATHER
