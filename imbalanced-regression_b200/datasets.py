@@ -68,7 +68,10 @@ class AgeDB(data.Dataset):
     label_column = 'age'
 
     def __init__(self, df, data_dir, img_size, split='train', reweight='none',
-                 lds=False, lds_kernel='gaussian', lds_ks=5, lds_sigma=2):
+                 lds=False, lds_kernel='gaussian', lds_ks=5, lds_sigma=2, device_transform=False):
+        # device_transform (not in the reference): __getitem__ stops after the resize and returns the uint8 HWC image;
+        # the rest of get_transform() runs on the GPU for the whole batch (gpu_transform_batch below)
+        self.device_transform = device_transform
         self.df = df
         self.data_dir = data_dir
         self.img_size = img_size
@@ -85,7 +88,11 @@ class AgeDB(data.Dataset):
         index = index % len(self.df)
         row = self.df.iloc[index]
         img = Image.open(os.path.join(self.data_dir, row['path'])).convert('RGB')
-        img = self.get_transform()(img)
+        if self.device_transform:
+            from torchvision import transforms
+            img = torch.from_numpy(np.asarray(transforms.Resize((self.img_size, self.img_size))(img)).copy())
+        else:
+            img = self.get_transform()(img)
         label = np.asarray([row[self.label_column]]).astype('float32')
         weight = np.asarray([self.weights[index]]).astype('float32') if self.weights is not None else \
             np.asarray([np.float32(1.)])

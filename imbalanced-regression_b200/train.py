@@ -30,7 +30,7 @@ from torch.utils.data import DataLoader, Dataset
 
 from resnet import resnet50
 from loss import *  # noqa: F401,F403  (looked up by name, as the reference does at train.py:255)
-from datasets import AgeDB, IMDBWIKI, lds_prepare_weights
+from datasets import AgeDB, IMDBWIKI, gpu_transform_batch, lds_prepare_weights
 from utils import AverageMeter, ProgressMeter, adjust_learning_rate, nvtx_range, prepare_folders, save_checkpoint
 from optim import FusedAdam, FusedSGD
 from parallel import DataParallel, ShardSampler, is_distributed
@@ -76,6 +76,9 @@ def build_parser():
     p.add_argument('--pretrained', type=str, default='')
     p.add_argument('--evaluate', action='store_true')
     p.add_argument('--synthetic', type=int, default=0, help='train on this many synthetic samples (no dataset needed)')
+    p.add_argument('--device_transform', action='store_true', default=False,
+                   help='(not a reference flag) the dataset yields the resized uint8 image; crop / flip / ToTensor / '
+                        'Normalize (datasets.py:38-53) run on the GPU for the whole batch (datasets.gpu_transform_batch)')
     return p
 
 
@@ -102,6 +105,7 @@ class SyntheticAges(Dataset):
     """N(0,1) images with an age-like skewed label column; weights from the GPU LDS path."""
 
     def __init__(self, n, img_size, args, seed=0, train=True):
+        self.device_transform = bool(getattr(args, 'device_transform', False))
         rng = np.random.RandomState(seed)
         self.labels = np.clip(np.round(rng.gamma(6.0, 6.5, size=n)), 0, 100).astype(np.float32)
         self.img_size, self.seed = img_size, seed
@@ -115,8 +119,11 @@ class SyntheticAges(Dataset):
     def __getitem__(self, i):
         g = torch.Generator().manual_seed(self.seed * 1000003 + i)
         w = np.float32(1.) if self.weights is None else self.weights[i]
-        return torch.randn(3, self.img_size, self.img_size, generator=g), np.asarray([self.labels[i]], np.float32), \
-            np.asarray([w], np.float32)
+        if self.device_transform:            # a "resized RGB image": uint8 HWC, transformed on the GPU per batch
+            img = torch.randint(0, 256, (self.img_size, self.img_size, 3), generator=g, dtype=torch.uint8)
+        else:
+            img = torch.randn(3, self.img_size, self.img_size, generator=g)
+        return img, np.asarray([self.labels[i]], np.float32), np.asarray([w], np.float32)
 
 
 def _label_column(loader):
@@ -145,6 +152,8 @@ def train(train_loader, model, optimizer, epoch, args, stats_loader=None):
     for idx, (inputs, targets, weights) in enumerate(train_loader):
         data_time.update(time.time() - end)
         inputs, targets, weights = (t.cuda(non_blocking=True) for t in (inputs, targets, weights))
+        if inputs.dtype == torch.uint8:           # --device_transform: RandomCrop(padding=16) / flip / ToTensor / Normalize
+            inputs = gpu_transform_batch(inputs, train=True)
         with nvtx_range("dirb200/forward"):
             outputs = model(inputs, targets, epoch)
             if args.fds:
@@ -178,7 +187,10 @@ def train(train_loader, model, optimizer, epoch, args, stats_loader=None):
         with torch.no_grad(), nvtx_range("dirb200/fds_collection_pass"):
             for (inputs, targets, _) in loader:
                 targets = targets.cuda(non_blocking=True)
-                _, feature = model(inputs.cuda(non_blocking=True), targets, epoch)
+                inputs = inputs.cuda(non_blocking=True)
+                if inputs.dtype == torch.uint8:   # the collection pass iterates the TRAIN loader: its transform
+                    inputs = gpu_transform_batch(inputs, train=True)
+                _, feature = model(inputs, targets, epoch)
                 fds.accumulate_batch(feature, targets)
         fds.update_last_epoch_stats(epoch)
         if epoch >= fds._epoch_host:            # gate of update_running_stats (fds.py:85), evaluated after the update
@@ -226,6 +238,8 @@ def validate(val_loader, model, train_labels=None, prefix='Val'):
     with torch.no_grad():
         for (inputs, targets, _) in val_loader:
             inputs, targets = inputs.cuda(non_blocking=True), targets.cuda(non_blocking=True)
+            if inputs.dtype == torch.uint8:       # --device_transform: the val / test chain (ToTensor + Normalize)
+                inputs = gpu_transform_batch(inputs, train=False)
             preds.append(model(inputs).reshape(-1).float())
             labels.append(targets.reshape(-1).float())
     if not preds:
@@ -273,11 +287,12 @@ def main(argv=None):
         df = pd.read_csv(os.path.join(args.data_dir, f"{args.dataset}.csv"))
         cls = AgeDB if args.dataset == 'agedb' else IMDBWIKI
         parts = {s: df[df['split'] == s] for s in ('train', 'val', 'test')}
+        dt = dict(device_transform=args.device_transform)
         train_dataset = cls(data_dir=args.data_dir, df=parts['train'], img_size=args.img_size, split='train',
                             reweight=args.reweight, lds=args.lds, lds_kernel=args.lds_kernel, lds_ks=args.lds_ks,
-                            lds_sigma=args.lds_sigma)
-        val_dataset = cls(data_dir=args.data_dir, df=parts['val'], img_size=args.img_size, split='val')
-        test_dataset = cls(data_dir=args.data_dir, df=parts['test'], img_size=args.img_size, split='test')
+                            lds_sigma=args.lds_sigma, **dt)
+        val_dataset = cls(data_dir=args.data_dir, df=parts['val'], img_size=args.img_size, split='val', **dt)
+        test_dataset = cls(data_dir=args.data_dir, df=parts['test'], img_size=args.img_size, split='test', **dt)
     mk = lambda ds, sampler: DataLoader(ds, batch_size=args.batch_size, sampler=sampler, shuffle=False,
                                         num_workers=args.workers, pin_memory=True, drop_last=False)
     n_train = len(train_dataset)

@@ -1,6 +1,7 @@
 """train.py (the reference-shaped driver) end to end on synthetic data: 3 tiny epochs with FDS + LDS, i.e. the
 whole state machine -- epoch 0 collect, epoch 1 smooth with identity tables, epoch 2 live calibration -- plus
-checkpoint writing and the validation pass."""
+checkpoint writing and the validation pass; once with the datasets' float tensors and once with --device_transform (uint8
+images, RandomCrop / flip / ToTensor / Normalize on the GPU per batch)."""
 import os
 import pytest
 import torch
@@ -8,9 +9,10 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_train_script_runs_three_epochs(tmp_path):
+@pytest.mark.parametrize("extra", [[], ["--device_transform"]], ids=["host_tensors", "device_transform"])
+def test_train_script_runs_three_epochs(tmp_path, extra):
     import train
-    argv = ["--synthetic", "192", "--batch_size", "64", "--epoch", "3", "--fds", "--lds", "--reweight", "sqrt_inv",
+    argv = extra + ["--synthetic", "192", "--batch_size", "64", "--epoch", "3", "--fds", "--lds", "--reweight", "sqrt_inv",
             "--lds_ks", "5", "--lds_sigma", "2", "--fds_ks", "5", "--fds_sigma", "2", "--bucket_num", "101",
             "--bucket_start", "0", "--workers", "0", "--img_size", "64", "--print_freq", "1",
             "--store_root", str(tmp_path), "--lr", "1e-4"]
