@@ -34,8 +34,10 @@ def lds_prepare_weights(labels, reweight, max_target=121, lds=False, lds_kernel=
     assert reweight in {'none', 'inverse', 'sqrt_inv'}
     assert reweight != 'none' if lds else True, \
         "Set reweight to 'sqrt_inv' (default) or 'inverse' when using LDS"
+    if reweight == 'none' and not return_hist:       # the reference returns None before counting anything (datasets.py:59)
+        return None
     device = device or torch.device('cuda')
-    lab = torch.as_tensor(np.asarray(labels), dtype=torch.float32).reshape(-1).to(device).contiguous()
+    lab = torch.as_tensor(np.array(labels, dtype=np.float32)).reshape(-1).to(device).contiguous()
     n = lab.numel()
     hist = torch.zeros(max_target, dtype=torch.int64, device=device)
     st = _lib.stream_ptr()
